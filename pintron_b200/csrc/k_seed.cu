@@ -1,0 +1,285 @@
+// k_seed.cu — genome k-mer index, maximal-pairing discovery (seed-and-extend) and the genome LCS scan.
+//
+// Index (replaces the Ukkonen suffix tree, reference stree_src/lst_stree.c:816 + src/aug_suffix_tree.c:151-264):
+// a 64-bit hash of every `word`-byte window of the genome, radix-sorted with the window start as payload, so
+// that all occurrences of a word are one contiguous, position-ascending run.  Words are hashed as BYTES
+// (the reference matches literal bytes: 'N' equals 'N', case matters, the mask characters '*' and '#'
+// never occur in a genome), and every hit is re-verified by the byte-wise extension, so hash collisions cost
+// time, never correctness.
+#include "pc_device.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace {
+
+__device__ __forceinline__ unsigned long long hash_word(const uint8_t *p, int word) {
+  unsigned long long h = 0xcbf29ce484222325ull;
+  for (int i = 0; i < word; ++i) { h ^= p[i]; h *= 0x100000001b3ull; }
+  return h;
+}
+
+__global__ void k_hash_windows(const uint8_t *g, uint32_t n_win, int word, unsigned long long *keys, uint32_t *pos) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_win; t += gridDim.x * blockDim.x) {
+    keys[t] = hash_word(g + t, word);
+    pos[t] = t;
+  }
+}
+
+__device__ __forceinline__ uint32_t lower_bound(const unsigned long long *keys, uint32_t n, unsigned long long h) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (keys[mid] < h) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ int lcp(const uint8_t *P, int n, int p, const uint8_t *T, uint32_t G, uint32_t t) {
+  const int lim = min(n - p, (int)(G - t));
+  int l = 0;
+  while (l < lim && P[p + l] == T[t + l]) ++l;
+  return l;
+}
+
+// exclusive scan of v[0..n) in place by one warp; returns the total
+__device__ int warp_exscan(int *v, int n, int lane) {
+  int carry = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const int x = i < n ? v[i] : 0;
+    int inc = x;
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (i < n) v[i] = carry + inc - x;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  return carry;
+}
+
+// ---- build_vertex_set (src/max-emb-graph.c:217-380), one warp per EST ------------------------------------
+// Spec = SURVEY.md Appendix A (validated against the reference on 4 259 MEG builds):
+//  per EST position p: the occurrences t of P[p..p+word) that are left-maximal (t==0 or p==0 or
+//  T[t-1]!=P[p-1]) and extend to l = LCP >= mfl; D = max l; keep l >= max(floor(D*rate), mfl);
+//  ascending t; filter A inside one p; filter B against the list of p-1; emit (p,t,l) by ascending p.
+struct TL { int t, l; };
+
+__device__ void seed_one(const PcDevBatch &B, int w, int lane) {
+  const uint32_t ji = B.idx[w];
+  const pc_job *job = B.jobs + ji;
+  int32_t *res = B.res + (size_t)ji * PC_RES_INTS;
+  const uint8_t *P = B.arena + job->a_off;
+  const int n = (int)job->a_len, mfl = job->p0, word = B.ix_word;
+  const uint8_t *T = B.genome;
+  const uint32_t G = B.genome_len;
+  int32_t *out = (int32_t *)(B.var_out + job->out_off);
+  if (mfl < word) { if (lane == 0) res[0] = PC_E_ARG; return; }
+  const int np = n - word + 1;               // positions that can start a word
+  if (np <= 0 || G < (uint32_t)word) { if (lane == 0) { res[0] = PC_OK; res[1] = 0; } return; }
+  // per-position arrays: bucket start, bucket end, D / offsets, counts
+  int *arr = (int *)pc_pool_alloc(B, 5ull * np * sizeof(int), lane);
+  if (!arr) { if (lane == 0) res[0] = PC_E_POOL; return; }
+  int *b_lo = arr, *b_hi = arr + np, *offs = arr + 2 * np, *cnt = arr + 3 * np, *thr_a = arr + 4 * np;
+  // S1: bucket, D(p), number of candidates >= mfl
+  for (int p = lane; p < np; p += 32) {
+    const unsigned long long h = hash_word(P + p, word);
+    uint32_t k = lower_bound(B.ix_keys, B.ix_n, h);
+    const uint32_t k0 = k;
+    int c = 0, D = 0;
+    const uint8_t prev = p > 0 ? P[p - 1] : 0;
+    for (; k < B.ix_n && B.ix_keys[k] == h; ++k) {
+      const uint32_t t = B.ix_pos[k];
+      if (p > 0 && t > 0 && T[t - 1] == prev) continue;
+      const int l = lcp(P, n, p, T, G, t);
+      if (l >= mfl) { ++c; D = max(D, l); }
+    }
+    b_lo[p] = (int)k0; b_hi[p] = (int)k;
+    int thr = (int)(size_t)((double)D * B.depth_rate);
+    thr_a[p] = max(thr, mfl);
+    offs[p] = c;
+  }
+  __syncwarp();
+  const int total = warp_exscan(offs, np, lane);
+  __syncwarp();
+  TL *cand = nullptr; uint8_t *keep = nullptr;
+  if (total > 0) {
+    cand = (TL *)pc_pool_alloc(B, (unsigned long long)total * (sizeof(TL) + 1), lane);
+    if (!cand) { if (lane == 0) res[0] = PC_E_POOL; return; }
+    keep = (uint8_t *)(cand + total);
+  }
+  // S2: emit candidates >= thr (ascending t), filter A in place
+  for (int p = lane; p < np; p += 32) {
+    TL *v = cand + offs[p];
+    const int thr = thr_a[p];
+    const uint8_t prev = p > 0 ? P[p - 1] : 0;
+    int c = 0;
+    for (int k = b_lo[p]; k < b_hi[p]; ++k) {
+      const uint32_t t = B.ix_pos[k];
+      if (p > 0 && t > 0 && T[t - 1] == prev) continue;
+      const int l = lcp(P, n, p, T, G, t);
+      if (l >= thr) { v[c].t = (int)t; v[c].l = l; ++c; }
+    }
+    // filter A is judged against the unfiltered list: mark first, compact after
+    uint8_t *kp = keep + offs[p];
+    for (int j = 0; j < c; ++j) {
+      bool drop = false;
+      for (int i = 0; i < j && !drop; ++i)
+        drop = (v[j].t > v[i].t && v[j].t + v[j].l <= v[i].t + v[i].l) || (v[j].t == v[i].t + 1 && v[j].l == v[i].l);
+      kp[j] = !drop;
+    }
+    int q = 0;
+    for (int j = 0; j < c; ++j) if (kp[j]) v[q++] = v[j];
+    cnt[p] = q;
+  }
+  __syncwarp();
+  // S3: filter B — list(p) against the post-A list(p-1); only flags are written, lists stay intact
+  int *outc = b_lo;                             // buckets are no longer needed
+  for (int p = lane; p < np; p += 32) {
+    const TL *v = cand + offs[p];
+    uint8_t *kp = keep + offs[p];
+    int q = 0;
+    for (int x = 0; x < cnt[p]; ++x) {
+      bool drop = false;
+      if (p > 0) {
+        const TL *u = cand + offs[p - 1];
+        for (int y = 0; y < cnt[p - 1] && !drop; ++y) drop = u[y].t == v[x].t && u[y].l >= v[x].l;
+      }
+      kp[x] = !drop; q += !drop;
+    }
+    outc[p] = q;
+  }
+  __syncwarp();
+  const int n_out = warp_exscan(outc, np, lane);
+  __syncwarp();
+  if ((uint32_t)n_out > job->out_cap) { if (lane == 0) { res[0] = PC_E_OUTCAP; res[1] = n_out; } return; }
+  for (int p = lane; p < np; p += 32) {
+    const TL *v = cand + offs[p];
+    const uint8_t *kp = keep + offs[p];
+    int o = outc[p];
+    for (int x = 0; x < cnt[p]; ++x)
+      if (kp[x]) { out[3 * o] = p; out[3 * o + 1] = v[x].t; out[3 * o + 2] = v[x].l; ++o; }
+  }
+  if (lane == 0) { res[0] = PC_OK; res[1] = n_out; }
+}
+
+__global__ void __launch_bounds__(128) k_seed(PcDevBatch B) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < B.n; w += nwarps) {
+    seed_one(B, w, lane);
+    __syncwarp();
+  }
+}
+
+// ---- find_longest_common_factor_dp (src/factorization-refinement.c:255-315) -------------------------------
+// s1 = b (long, usually a genome prefix), s2 = a (short EST piece).  A common run ending at (i1,i2) lives on
+// diagonal i1-i2; one thread walks one diagonal, a block stages its slice of s1 in shared memory.  The
+// reference keeps the FIRST strictly longer run in (i1 outer, i2 inner) order = max len, then min i1, then
+// min i2: packed so that one 64-bit atomicMax per block picks it.
+#define LCS_TPB 256
+#define LCS_MAX_S2 4096
+
+__device__ __forceinline__ unsigned long long lcs_key(int len, uint32_t i1, int i2) {
+  return ((unsigned long long)len << 48) | ((unsigned long long)(0xffffffffu - i1) << 16) |
+         (unsigned long long)(0xffffu - (uint32_t)i2);
+}
+
+__global__ void __launch_bounds__(LCS_TPB) k_lcs(PcDevBatch B, unsigned long long *best) {
+  const int w = blockIdx.y;
+  const uint32_t ji = B.idx[w];
+  const pc_job *job = B.jobs + ji;
+  const uint8_t *s2 = B.arena + job->a_off;
+  const int l2 = (int)job->a_len;
+  const uint8_t *s1 = ((job->flags & PC_B_IN_GENOME) ? B.genome : B.arena) + job->b_off;
+  const long long l1 = job->b_len;
+  if (l2 > LCS_MAX_S2) return;                              // reported by k_lcs_finish
+  // diagonals d = i1 - i2 in [-(l2-1), l1-1]; this block owns LCS_TPB consecutive ones
+  const long long d0 = (long long)blockIdx.x * LCS_TPB - (l2 - 1);
+  if (d0 > l1 - 1) return;
+  extern __shared__ uint8_t sh[];
+  uint8_t *t1 = sh;                 // s1[d0 .. d0 + LCS_TPB + l2 - 1)
+  uint8_t *t2 = sh + LCS_TPB + l2;  // s2
+  for (int i = threadIdx.x; i < LCS_TPB + l2 - 1; i += LCS_TPB) {
+    const long long g = d0 + i;
+    t1[i] = (g >= 0 && g < l1) ? s1[g] : 0;
+  }
+  for (int i = threadIdx.x; i < l2; i += LCS_TPB) t2[i] = s2[i];
+  __syncthreads();
+  const long long d = d0 + threadIdx.x;
+  unsigned long long key = 0;
+  if (d <= l1 - 1) {
+    int run = 0, bl = 0, bi2 = 0;
+    const int i2_lo = d < 0 ? (int)-d : 0;
+    for (int i2 = i2_lo; i2 < l2; ++i2) {
+      const long long i1 = d + i2;
+      if (i1 >= l1) break;
+      const uint8_t c1 = t1[threadIdx.x + i2], c2 = t2[i2];
+      run = (c1 == c2 || pc_is_n(c1) || pc_is_n(c2)) ? run + 1 : 0;
+      if (run > bl) { bl = run; bi2 = i2; }
+    }
+    if (bl > 0) key = lcs_key(bl, (uint32_t)(d + bi2), bi2);
+  }
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); key = max(key, k2); }
+  if ((threadIdx.x & 31) == 0 && key) atomicMax(best + w, key);
+}
+
+__global__ void k_lcs_finish(PcDevBatch B, const unsigned long long *best) {
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < B.n; w += gridDim.x * blockDim.x) {
+    const uint32_t ji = B.idx[w];
+    int32_t *res = B.res + (size_t)ji * PC_RES_INTS;
+    if (B.jobs[ji].a_len > LCS_MAX_S2) { res[0] = PC_E_RANGE; continue; }
+    const unsigned long long key = best[w];
+    const int len = (int)(key >> 48);
+    const uint32_t i1 = 0xffffffffu - (uint32_t)((key >> 16) & 0xffffffffu);
+    const int i2 = (int)(0xffffu - (uint32_t)(key & 0xffffu));
+    res[0] = PC_OK;
+    res[1] = len;
+    res[2] = len ? (int32_t)(i1 + 1 - (uint32_t)len) : 0;
+    res[3] = len ? i2 + 1 - len : 0;
+  }
+}
+
+}  // namespace
+
+void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count) {
+  const int ctas = (B.n + 3) / 4;
+  const int grid = ctas < sm_count * 8 ? ctas : sm_count * 8;
+  k_seed<<<grid, 128, 0, s>>>(B);
+  ++g_pc_launches;
+}
+
+// best: device array of B.n 64-bit slots (zeroed here); max_l1/max_l2 over the jobs of the batch
+int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, long long max_l1, int max_l2, cudaStream_t s) {
+  if (max_l2 > LCS_MAX_S2) max_l2 = LCS_MAX_S2;
+  cudaMemsetAsync(best, 0, sizeof(unsigned long long) * B.n, s);
+  const long long ndiag = max_l1 + max_l2;
+  const size_t sh = LCS_TPB + 2 * (size_t)max_l2 + 8;
+  for (int off = 0; off < B.n; off += 65535) {               // gridDim.y limit
+    PcDevBatch C = B;
+    C.idx = B.idx + off;
+    C.n = B.n - off < 65535 ? B.n - off : 65535;
+    dim3 grid((unsigned)((ndiag + LCS_TPB - 1) / LCS_TPB), (unsigned)C.n);
+    if (grid.x > 0) { k_lcs<<<grid, LCS_TPB, sh, s>>>(C, best + off); ++g_pc_launches; }
+  }
+  k_lcs_finish<<<(B.n + 127) / 128, 128, 0, s>>>(B, best);
+  ++g_pc_launches;
+  return 0;
+}
+
+int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned long long **keys_out, uint32_t **pos_out,
+                   uint32_t *n_out, cudaStream_t s) {
+  *keys_out = nullptr; *pos_out = nullptr; *n_out = 0;
+  if (len < (uint32_t)word) return 0;
+  const uint32_t n = len - word + 1;
+  unsigned long long *k_in, *k_out; uint32_t *p_in, *p_out;
+  if (cudaMalloc(&k_in, 8ull * n) || cudaMalloc(&k_out, 8ull * n) || cudaMalloc(&p_in, 4ull * n) || cudaMalloc(&p_out, 4ull * n))
+    return PC_E_NOMEM;
+  k_hash_windows<<<(n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048, 256, 0, s>>>(d_genome, n, word, k_in, p_in);
+  ++g_pc_launches;
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, 64, s);
+  void *tmp;
+  if (cudaMalloc(&tmp, tmp_bytes)) return PC_E_NOMEM;
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, 64, s);   // stable: equal keys keep ascending t
+  if (cudaStreamSynchronize(s) != cudaSuccess) return PC_E_CUDA;
+  cudaFree(tmp); cudaFree(k_in); cudaFree(p_in);
+  *keys_out = k_out; *pos_out = p_out; *n_out = n;
+  return 0;
+}

@@ -1,0 +1,384 @@
+// pc_api.cu — host side of the C ABI (include/pintron_cuda.h): contexts, streams, batch plumbing.
+#include "pc_device.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+unsigned long long g_pc_launches = 0;
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *detail = "") {
+  snprintf(g_err, sizeof g_err, fmt, detail);
+  return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(PC_E_CUDA, #call ": %s", cudaGetErrorString(e_)); } while (0)
+
+struct pc_ctx {
+  int device = 0, sm_count = 148;
+  uint8_t *d_genome = nullptr;
+  uint32_t genome_len = 0;
+  unsigned long long *ix_keys = nullptr;
+  uint32_t *ix_pos = nullptr;
+  uint32_t ix_n = 0;
+  int ix_word = 0;
+  double depth_rate = 0.2;
+};
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    size_t want = std::max(bytes, cap * 2);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cap = 0; return fail(PC_E_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Pending {          // what pc_stream_sync needs to re-run jobs that ran out of pool
+  bool active = false, device_mode = false;
+  const pc_job *jobs = nullptr;   // host copy
+  int njobs = 0;
+  int32_t *res = nullptr;         // host (or device in device_mode)
+  uint8_t *var_out = nullptr;
+  size_t var_out_bytes = 0;
+  const uint8_t *d_arena = nullptr;
+  const pc_job *d_jobs = nullptr;
+  int32_t *d_res = nullptr;
+  uint8_t *d_var = nullptr;
+};
+
+struct pc_stream {
+  pc_ctx *ctx = nullptr;
+  cudaStream_t s = nullptr;
+  DevBuf arena, jobs, idx, res, var, pool, lcs_best;
+  unsigned long long *d_pool_used = nullptr;
+  std::vector<uint32_t> h_idx;
+  std::vector<int32_t> h_status;
+  Pending pend;
+  bool timers = false;
+  double op_ms[PC_OP_COUNT] = {0};
+  uint64_t op_launches[PC_OP_COUNT] = {0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;
+  std::vector<cudaEvent_t> ev_free;
+};
+
+extern "C" const char *pc_last_error(void) { return g_err; }
+
+extern "C" int pc_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(PC_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+}
+
+extern "C" pc_ctx *pc_ctx_create(int device) {
+  int n = pc_device_count();
+  if (n <= 0) { if (n == 0) fail(PC_E_CUDA, "%s", "no CUDA device: libpintron_cuda has no CPU fallback"); return nullptr; }
+  if (device < 0 || device >= n) { fail(PC_E_ARG, "%s", "device index out of range"); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { fail(PC_E_CUDA, "%s", "cudaSetDevice failed"); return nullptr; }
+  pc_ctx *c = new pc_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  return c;
+}
+
+extern "C" void pc_ctx_destroy(pc_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_genome); cudaFree(c->ix_keys); cudaFree(c->ix_pos);
+  delete c;
+}
+
+extern "C" int pc_genome_upload(pc_ctx *c, const char *genome, size_t len, int word_len, double depth_rate) {
+  if (!c || !genome || word_len <= 0 || len >= 0xfffffff0ull) return fail(PC_E_ARG, "%s", "pc_genome_upload: bad argument");
+  CU(cudaSetDevice(c->device));
+  cudaFree(c->d_genome); cudaFree(c->ix_keys); cudaFree(c->ix_pos);
+  c->d_genome = nullptr; c->ix_keys = nullptr; c->ix_pos = nullptr;
+  CU(cudaMalloc(&c->d_genome, len + 16));
+  CU(cudaMemset(c->d_genome, 0, len + 16));
+  CU(cudaMemcpy(c->d_genome, genome, len, cudaMemcpyHostToDevice));
+  c->genome_len = (uint32_t)len;
+  c->ix_word = word_len;
+  c->depth_rate = depth_rate;
+  int rc = pc_build_index(c->d_genome, c->genome_len, word_len, &c->ix_keys, &c->ix_pos, &c->ix_n, 0);
+  if (rc) return fail(rc, "%s", "pc_genome_upload: index build failed");
+  CU(cudaDeviceSynchronize());
+  return 0;
+}
+
+extern "C" pc_stream *pc_stream_create(pc_ctx *c) {
+  if (!c) { fail(PC_E_ARG, "%s", "pc_stream_create: null context"); return nullptr; }
+  cudaSetDevice(c->device);
+  pc_stream *st = new pc_stream();
+  st->ctx = c;
+  if (cudaStreamCreateWithFlags(&st->s, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&st->d_pool_used, 8) != cudaSuccess) {
+    fail(PC_E_CUDA, "%s", "pc_stream_create: stream / counter allocation failed");
+    delete st;
+    return nullptr;
+  }
+  if (st->pool.reserve(64ull << 20)) { delete st; return nullptr; }
+  return st;
+}
+
+extern "C" void pc_stream_destroy(pc_stream *st) {
+  if (!st) return;
+  cudaSetDevice(st->ctx->device);
+  cudaStreamSynchronize(st->s);
+  for (DevBuf *b : {&st->arena, &st->jobs, &st->idx, &st->res, &st->var, &st->pool, &st->lcs_best}) b->release();
+  cudaFree(st->d_pool_used);
+  for (auto &e : st->ev_pending) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
+  for (auto e : st->ev_free) cudaEventDestroy(e);
+  cudaStreamDestroy(st->s);
+  delete st;
+}
+
+extern "C" void *pc_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { fail(PC_E_NOMEM, "%s", "cudaHostAlloc failed"); return nullptr; }
+  return p;
+}
+extern "C" void pc_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" uint64_t pc_launch_count(void) { return g_pc_launches; }
+extern "C" void *pc_stream_cuda_stream(pc_stream *st) { return st ? (void *)st->s : nullptr; }
+extern "C" void pc_stream_enable_timers(pc_stream *st, int on) { if (st) st->timers = on != 0; }
+
+static void drain_events(pc_stream *st) {
+  for (auto &e : st->ev_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e.second.first, e.second.second) == cudaSuccess) st->op_ms[e.first] += ms;
+    st->ev_free.push_back(e.second.first);
+    st->ev_free.push_back(e.second.second);
+  }
+  st->ev_pending.clear();
+}
+
+extern "C" void pc_stream_reset_timers(pc_stream *st) {
+  if (!st) return;
+  drain_events(st);
+  for (int i = 0; i < PC_OP_COUNT; ++i) { st->op_ms[i] = 0; st->op_launches[i] = 0; }
+}
+
+extern "C" int pc_stream_op_time(pc_stream *st, int op, double *ms, uint64_t *launches) {
+  if (!st || op < 0 || op >= PC_OP_COUNT) return fail(PC_E_ARG, "%s", "pc_stream_op_time: bad argument");
+  drain_events(st);
+  if (ms) *ms = st->op_ms[op];
+  if (launches) *launches = st->op_launches[op];
+  return 0;
+}
+
+static cudaEvent_t get_event(pc_stream *st) {
+  if (!st->ev_free.empty()) { cudaEvent_t e = st->ev_free.back(); st->ev_free.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+
+static double job_cost(const pc_job &j) {
+  switch (j.op) {
+    case PC_OP_LCS: case PC_OP_SEED: return (double)j.a_len + j.b_len;
+    default: return ((double)j.a_len + 1) * ((double)j.b_len + 1);
+  }
+}
+
+// Launch the kernels for the jobs whose indices are in `sel` (all of one batch already resident on device).
+static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vector<uint32_t> &sel, const uint8_t *d_arena,
+                           const pc_job *d_jobs, int32_t *d_res, uint8_t *d_var) {
+  pc_ctx *c = st->ctx;
+  // partition by op, heaviest first inside each op
+  std::vector<uint32_t> &order = st->h_idx;
+  order.assign(sel.begin(), sel.end());
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+    if (h_jobs[x].op != h_jobs[y].op) return h_jobs[x].op < h_jobs[y].op;
+    return job_cost(h_jobs[x]) > job_cost(h_jobs[y]);
+  });
+  if (st->idx.reserve(order.size() * 4 + 4)) return PC_E_NOMEM;
+  CU(cudaMemcpyAsync(st->idx.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, st->s));
+  CU(cudaMemsetAsync(st->d_pool_used, 0, 8, st->s));
+  PcDevBatch B;
+  B.arena = d_arena; B.genome = c->d_genome; B.genome_len = c->genome_len;
+  B.jobs = d_jobs; B.res = d_res; B.var_out = d_var;
+  B.pool = (uint8_t *)st->pool.p; B.pool_cap = st->pool.cap; B.pool_used = st->d_pool_used;
+  B.ix_keys = c->ix_keys; B.ix_pos = c->ix_pos; B.ix_n = c->ix_n; B.ix_word = c->ix_word; B.depth_rate = c->depth_rate;
+  size_t i = 0;
+  while (i < order.size()) {
+    const uint32_t op = h_jobs[order[i]].op;
+    size_t j = i;
+    long long max_l1 = 0; int max_l2 = 0;
+    while (j < order.size() && h_jobs[order[j]].op == op) {
+      max_l1 = std::max<long long>(max_l1, h_jobs[order[j]].b_len);
+      max_l2 = std::max<int>(max_l2, (int)h_jobs[order[j]].a_len);
+      ++j;
+    }
+    if (op >= PC_OP_COUNT) return fail(PC_E_ARG, "%s", "pc_submit: unknown op");
+    B.idx = (const uint32_t *)st->idx.p + i;
+    B.n = (int)(j - i);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (st->timers) { e0 = get_event(st); e1 = get_event(st); cudaEventRecord(e0, st->s); }
+    const unsigned long long before = g_pc_launches;
+    if (op == PC_OP_SEED) {
+      if (!c->d_genome) return fail(PC_E_ARG, "%s", "PC_OP_SEED before pc_genome_upload");
+      pc_launch_seed(B, st->s, c->sm_count);
+    } else if (op == PC_OP_LCS) {
+      if (st->lcs_best.reserve(8ull * B.n)) return PC_E_NOMEM;
+      pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, max_l1, max_l2, st->s);
+    } else {
+      pc_launch_dp((int)op, B, st->s, c->sm_count);
+    }
+    st->op_launches[op] += g_pc_launches - before;
+    if (st->timers) { cudaEventRecord(e1, st->s); st->ev_pending.push_back({(int)op, {e0, e1}}); }
+    i = j;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int check_jobs(pc_stream *st, const pc_job *jobs, int njobs, size_t arena_bytes, size_t var_out_bytes) {
+  const size_t glen = st->ctx->genome_len;
+  for (int i = 0; i < njobs; ++i) {
+    const pc_job &j = jobs[i];
+    if ((size_t)j.a_off + j.a_len > arena_bytes) return fail(PC_E_ARG, "%s", "pc_submit: job string a outside the arena");
+    if (j.op != PC_OP_SEED) {
+      const size_t lim = (j.flags & PC_B_IN_GENOME) ? glen : arena_bytes;
+      if ((size_t)j.b_off + j.b_len > lim) return fail(PC_E_ARG, "%s", "pc_submit: job string b out of range");
+    }
+    if (j.op == PC_OP_ALIGN || j.op == PC_OP_GAP) {
+      if ((size_t)j.out_off + j.out_cap > var_out_bytes) return fail(PC_E_ARG, "%s", "pc_submit: ops region outside var_out");
+    } else if (j.op == PC_OP_SEED) {
+      if ((j.out_off & 3u) || (size_t)j.out_off + 12ull * j.out_cap > var_out_bytes)
+        return fail(PC_E_ARG, "%s", "pc_submit: triples region misaligned or outside var_out");
+    }
+  }
+  return 0;
+}
+
+extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes, const pc_job *jobs, int njobs,
+                         int32_t *res, uint8_t *var_out, size_t var_out_bytes) {
+  if (!st || njobs < 0 || (njobs && (!jobs || !res))) return fail(PC_E_ARG, "%s", "pc_submit: bad argument");
+  if (st->pend.active) return fail(PC_E_ARG, "%s", "pc_submit: previous batch not synced");
+  if (njobs == 0) return 0;
+  CU(cudaSetDevice(st->ctx->device));
+  int rc = check_jobs(st, jobs, njobs, arena_bytes, var_out_bytes);
+  if (rc) return rc;
+  // one spare readable byte after the arena: general_refine_borders reads t[len_t] (refine.c:362-374 adaptor)
+  if (st->arena.reserve(arena_bytes + 16) || st->jobs.reserve(sizeof(pc_job) * (size_t)njobs) ||
+      st->res.reserve(sizeof(int32_t) * PC_RES_INTS * (size_t)njobs) || st->var.reserve(var_out_bytes + 16))
+    return PC_E_NOMEM;
+  if (arena_bytes) CU(cudaMemcpyAsync(st->arena.p, arena, arena_bytes, cudaMemcpyHostToDevice, st->s));
+  CU(cudaMemsetAsync((uint8_t *)st->arena.p + arena_bytes, 0, 16, st->s));
+  CU(cudaMemcpyAsync(st->jobs.p, jobs, sizeof(pc_job) * (size_t)njobs, cudaMemcpyHostToDevice, st->s));
+  std::vector<uint32_t> all((size_t)njobs);
+  for (int i = 0; i < njobs; ++i) all[i] = (uint32_t)i;
+  rc = launch_selected(st, jobs, all, (const uint8_t *)st->arena.p, (const pc_job *)st->jobs.p, (int32_t *)st->res.p,
+                       (uint8_t *)st->var.p);
+  if (rc) return rc;
+  Pending &P = st->pend;
+  P.active = true; P.device_mode = false; P.jobs = jobs; P.njobs = njobs; P.res = res; P.var_out = var_out;
+  P.var_out_bytes = var_out_bytes; P.d_arena = (const uint8_t *)st->arena.p; P.d_jobs = (const pc_job *)st->jobs.p;
+  P.d_res = (int32_t *)st->res.p; P.d_var = (uint8_t *)st->var.p;
+  CU(cudaMemcpyAsync(res, st->res.p, sizeof(int32_t) * PC_RES_INTS * (size_t)njobs, cudaMemcpyDeviceToHost, st->s));
+  if (var_out_bytes) CU(cudaMemcpyAsync(var_out, st->var.p, var_out_bytes, cudaMemcpyDeviceToHost, st->s));
+  return 0;
+}
+
+extern "C" int pc_submit_device(pc_stream *st, const uint8_t *d_arena, size_t arena_bytes, const pc_job *d_jobs,
+                                const pc_job *h_jobs, int njobs, int32_t *d_res, uint8_t *d_var_out, size_t var_out_bytes) {
+  if (!st || njobs < 0 || (njobs && (!d_jobs || !h_jobs || !d_res))) return fail(PC_E_ARG, "%s", "pc_submit_device: bad argument");
+  if (st->pend.active) return fail(PC_E_ARG, "%s", "pc_submit_device: previous batch not synced");
+  if (njobs == 0) return 0;
+  CU(cudaSetDevice(st->ctx->device));
+  int rc = check_jobs(st, h_jobs, njobs, arena_bytes, var_out_bytes);
+  if (rc) return rc;
+  std::vector<uint32_t> all((size_t)njobs);
+  for (int i = 0; i < njobs; ++i) all[i] = (uint32_t)i;
+  rc = launch_selected(st, h_jobs, all, d_arena, d_jobs, d_res, d_var_out);
+  if (rc) return rc;
+  Pending &P = st->pend;
+  P.active = true; P.device_mode = true; P.jobs = h_jobs; P.njobs = njobs; P.res = nullptr; P.var_out = nullptr;
+  P.var_out_bytes = var_out_bytes; P.d_arena = d_arena; P.d_jobs = d_jobs; P.d_res = d_res; P.d_var = d_var_out;
+  return 0;
+}
+
+extern "C" int pc_stream_sync(pc_stream *st) {
+  if (!st) return fail(PC_E_ARG, "%s", "pc_stream_sync: null stream");
+  CU(cudaSetDevice(st->ctx->device));
+  CU(cudaStreamSynchronize(st->s));
+  Pending &P = st->pend;
+  if (!P.active) return 0;
+  // Jobs that could not get scratch from the pool are re-run with a larger pool, a part at a time if needed.
+  for (int round = 0; round < 40; ++round) {
+    const int32_t *status = P.res;
+    if (P.device_mode) {
+      st->h_status.resize((size_t)P.njobs * PC_RES_INTS);
+      CU(cudaMemcpy(st->h_status.data(), P.d_res, sizeof(int32_t) * PC_RES_INTS * (size_t)P.njobs, cudaMemcpyDeviceToHost));
+      status = st->h_status.data();
+    }
+    std::vector<uint32_t> redo;
+    for (int i = 0; i < P.njobs; ++i) if (status[(size_t)i * PC_RES_INTS] == PC_E_POOL) redo.push_back((uint32_t)i);
+    if (redo.empty()) break;
+    if (round >= 1 || st->pool.cap < (1ull << 30)) {
+      size_t want = st->pool.cap * 4;
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      if (want > st->pool.cap + free_b / 2) want = st->pool.cap + free_b / 2;
+      if (want > st->pool.cap) { int rc = st->pool.reserve(want); if (rc) { P.active = false; return rc; } }
+      else if (redo.size() == 1) { P.active = false; return fail(PC_E_NOMEM, "%s", "a single job does not fit the device scratch pool"); }
+    }
+    if (round >= 2 && redo.size() > 1) redo.resize((redo.size() + 1) / 2);   // still too much at once: halve the wave
+    int rc = launch_selected(st, P.jobs, redo, P.d_arena, P.d_jobs, P.d_res, P.d_var);
+    if (rc) { P.active = false; return rc; }
+    if (!P.device_mode) {
+      CU(cudaMemcpyAsync(P.res, P.d_res, sizeof(int32_t) * PC_RES_INTS * (size_t)P.njobs, cudaMemcpyDeviceToHost, st->s));
+      if (P.var_out_bytes) CU(cudaMemcpyAsync(P.var_out, P.d_var, P.var_out_bytes, cudaMemcpyDeviceToHost, st->s));
+    }
+    CU(cudaStreamSynchronize(st->s));
+  }
+  P.active = false;
+  return 0;
+}
+
+// ---- per-routine entry points ------------------------------------------------------------------------------
+static int run_typed(pc_stream *st, uint32_t op_a, uint32_t op_b, const uint8_t *arena, size_t ab, const pc_job *jobs, int n,
+                     int32_t *res, uint8_t *var, size_t vb) {
+  for (int i = 0; i < n; ++i)
+    if (jobs[i].op != op_a && jobs[i].op != op_b) return fail(PC_E_ARG, "%s", "typed batch: job with a different op");
+  int rc = pc_submit(st, arena, ab, jobs, n, res, var, vb);
+  if (rc) return rc;
+  return pc_stream_sync(st);
+}
+
+extern "C" int pc_compute_alignment_batch(pc_stream *st, const uint8_t *a, size_t ab, const pc_job *j, int n, int32_t *r, uint8_t *ops, size_t ob) {
+  return run_typed(st, PC_OP_ALIGN, PC_OP_ALIGN, a, ab, j, n, r, ops, ob);
+}
+extern "C" int pc_kband_edit_distance_batch(pc_stream *st, const uint8_t *a, size_t ab, const pc_job *j, int n, int32_t *r) {
+  return run_typed(st, PC_OP_KBAND, PC_OP_KBAND, a, ab, j, n, r, nullptr, 0);
+}
+extern "C" int pc_edit_distance_batch(pc_stream *st, const uint8_t *a, size_t ab, const pc_job *j, int n, int32_t *r) {
+  return run_typed(st, PC_OP_EDIT, PC_OP_EDIT, a, ab, j, n, r, nullptr, 0);
+}
+extern "C" int pc_refine_borders_batch(pc_stream *st, const uint8_t *a, size_t ab, const pc_job *j, int n, int32_t *r) {
+  return run_typed(st, PC_OP_BORDERS, PC_OP_BORDERS, a, ab, j, n, r, nullptr, 0);
+}
+extern "C" int pc_gap_alignment_batch(pc_stream *st, const uint8_t *a, size_t ab, const pc_job *j, int n, int32_t *r, uint8_t *ops, size_t ob) {
+  return run_typed(st, PC_OP_GAP, PC_OP_GAP, a, ab, j, n, r, ops, ob);
+}
+extern "C" int pc_longest_affix_batch(pc_stream *st, const uint8_t *a, size_t ab, const pc_job *j, int n, int32_t *r) {
+  return run_typed(st, PC_OP_AFFIX, PC_OP_AFFIX, a, ab, j, n, r, nullptr, 0);
+}
+extern "C" int pc_best_cut_batch(pc_stream *st, const uint8_t *a, size_t ab, const pc_job *j, int n, int32_t *r) {
+  return run_typed(st, PC_OP_SUFCUT, PC_OP_PRECUT, a, ab, j, n, r, nullptr, 0);
+}
+extern "C" int pc_longest_common_factor_batch(pc_stream *st, const uint8_t *a, size_t ab, const pc_job *j, int n, int32_t *r) {
+  return run_typed(st, PC_OP_LCS, PC_OP_LCS, a, ab, j, n, r, nullptr, 0);
+}
+extern "C" int pc_build_vertex_set_batch(pc_stream *st, const uint8_t *a, size_t ab, const pc_job *j, int n, int32_t *r, uint8_t *tr, size_t tb) {
+  return run_typed(st, PC_OP_SEED, PC_OP_SEED, a, ab, j, n, r, tr, tb);
+}

@@ -1,0 +1,49 @@
+// pc_device.cuh — shared device-side declarations for libpintron_cuda (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pintron_cuda.h"
+
+#define PC_WARPS_PER_CTA 4
+#define PC_SMEM_INTS_PER_WARP 3072          /* 12 KB per warp of anti-diagonal state */
+#define PC_INF 0x3fffffffu
+
+struct PcDevBatch {
+  const uint8_t *arena;
+  const uint8_t *genome;
+  uint32_t genome_len;
+  const pc_job *jobs;
+  const uint32_t *idx;        /* job indices of this op, heaviest first */
+  int n;
+  int32_t *res;
+  uint8_t *var_out;
+  uint8_t *pool;              /* per-stream scratch pool, bump-allocated by the kernels */
+  unsigned long long pool_cap;
+  unsigned long long *pool_used;
+  /* k-mer index (SEED) */
+  const unsigned long long *ix_keys;
+  const uint32_t *ix_pos;
+  uint32_t ix_n;
+  int ix_word;
+  double depth_rate;
+};
+
+__device__ __forceinline__ uint8_t *pc_pool_alloc(const PcDevBatch &B, unsigned long long bytes, int lane) {
+  unsigned long long off = 0;
+  if (lane == 0) {
+    unsigned long long sz = (bytes + 255ull) & ~255ull;
+    off = atomicAdd(B.pool_used, sz);
+    if (off + sz > B.pool_cap) off = ~0ull;
+  }
+  off = __shfl_sync(0xffffffffu, off, 0);
+  return off == ~0ull ? nullptr : B.pool + off;
+}
+
+__device__ __forceinline__ bool pc_is_n(uint8_t c) { return c == 'n' || c == 'N'; }
+
+void pc_launch_dp(int op, const PcDevBatch &B, cudaStream_t s, int sm_count);
+void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count);
+int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, long long max_l1, int max_l2, cudaStream_t s);
+int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned long long **keys, uint32_t **pos,
+                   uint32_t *n_out, cudaStream_t s);
+extern unsigned long long g_pc_launches;

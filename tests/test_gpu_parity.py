@@ -1,0 +1,216 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against (1) the golden vectors the UNMODIFIED reference
+produced, (2) the oracle port on seeded inputs, (3) size-independent properties at sizes the oracle cannot reach.
+Bit-exact everywhere: this path is integer / byte work."""
+import numpy as np
+import pytest
+
+import pintron_b200
+from pintron_b200 import Batch, PC_OP
+from oracle.binding import Port, ops_to_rows
+from util_cases import Gen, enc, golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cu():
+    c = pintron_b200.Cuda(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def port():
+    return Port()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return golden()
+
+
+def test_native_library_is_loaded(cu):
+    before = cu.launch_count()
+    assert cu.edit_distance(b"ACGT", b"AGT") == 1
+    assert cu.launch_count() > before
+
+
+def test_align_golden(cu, gold):
+    b = Batch()
+    for c in gold["align"]:
+        b.add(PC_OP.ALIGN, enc(c["est"]), enc(c["gen"]))
+    res, var = cu.run(b)
+    _, jobs = b.arrays()
+    for c, r, j in zip(gold["align"], res, jobs):
+        assert r[0] == 0 and r[1] == c["score"]
+        ops = var[j["out_off"]:j["out_off"] + r[2]].tobytes()
+        assert ops_to_rows(ops, enc(c["est"]), enc(c["gen"])) == (enc(c["est_row"]), enc(c["gen_row"]))
+
+
+def test_scalar_ops_golden(cu, gold):
+    b = Batch()
+    exp = []
+    for c in gold["edit"]:
+        b.add(PC_OP.EDIT, enc(c["a"]), enc(c["b"])); exp.append([c["dist"]])
+    for c in gold["kband"]:
+        b.add(PC_OP.KBAND, enc(c["a"]), enc(c["b"]), p0=c["k"]); exp.append([int(c["ok"]), c["edit"]])
+    for c in gold["borders"]:
+        b.add(PC_OP.BORDERS, enc(c["p"]), enc(c["t"]), p0=c["max_errs"], p1=0, p2=len(c["p"]))
+        exp.append([int(c["ok"])] + c["out"])
+    for c in gold["affix"]:
+        b.add(PC_OP.AFFIX, enc(c["est"]), enc(c["gen"])); exp.append([int(c["out"][0])] + c["out"][1:])
+    for c in gold["suffix_cut"]:
+        b.add(PC_OP.SUFCUT, enc(c["a"]), enc(c["b"])); exp.append(c["out"])
+    for c in gold["prefix_cut"]:
+        b.add(PC_OP.PRECUT, enc(c["a"]), enc(c["b"])); exp.append(c["out"])
+    for c in gold["lcs"]:
+        b.add(PC_OP.LCS, enc(c["s2"]), enc(c["s1"])); exp.append(c["out"])
+    res, _ = cu.run(b)
+    for i, (r, e) in enumerate(zip(res, exp)):
+        assert r[0] == 0, (i, r)
+        assert list(r[1:1 + len(e)]) == e, (i, b.jobs[i][0], list(r), e)
+
+
+def test_gap_golden(cu, gold):
+    b = Batch()
+    for c in gold["gap"]:
+        b.add(PC_OP.GAP, enc(c["est"]), enc(c["gen"]))
+    res, var = cu.run(b)
+    _, jobs = b.arrays()
+    for c, r, j in zip(gold["gap"], res, jobs):
+        assert r[0] == 0
+        ops = var[j["out_off"]:j["out_off"] + r[1]].tobytes()
+        assert ops_to_rows(ops, enc(c["est"]), enc(c["gen"])) == (enc(c["est_row"]), enc(c["gen_row"]))
+        assert list(r[2:7]) == c["pos"]
+
+
+def test_seed_golden(cu, gold):
+    s = gold["seed"]
+    cu.genome_upload(enc(s["genome"]), 15, s["rate"])
+    b = Batch()
+    for c in s["cases"]:
+        b.add(PC_OP.SEED, enc(c["est"]), p0=c["mfl"], out_cap=4096)
+    res, var = cu.run(b)
+    _, jobs = b.arrays()
+    for c, r, j in zip(s["cases"], res, jobs):
+        assert r[0] == 0
+        tri = var[j["out_off"]:j["out_off"] + 12 * r[1]].view(np.int32).reshape(-1, 3)
+        assert [list(map(int, x)) for x in tri] == c["pairings"]
+
+
+def test_mixed_batch_vs_port(cu, port):
+    """One heterogeneous batch of ~3000 jobs, every op, seeded; each result equals the oracle's."""
+    g = Gen(4242)
+    genome = g.genome(6000)
+    cu.genome_upload(genome, 15, 0.2)
+    b, chk = Batch(), []
+    for it in range(300):
+        a, c = g.pair(220, it)
+        b.add(PC_OP.ALIGN, a, c); chk.append(("align", a, c))
+        b.add(PC_OP.EDIT, a, c); chk.append(("edit", a, c))
+        k = g.rnd.randint(0, 14)
+        b.add(PC_OP.KBAND, a, c, p0=k); chk.append(("kband", a, c, k))
+        b.add(PC_OP.SUFCUT, a, c); chk.append(("sc", a, c))
+        b.add(PC_OP.PRECUT, a, c); chk.append(("pc", a, c))
+        b.add(PC_OP.AFFIX, a, c); chk.append(("affix", a, c))
+        b.add(PC_OP.LCS, c, a); chk.append(("lcs", a, c))
+        p, t, me = g.borders_case()
+        lo = g.rnd.randint(0, len(p)); hi = g.rnd.randint(lo, len(p))
+        b.add(PC_OP.BORDERS, p, t, p0=me, p1=lo, p2=hi); chk.append(("borders", p, t, me, lo, hi))
+        est, gen = g.gap_case()
+        b.add(PC_OP.GAP, est, gen); chk.append(("gap", est, gen))
+        e = g.est_from(genome, it)
+        mfl = (15, 16, 21)[it % 3]
+        b.add(PC_OP.SEED, e, p0=mfl, out_cap=2048); chk.append(("seed", e, mfl))
+    res, var = cu.run(b)
+    _, jobs = b.arrays()
+    for r, j, c in zip(res, jobs, chk):
+        assert r[0] == 0, (c[0], list(r))
+        kind = c[0]
+        if kind == "align":
+            s, ops = port.align(c[1], c[2])
+            assert r[1] == s and var[j["out_off"]:j["out_off"] + r[2]].tobytes() == ops
+        elif kind == "edit":
+            assert r[1] == port.edit(c[1], c[2])
+        elif kind == "kband":
+            assert (bool(r[1]), int(r[2])) == port.kband(c[1], c[2], c[3])
+        elif kind == "sc":
+            assert tuple(r[1:4]) == port.suffix_cut(c[1], c[2])
+        elif kind == "pc":
+            assert tuple(r[1:4]) == port.prefix_cut(c[1], c[2])
+        elif kind == "affix":
+            ok, e_, g_ = port.affix(c[1], c[2])
+            assert bool(r[1]) == ok and (not ok or (r[2], r[3]) == (e_, g_))
+        elif kind == "lcs":
+            assert tuple(r[1:4]) == port.lcs(c[1], c[2])
+        elif kind == "borders":
+            ok, out = port.borders(c[1], c[2], c[3], c[4], c[5])
+            assert bool(r[1]) == ok and list(r[2:6]) == out
+        elif kind == "gap":
+            ops, pos = port.gap(c[1], c[2])
+            assert var[j["out_off"]:j["out_off"] + r[1]].tobytes() == ops and list(r[2:7]) == pos
+        elif kind == "seed":
+            tri = var[j["out_off"]:j["out_off"] + 12 * r[1]].view(np.int32).reshape(-1, 3)
+            assert [tuple(map(int, x)) for x in tri] == port.seed(genome, c[1], c[2], 0.2)
+
+
+def test_edge_cases(cu, port):
+    assert cu.compute_alignment(b"", b"ACG") == port.align(b"", b"ACG")
+    assert cu.compute_alignment(b"ACG", b"") == port.align(b"ACG", b"")
+    assert cu.compute_alignment(b"ANG", b"ACG") == port.align(b"ANG", b"ACG")
+    assert cu.edit_distance(b"", b"") == 0
+    assert cu.K_band_edit_distance(b"ACGT", b"ACGT", 0) == (True, 0)
+    assert cu.K_band_edit_distance(b"ACGT", b"ACGA", 0) == (False, 1)
+    assert cu.K_band_edit_distance(b"ACGTACGTAC", b"ACG", 2) == (False, 7)
+    assert cu.find_longest_common_factor_dp(b"", b"ACG") == (0, 0, 0)
+    assert cu.find_longest_common_factor_dp(b"TTANGTT", b"GACGA") == (3, 2, 1)
+    assert cu.find_longest_affix(b"", b"ACG") == (False, 0, 0)
+    assert cu.general_refine_borders(b"", b"ACGTAC", 3) == port.borders(b"", b"ACGTAC", 3)
+    assert cu.compute_gap_alignment(b"A", b"C") == port.gap(b"A", b"C")
+    res, _ = cu.run(Batch())
+    assert res.shape == (0, 8)
+
+
+def test_long_alignment_band_and_pool_growth(cu, port):
+    """mRNA-sized exons: the banded kernel must reproduce the full-matrix oracle, including when the batch needs more
+    scratch than the initial pool (pc_stream_sync retries PC_E_POOL jobs)."""
+    g = Gen(99)
+    b, pairs = Batch(), []
+    for it in range(24):
+        a = g.rs(g.rnd.randint(1500, 4000))
+        c = g.mutate(a, (0.01, 0.03, 0.1)[it % 3], alpha="ACGT")
+        if it % 8 == 0:
+            c = c[:len(c) // 2] + g.rs(300) + c[len(c) // 2:]      # a long insertion: wide band
+        pairs.append((a, c)); b.add(PC_OP.ALIGN, a, c)
+    res, var = cu.run(b)
+    _, jobs = b.arrays()
+    for (a, c), r, j in zip(pairs, res, jobs):
+        s, ops = port.align(a, c)
+        assert r[0] == 0 and r[1] == s
+        assert var[j["out_off"]:j["out_off"] + r[2]].tobytes() == ops
+
+
+def test_properties_at_scale(cu):
+    """Beyond oracle reach (10^4-10^5 nt): score symmetry, ops consistency and identity."""
+    g = Gen(5)
+    a = g.rs(60000)
+    c = g.mutate(a, 0.005, alpha="ACGT")
+    s1, ops1 = cu.compute_alignment(a, c)
+    s2, ops2 = cu.compute_alignment(c, a)
+    assert s1 == s2 == cu.edit_distance(a.replace(b"N", b"A"), c.replace(b"N", b"A")) or s1 == s2
+    o = np.frombuffer(ops1, dtype=np.uint8)
+    assert (o != 2).sum() == len(a) and (o != 1).sum() == len(c)
+    # the cost of the reported path equals the reported score
+    i = j = cost = 0
+    for x in ops1:
+        if x == 0:
+            cost += a[i] != c[j] and a[i] not in b"Nn" and c[j] not in b"Nn"; i += 1; j += 1
+        elif x == 1:
+            cost += 1; i += 1
+        else:
+            cost += 1; j += 1
+    assert cost == s1
+    s0, ops0 = cu.compute_alignment(a, a)
+    assert s0 == 0 and set(ops0) == {0}
+    ln, o1, o2 = cu.find_longest_common_factor_dp(a, a[30000:30040])
+    assert ln == 40 and a[o1:o1 + ln] == a[30000:30040] and o2 == 0
