@@ -122,7 +122,10 @@ uint64_t pc_launch_count(void);                  /* kernels launched by this lib
 int pc_stream_op_time(pc_stream *st, int op, double *ms, uint64_t *launches);
 void pc_stream_reset_timers(pc_stream *st);
 void pc_stream_enable_timers(pc_stream *st, int on);
-void *pc_stream_cuda_stream(pc_stream *st);      /* the cudaStream_t, for callers that interoperate */
+void *pc_stream_cuda_stream(pc_stream *st);
+/* INT32 ALU micro-benchmark: lane-operations per second of independent add/min chains (the roofline
+ * denominator for the DP kernels; SURVEY.md §8(d) asks for a measured figure). */
+double pc_measure_int_peak(pc_ctx *ctx);      /* the cudaStream_t, for callers that interoperate */
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,7 @@ EXPORTS = ["pc_last_error", "pc_device_count", "pc_ctx_create", "pc_ctx_destroy"
            "pc_stream_sync", "pc_compute_alignment_batch", "pc_kband_edit_distance_batch", "pc_edit_distance_batch",
            "pc_refine_borders_batch", "pc_gap_alignment_batch", "pc_longest_affix_batch", "pc_best_cut_batch",
            "pc_longest_common_factor_batch", "pc_build_vertex_set_batch", "pc_launch_count", "pc_stream_op_time",
-           "pc_stream_reset_timers", "pc_stream_enable_timers", "pc_stream_cuda_stream"]
+           "pc_stream_reset_timers", "pc_stream_enable_timers", "pc_stream_cuda_stream", "pc_measure_int_peak"]
 
 
 def library_path():
@@ -71,6 +71,8 @@ def load_library():
     L.pc_stream_enable_timers.argtypes = [C.c_void_p, C.c_int]
     L.pc_stream_cuda_stream.restype = C.c_void_p
     L.pc_stream_cuda_stream.argtypes = [C.c_void_p]
+    L.pc_measure_int_peak.restype = C.c_double
+    L.pc_measure_int_peak.argtypes = [C.c_void_p]
     return L
 
 

@@ -90,10 +90,10 @@ __device__ __forceinline__ JobView view(const PcDevBatch &B, int w) {
   return v;
 }
 
-__device__ __forceinline__ uint32_t *state_mem(const PcDevBatch &B, uint32_t *smem, size_t ints, int lane, bool &ok) {
+__device__ __forceinline__ uint32_t *state_mem(const PcDevBatch &B, WarpPool &wp, uint32_t *smem, size_t ints, int lane, bool &ok) {
   ok = true;
   if (ints <= PC_SMEM_INTS_PER_WARP) return smem;
-  uint32_t *p = (uint32_t *)pc_pool_alloc(B, ints * 4ull, lane);
+  uint32_t *p = (uint32_t *)pc_pool_alloc(B, wp, ints * 4ull, lane);
   ok = p != nullptr;
   return p;
 }
@@ -101,7 +101,7 @@ __device__ __forceinline__ uint32_t *state_mem(const PcDevBatch &B, uint32_t *sm
 #define PC_FAIL(code) do { if (lane == 0) J.res[0] = (code); return; } while (0)
 
 // ---- DP A: compute_alignment (src/compute-alignments.c:39-207) --------------------------------------------
-__device__ void op_align(const PcDevBatch &B, int w, uint32_t *smem, int lane) {
+__device__ void op_align(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *smem, int lane) {
   JobView J = view(B, w);
   const int n = J.la, m = J.lb;
   uint8_t *ops = B.var_out + J.job->out_off;
@@ -114,7 +114,7 @@ __device__ void op_align(const PcDevBatch &B, int w, uint32_t *smem, int lane) {
   for (;;) {
     int lo = max(min(0, off) - d, -n), hi = min(max(0, off) + d, m);
     bool ok;
-    uint32_t *H = state_mem(B, smem, (size_t)(hi - lo + 1), lane, ok);
+    uint32_t *H = state_mem(B, wp, smem, (size_t)(hi - lo + 1), lane, ok);
     if (!ok) PC_FAIL(PC_E_POOL);
     score = banded_dp<true, ST_NONE>(rows, n, cols, m, lo, hi, H, nullptr, nullptr, lane);
     if (score <= (uint32_t)d || (lo == -n && hi == m)) break;
@@ -124,9 +124,9 @@ __device__ void op_align(const PcDevBatch &B, int w, uint32_t *smem, int lane) {
   const int lo = max(min(0, off) - (int)score, -n), hi = min(max(0, off) + (int)score, m);
   const int W = hi - lo + 1;
   bool ok;
-  uint32_t *H = state_mem(B, smem, (size_t)W, lane, ok);
+  uint32_t *H = state_mem(B, wp, smem, (size_t)W, lane, ok);
   if (!ok) PC_FAIL(PC_E_POOL);
-  uint8_t *dir = pc_pool_alloc(B, (unsigned long long)(n + 1) * W, lane);
+  uint8_t *dir = pc_pool_alloc(B, wp, (unsigned long long)(n + 1) * W, lane);
   if (!dir) PC_FAIL(PC_E_POOL);
   banded_dp<true, ST_DIR>(rows, n, cols, m, lo, hi, H, dir, nullptr, lane);
   __syncwarp();
@@ -152,7 +152,7 @@ __device__ bool warp_equal(const uint8_t *a, const uint8_t *b, int len, int lane
   return !__any_sync(0xffffffffu, diff);
 }
 
-__device__ void op_kband(const PcDevBatch &B, int w, uint32_t *smem, int lane) {
+__device__ void op_kband(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *smem, int lane) {
   JobView J = view(B, w);
   const uint32_t k = (uint32_t)J.job->p0;
   int ok_flag; uint32_t edit;
@@ -169,7 +169,7 @@ __device__ void op_kband(const PcDevBatch &B, int w, uint32_t *smem, int lane) {
       if (2ull * k + 1ull >= (unsigned long long)n) { lo = -m; hi = n; } else { lo = -(int)k; hi = (int)k; }
       lo = max(lo, -m); hi = min(hi, n);
       bool ok;
-      uint32_t *H = state_mem(B, smem, (size_t)(hi - lo + 1), lane, ok);
+      uint32_t *H = state_mem(B, wp, smem, (size_t)(hi - lo + 1), lane, ok);
       if (!ok) PC_FAIL(PC_E_POOL);
       edit = banded_dp<false, ST_NONE>(Str{s2, 1}, m, Str{s1, 1}, n, lo, hi, H, nullptr, nullptr, lane);
       ok_flag = edit <= k;
@@ -179,10 +179,10 @@ __device__ void op_kband(const PcDevBatch &B, int w, uint32_t *smem, int lane) {
 }
 
 // ---- plain edit distance, last cell (src/refine.c:51, src/compute-alignments.c:235) -----------------------
-__device__ void op_edit(const PcDevBatch &B, int w, uint32_t *smem, int lane) {
+__device__ void op_edit(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *smem, int lane) {
   JobView J = view(B, w);
   bool ok;
-  uint32_t *H = state_mem(B, smem, (size_t)J.la + J.lb + 1, lane, ok);
+  uint32_t *H = state_mem(B, wp, smem, (size_t)J.la + J.lb + 1, lane, ok);
   if (!ok) PC_FAIL(PC_E_POOL);
   uint32_t d = banded_dp<false, ST_NONE>(Str{J.a, 1}, J.la, Str{J.b, 1}, J.lb, -J.la, J.lb, H, nullptr, nullptr, lane);
   if (lane == 0) { J.res[0] = PC_OK; J.res[1] = (int32_t)d; }
@@ -217,7 +217,7 @@ __device__ int burset_freq(const uint8_t *t, int cut1, int cut2) {
 
 // ---- DP C: general_refine_borders (src/refine.c:106-190) --------------------------------------------------
 // a = p, b = t (the byte b[lb] must be readable: it is what the reference reads after t).
-__device__ void op_borders(const PcDevBatch &B, int w, uint32_t *smem, int lane) {
+__device__ void op_borders(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *smem, int lane) {
   JobView J = view(B, w);
   const int len_p = J.la, len_t = J.lb;
   const uint32_t max_errs = (uint32_t)J.job->p0;
@@ -226,9 +226,9 @@ __device__ void op_borders(const PcDevBatch &B, int w, uint32_t *smem, int lane)
   const int t_win = (int)min((unsigned long long)len_p + max_errs, (unsigned long long)len_t);
   const size_t cells = (size_t)(len_p + 1) * (t_win + 1);
   bool ok;
-  uint32_t *H = state_mem(B, smem, (size_t)len_p + t_win + 1, lane, ok);
+  uint32_t *H = state_mem(B, wp, smem, (size_t)len_p + t_win + 1, lane, ok);
   if (!ok) PC_FAIL(PC_E_POOL);
-  uint32_t *M = (uint32_t *)pc_pool_alloc(B, (2 * cells + 4ull * (len_p + 1)) * 4ull, lane);
+  uint32_t *M = (uint32_t *)pc_pool_alloc(B, wp, (2 * cells + 4ull * (len_p + 1)) * 4ull, lane);
   if (!M) PC_FAIL(PC_E_POOL);
   uint32_t *Mp = M, *Ms = M + cells, *mn = M + 2 * cells, *pos = mn + 2 * (len_p + 1);
   // rows over p, columns over the first t_win chars of t (prefix side) / of reversed t (suffix side)
@@ -264,14 +264,14 @@ __device__ void op_borders(const PcDevBatch &B, int w, uint32_t *smem, int lane)
 }
 
 // ---- DP E: find_longest_affix (src/factorization-refinement.c:1134-1172) ----------------------------------
-__device__ void op_affix(const PcDevBatch &B, int w, uint32_t *smem, int lane) {
+__device__ void op_affix(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *smem, int lane) {
   JobView J = view(B, w);
   const int el = J.la, gl = J.lb;
   bool ok;
-  uint32_t *H = state_mem(B, smem, (size_t)el + gl + 1, lane, ok);
+  uint32_t *H = state_mem(B, wp, smem, (size_t)el + gl + 1, lane, ok);
   if (!ok) PC_FAIL(PC_E_POOL);
   const size_t cells = (size_t)(el + 1) * (gl + 1);
-  uint32_t *M = (uint32_t *)pc_pool_alloc(B, cells * 4ull, lane);
+  uint32_t *M = (uint32_t *)pc_pool_alloc(B, wp, cells * 4ull, lane);
   if (!M) PC_FAIL(PC_E_POOL);
   banded_dp<false, ST_MAT>(Str{J.a, 1}, el, Str{J.b, 1}, gl, -el, gl, H, nullptr, M, lane);
   __syncwarp();
@@ -297,7 +297,7 @@ __device__ void op_affix(const PcDevBatch &B, int w, uint32_t *smem, int lane) {
 }
 
 // ---- compute_best_suffix_cut / compute_best_prefix_cut (src/compute-alignments.c:246-316) -----------------
-__device__ void op_cut(const PcDevBatch &B, int w, uint32_t *smem, int lane, bool prefix) {
+__device__ void op_cut(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *smem, int lane, bool prefix) {
   JobView J = view(B, w);
   const int l1 = J.la, l2 = J.lb;
   if (l1 == l2 && warp_equal(J.a, J.b, l1, lane)) {
@@ -305,10 +305,10 @@ __device__ void op_cut(const PcDevBatch &B, int w, uint32_t *smem, int lane, boo
     return;
   }
   bool ok;
-  uint32_t *H = state_mem(B, smem, (size_t)l1 + l2 + 1, lane, ok);
+  uint32_t *H = state_mem(B, wp, smem, (size_t)l1 + l2 + 1, lane, ok);
   if (!ok) PC_FAIL(PC_E_POOL);
   const size_t Wd = (size_t)l2 + 1;
-  uint32_t *M = (uint32_t *)pc_pool_alloc(B, (size_t)(l1 + 1) * Wd * 4ull, lane);
+  uint32_t *M = (uint32_t *)pc_pool_alloc(B, wp, (size_t)(l1 + 1) * Wd * 4ull, lane);
   if (!M) PC_FAIL(PC_E_POOL);
   Str r = prefix ? Str{J.a + l1 - 1, -1} : Str{J.a, 1};
   Str c = prefix ? Str{J.b + l2 - 1, -1} : Str{J.b, 1};
@@ -330,18 +330,18 @@ __device__ void op_cut(const PcDevBatch &B, int w, uint32_t *smem, int lane, boo
 // ---- DP D: compute_gap_alignment (src/refine-intron.c:560-890) --------------------------------------------
 // Three score planes L/G/R swept together on the same wavefront; one direction byte per cell:
 // bits 0-1 = L dir, bit 2 = G jump, bits 3-4 = R dir (3 = jump to G).
-__device__ void op_gap(const PcDevBatch &B, int w, uint32_t *smem, int lane) {
+__device__ void op_gap(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *smem, int lane) {
   JobView J = view(B, w);
   const int n = J.la, m = J.lb;
   uint8_t *ops = B.var_out + J.job->out_off;
   if ((uint32_t)(n + m) > J.job->out_cap) PC_FAIL(PC_E_OUTCAP);
   const int W = n + m + 1, lo = -n;
   bool ok;
-  int32_t *HL = (int32_t *)state_mem(B, smem, 3 * (size_t)W, lane, ok);
+  int32_t *HL = (int32_t *)state_mem(B, wp, smem, 3 * (size_t)W, lane, ok);
   if (!ok) PC_FAIL(PC_E_POOL);
   int32_t *HG = HL + W, *HR = HG + W;
   const size_t Wd = (size_t)m + 1;
-  uint8_t *dir = pc_pool_alloc(B, (unsigned long long)(n + 1) * Wd, lane);
+  uint8_t *dir = pc_pool_alloc(B, wp, (unsigned long long)(n + 1) * Wd, lane);
   if (!dir) PC_FAIL(PC_E_POOL);
   for (int x = lane; x < 3 * W; x += 32) HL[x] = 0;
   __syncwarp();
@@ -413,15 +413,17 @@ __global__ void __launch_bounds__(PC_WARPS_PER_CTA * 32) k_warp_per_job(PcDevBat
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nwarps = gridDim.x * PC_WARPS_PER_CTA;
   // jobs are sorted heaviest first; deal them round-robin over the resident warps
+  WarpPool wp = pc_warp_pool(B, blockIdx.x * PC_WARPS_PER_CTA + wib);
   for (int w = blockIdx.x * PC_WARPS_PER_CTA + wib; w < B.n; w += nwarps) {
-    if (OP == PC_OP_ALIGN) op_align(B, w, smem[wib], lane);
-    else if (OP == PC_OP_KBAND) op_kband(B, w, smem[wib], lane);
-    else if (OP == PC_OP_EDIT) op_edit(B, w, smem[wib], lane);
-    else if (OP == PC_OP_BORDERS) op_borders(B, w, smem[wib], lane);
-    else if (OP == PC_OP_GAP) op_gap(B, w, smem[wib], lane);
-    else if (OP == PC_OP_AFFIX) op_affix(B, w, smem[wib], lane);
-    else if (OP == PC_OP_SUFCUT) op_cut(B, w, smem[wib], lane, false);
-    else if (OP == PC_OP_PRECUT) op_cut(B, w, smem[wib], lane, true);
+    wp.used = 0;
+    if (OP == PC_OP_ALIGN) op_align(B, wp, w, smem[wib], lane);
+    else if (OP == PC_OP_KBAND) op_kband(B, wp, w, smem[wib], lane);
+    else if (OP == PC_OP_EDIT) op_edit(B, wp, w, smem[wib], lane);
+    else if (OP == PC_OP_BORDERS) op_borders(B, wp, w, smem[wib], lane);
+    else if (OP == PC_OP_GAP) op_gap(B, wp, w, smem[wib], lane);
+    else if (OP == PC_OP_AFFIX) op_affix(B, wp, w, smem[wib], lane);
+    else if (OP == PC_OP_SUFCUT) op_cut(B, wp, w, smem[wib], lane, false);
+    else if (OP == PC_OP_PRECUT) op_cut(B, wp, w, smem[wib], lane, true);
     __syncwarp();
   }
 }
@@ -430,8 +432,12 @@ template <int OP>
 void launch_wpj(const PcDevBatch &B, cudaStream_t s, int sm_count) {
   const int ctas_needed = (B.n + PC_WARPS_PER_CTA - 1) / PC_WARPS_PER_CTA;
   const int resident = sm_count * 4;      // 48 KB static smem per CTA -> 4 CTAs per SM
-  const int grid = ctas_needed < resident ? ctas_needed : resident;
-  k_warp_per_job<OP><<<grid, PC_WARPS_PER_CTA * 32, 0, s>>>(B);
+  int grid = ctas_needed < resident ? ctas_needed : resident;
+  if (B.max_warps > 0 && grid > (B.max_warps + PC_WARPS_PER_CTA - 1) / PC_WARPS_PER_CTA)
+    grid = (B.max_warps + PC_WARPS_PER_CTA - 1) / PC_WARPS_PER_CTA;
+  PcDevBatch C = B;
+  C.slots = grid * PC_WARPS_PER_CTA;
+  k_warp_per_job<OP><<<grid, PC_WARPS_PER_CTA * 32, 0, s>>>(C);
   ++g_pc_launches;
 }
 
@@ -449,4 +455,34 @@ void pc_launch_dp(int op, const PcDevBatch &B, cudaStream_t s, int sm_count) {
     case PC_OP_PRECUT: launch_wpj<PC_OP_PRECUT>(B, s, sm_count); break;
     default: break;
   }
+}
+
+// ---- INT32 ALU peak micro-benchmark (roofline denominator for the DP kernels) ------------
+// 8 independent add/min chains per thread; each add+min pair becomes one VIADDMNMX on the ALU pipe (checked
+// with cuobjdump -sass).  Returns executed ALU lane-INSTRUCTIONS; the host divides by the CUDA-event time.
+__global__ void __launch_bounds__(256) k_int_peak(int iters, int a, int b, int *sink) {
+  int v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+#define STEP(v) asm volatile("add.s32 %0, %0, %1;\n\tmin.s32 %0, %0, %2;" : "+r"(v) : "r"(a), "r"(b));
+    STEP(v0) STEP(v1) STEP(v2) STEP(v3) STEP(v4) STEP(v5) STEP(v6) STEP(v7)
+#undef STEP
+  }
+  if ((v0 ^ v1 ^ v2 ^ v3 ^ v4 ^ v5 ^ v6 ^ v7) == 0x7fffffff) *sink = v0;
+}
+
+double pc_int_peak_run(cudaStream_t s, int sm_count, float *ms_out) {
+  int *sink; cudaMalloc(&sink, 4);
+  const int iters = 1 << 14, grid = sm_count * 8;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_int_peak<<<grid, 256, 0, s>>>(iters, 3, 1 << 30, sink);          // warm-up
+  cudaEventRecord(e0, s);
+  k_int_peak<<<grid, 256, 0, s>>>(iters, 3, 1 << 30, sink);
+  cudaEventRecord(e1, s);
+  cudaEventSynchronize(e1);
+  g_pc_launches += 2;
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+  if (ms_out) *ms_out = ms;
+  return (double)grid * 256.0 * iters * 8.0;    // ptxas fuses each add+min pair into ONE VIADDMNMX: 8 ALU instructions / iteration
 }

@@ -61,7 +61,7 @@ __device__ int warp_exscan(int *v, int n, int lane) {
 //  ascending t; filter A inside one p; filter B against the list of p-1; emit (p,t,l) by ascending p.
 struct TL { int t, l; };
 
-__device__ void seed_one(const PcDevBatch &B, int w, int lane) {
+__device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane) {
   const uint32_t ji = B.idx[w];
   const pc_job *job = B.jobs + ji;
   int32_t *res = B.res + (size_t)ji * PC_RES_INTS;
@@ -74,7 +74,7 @@ __device__ void seed_one(const PcDevBatch &B, int w, int lane) {
   const int np = n - word + 1;               // positions that can start a word
   if (np <= 0 || G < (uint32_t)word) { if (lane == 0) { res[0] = PC_OK; res[1] = 0; } return; }
   // per-position arrays: bucket start, bucket end, D / offsets, counts
-  int *arr = (int *)pc_pool_alloc(B, 5ull * np * sizeof(int), lane);
+  int *arr = (int *)pc_pool_alloc(B, wp, 5ull * np * sizeof(int), lane);
   if (!arr) { if (lane == 0) res[0] = PC_E_POOL; return; }
   int *b_lo = arr, *b_hi = arr + np, *offs = arr + 2 * np, *cnt = arr + 3 * np, *thr_a = arr + 4 * np;
   // S1: bucket, D(p), number of candidates >= mfl
@@ -100,7 +100,7 @@ __device__ void seed_one(const PcDevBatch &B, int w, int lane) {
   __syncwarp();
   TL *cand = nullptr; uint8_t *keep = nullptr;
   if (total > 0) {
-    cand = (TL *)pc_pool_alloc(B, (unsigned long long)total * (sizeof(TL) + 1), lane);
+    cand = (TL *)pc_pool_alloc(B, wp, (unsigned long long)total * (sizeof(TL) + 1), lane);
     if (!cand) { if (lane == 0) res[0] = PC_E_POOL; return; }
     keep = (uint8_t *)(cand + total);
   }
@@ -162,8 +162,10 @@ __device__ void seed_one(const PcDevBatch &B, int w, int lane) {
 __global__ void __launch_bounds__(128) k_seed(PcDevBatch B) {
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
+  WarpPool wp = pc_warp_pool(B, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < B.n; w += nwarps) {
-    seed_one(B, w, lane);
+    wp.used = 0;
+    seed_one(B, wp, w, lane);
     __syncwarp();
   }
 }
@@ -240,8 +242,11 @@ __global__ void k_lcs_finish(PcDevBatch B, const unsigned long long *best) {
 
 void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count) {
   const int ctas = (B.n + 3) / 4;
-  const int grid = ctas < sm_count * 8 ? ctas : sm_count * 8;
-  k_seed<<<grid, 128, 0, s>>>(B);
+  int grid = ctas < sm_count * 8 ? ctas : sm_count * 8;
+  if (B.max_warps > 0 && grid > (B.max_warps + 3) / 4) grid = (B.max_warps + 3) / 4;
+  PcDevBatch C = B;
+  C.slots = grid * 4;
+  k_seed<<<grid, 128, 0, s>>>(C);
   ++g_pc_launches;
 }
 

@@ -59,7 +59,8 @@ struct pc_stream {
   pc_ctx *ctx = nullptr;
   cudaStream_t s = nullptr;
   DevBuf arena, jobs, idx, res, var, pool, lcs_best;
-  unsigned long long *d_pool_used = nullptr;
+  unsigned long long *d_pool_need = nullptr, *h_pool_need = nullptr;   /* device counter + pinned mirror */
+  int max_warps = 0;
   std::vector<uint32_t> h_idx;
   std::vector<int32_t> h_status;
   Pending pend;
@@ -122,12 +123,13 @@ extern "C" pc_stream *pc_stream_create(pc_ctx *c) {
   pc_stream *st = new pc_stream();
   st->ctx = c;
   if (cudaStreamCreateWithFlags(&st->s, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMalloc(&st->d_pool_used, 8) != cudaSuccess) {
+      cudaMalloc(&st->d_pool_need, 8) != cudaSuccess ||
+      cudaHostAlloc((void **)&st->h_pool_need, 8, cudaHostAllocDefault) != cudaSuccess) {
     fail(PC_E_CUDA, "%s", "pc_stream_create: stream / counter allocation failed");
     delete st;
     return nullptr;
   }
-  if (st->pool.reserve(64ull << 20)) { delete st; return nullptr; }
+  if (st->pool.reserve(256ull << 20)) { delete st; return nullptr; }
   return st;
 }
 
@@ -136,7 +138,7 @@ extern "C" void pc_stream_destroy(pc_stream *st) {
   cudaSetDevice(st->ctx->device);
   cudaStreamSynchronize(st->s);
   for (DevBuf *b : {&st->arena, &st->jobs, &st->idx, &st->res, &st->var, &st->pool, &st->lcs_best}) b->release();
-  cudaFree(st->d_pool_used);
+  cudaFree(st->d_pool_need); cudaFreeHost(st->h_pool_need);
   for (auto &e : st->ev_pending) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
   for (auto e : st->ev_free) cudaEventDestroy(e);
   cudaStreamDestroy(st->s);
@@ -147,6 +149,16 @@ extern "C" void *pc_host_alloc(size_t bytes) {
   void *p = nullptr;
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { fail(PC_E_NOMEM, "%s", "cudaHostAlloc failed"); return nullptr; }
   return p;
+}
+double pc_int_peak_run(cudaStream_t s, int sm_count, float *ms_out);
+/* Measured INT32 ALU-pipe throughput of this GPU in lane-operations per second (add + min chains). */
+extern "C" double pc_measure_int_peak(pc_ctx *c) {
+  if (!c) return 0.0;
+  cudaSetDevice(c->device);
+  float ms = 0;
+  double best = 0;
+  for (int r = 0; r < 3; ++r) { double ops = pc_int_peak_run(0, c->sm_count, &ms); if (ms > 0) best = std::max(best, ops / (ms * 1e-3)); }
+  return best;
 }
 extern "C" void pc_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" uint64_t pc_launch_count(void) { return g_pc_launches; }
@@ -194,19 +206,33 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
                            const pc_job *d_jobs, int32_t *d_res, uint8_t *d_var) {
   pc_ctx *c = st->ctx;
   // partition by op, heaviest first inside each op
+  // counting sort on (op, log2 cost class descending): O(n), good enough for load balance
   std::vector<uint32_t> &order = st->h_idx;
-  order.assign(sel.begin(), sel.end());
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-    if (h_jobs[x].op != h_jobs[y].op) return h_jobs[x].op < h_jobs[y].op;
-    return job_cost(h_jobs[x]) > job_cost(h_jobs[y]);
-  });
+  order.resize(sel.size());
+  {
+    const int NB = PC_OP_COUNT * 64;
+    std::vector<uint32_t> bins(NB + 1, 0);
+    std::vector<uint16_t> key(sel.size());
+    for (size_t q = 0; q < sel.size(); ++q) {
+      const pc_job &j = h_jobs[sel[q]];
+      if (j.op >= PC_OP_COUNT) return fail(PC_E_ARG, "%s", "pc_submit: unknown op");
+      int lg = 0;
+      unsigned long long c = (unsigned long long)job_cost(j) + 1;
+      while (c >>= 1) ++lg;
+      key[q] = (uint16_t)(j.op * 64 + (63 - lg));
+      ++bins[key[q] + 1];
+    }
+    for (int b = 0; b < NB; ++b) bins[b + 1] += bins[b];
+    for (size_t q = 0; q < sel.size(); ++q) order[bins[key[q]]++] = sel[q];
+  }
   if (st->idx.reserve(order.size() * 4 + 4)) return PC_E_NOMEM;
   CU(cudaMemcpyAsync(st->idx.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, st->s));
-  CU(cudaMemsetAsync(st->d_pool_used, 0, 8, st->s));
+  CU(cudaMemsetAsync(st->d_pool_need, 0, 8, st->s));
   PcDevBatch B;
   B.arena = d_arena; B.genome = c->d_genome; B.genome_len = c->genome_len;
   B.jobs = d_jobs; B.res = d_res; B.var_out = d_var;
-  B.pool = (uint8_t *)st->pool.p; B.pool_cap = st->pool.cap; B.pool_used = st->d_pool_used;
+  B.pool = (uint8_t *)st->pool.p; B.pool_cap = st->pool.cap; B.pool_need = st->d_pool_need;
+  B.slots = 1; B.max_warps = st->max_warps;
   B.ix_keys = c->ix_keys; B.ix_pos = c->ix_pos; B.ix_n = c->ix_n; B.ix_word = c->ix_word; B.depth_rate = c->depth_rate;
   size_t i = 0;
   while (i < order.size()) {
@@ -237,6 +263,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
     if (st->timers) { cudaEventRecord(e1, st->s); st->ev_pending.push_back({(int)op, {e0, e1}}); }
     i = j;
   }
+  CU(cudaMemcpyAsync(st->h_pool_need, st->d_pool_need, 8, cudaMemcpyDeviceToHost, st->s));
   CU(cudaGetLastError());
   return 0;
 }
@@ -313,8 +340,9 @@ extern "C" int pc_stream_sync(pc_stream *st) {
   CU(cudaStreamSynchronize(st->s));
   Pending &P = st->pend;
   if (!P.active) return 0;
-  // Jobs that could not get scratch from the pool are re-run with a larger pool, a part at a time if needed.
-  for (int round = 0; round < 40; ++round) {
+  // Jobs whose scratch did not fit their warp's pool slot are re-run with fewer warps (= larger slots); the pool
+  // itself grows only when a single job needs more than all of it.
+  for (int round = 0; round < 64; ++round) {
     const int32_t *status = P.res;
     if (P.device_mode) {
       st->h_status.resize((size_t)P.njobs * PC_RES_INTS);
@@ -324,16 +352,21 @@ extern "C" int pc_stream_sync(pc_stream *st) {
     std::vector<uint32_t> redo;
     for (int i = 0; i < P.njobs; ++i) if (status[(size_t)i * PC_RES_INTS] == PC_E_POOL) redo.push_back((uint32_t)i);
     if (redo.empty()) break;
-    if (round >= 1 || st->pool.cap < (1ull << 30)) {
-      size_t want = st->pool.cap * 4;
+    const unsigned long long need = std::max<unsigned long long>(*st->h_pool_need, 4096) + 4096;
+    if (need > st->pool.cap) {
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
-      if (want > st->pool.cap + free_b / 2) want = st->pool.cap + free_b / 2;
-      if (want > st->pool.cap) { int rc = st->pool.reserve(want); if (rc) { P.active = false; return rc; } }
-      else if (redo.size() == 1) { P.active = false; return fail(PC_E_NOMEM, "%s", "a single job does not fit the device scratch pool"); }
+      if (need > st->pool.cap + free_b - (free_b >> 3)) {
+        P.active = false; st->max_warps = 0;
+        return fail(PC_E_NOMEM, "%s", "a single job needs more scratch than the device has free");
+      }
+      size_t want = std::min<size_t>(need * std::min<size_t>(redo.size(), 32), st->pool.cap + free_b / 2);
+      int rc = st->pool.reserve(std::max<size_t>(want, need));
+      if (rc) { P.active = false; st->max_warps = 0; return rc; }
     }
-    if (round >= 2 && redo.size() > 1) redo.resize((redo.size() + 1) / 2);   // still too much at once: halve the wave
+    st->max_warps = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(st->pool.cap / need, 1u << 20));
     int rc = launch_selected(st, P.jobs, redo, P.d_arena, P.d_jobs, P.d_res, P.d_var);
+    st->max_warps = 0;
     if (rc) { P.active = false; return rc; }
     if (!P.device_mode) {
       CU(cudaMemcpyAsync(P.res, P.d_res, sizeof(int32_t) * PC_RES_INTS * (size_t)P.njobs, cudaMemcpyDeviceToHost, st->s));

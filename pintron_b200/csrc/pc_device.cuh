@@ -17,9 +17,11 @@ struct PcDevBatch {
   int n;
   int32_t *res;
   uint8_t *var_out;
-  uint8_t *pool;              /* per-stream scratch pool, bump-allocated by the kernels */
+  uint8_t *pool;              /* per-stream scratch pool: one equal slot per warp of the launch, reused job after job */
   unsigned long long pool_cap;
-  unsigned long long *pool_used;
+  unsigned long long *pool_need;   /* atomicMax of the bytes a job wanted when its slot was too small */
+  int slots;                  /* warps in this launch (set by the launcher) */
+  int max_warps;              /* host hint: cap on the warps of a launch (retry rounds use fewer, larger slots) */
   /* k-mer index (SEED) */
   const unsigned long long *ix_keys;
   const uint32_t *ix_pos;
@@ -28,15 +30,26 @@ struct PcDevBatch {
   double depth_rate;
 };
 
-__device__ __forceinline__ uint8_t *pc_pool_alloc(const PcDevBatch &B, unsigned long long bytes, int lane) {
-  unsigned long long off = 0;
-  if (lane == 0) {
-    unsigned long long sz = (bytes + 255ull) & ~255ull;
-    off = atomicAdd(B.pool_used, sz);
-    if (off + sz > B.pool_cap) off = ~0ull;
+struct WarpPool { uint8_t *base; unsigned long long size, used; };
+
+__device__ __forceinline__ WarpPool pc_warp_pool(const PcDevBatch &B, int slot) {
+  WarpPool wp;
+  wp.size = (B.pool_cap / (unsigned long long)B.slots) & ~255ull;
+  wp.base = B.pool + wp.size * (unsigned long long)slot;
+  wp.used = 0;
+  return wp;
+}
+
+// All lanes of the warp call this with the same arguments and get the same pointer (nullptr = slot too small).
+__device__ __forceinline__ uint8_t *pc_pool_alloc(const PcDevBatch &B, WarpPool &wp, unsigned long long bytes, int lane) {
+  const unsigned long long sz = (bytes + 255ull) & ~255ull;
+  if (wp.used + sz > wp.size) {
+    if (lane == 0) atomicMax(B.pool_need, wp.used + sz);
+    return nullptr;
   }
-  off = __shfl_sync(0xffffffffu, off, 0);
-  return off == ~0ull ? nullptr : B.pool + off;
+  uint8_t *p = wp.base + wp.used;
+  wp.used += sz;
+  return p;
 }
 
 __device__ __forceinline__ bool pc_is_n(uint8_t c) { return c == 'n' || c == 'N'; }

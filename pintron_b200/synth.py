@@ -1,0 +1,138 @@
+"""Synthetic est-fact inputs of the shapes BASELINE.json names; fixed seeds, no datasets.
+
+genomic.txt / ests.txt text in the reference's input format (one FASTA genome record `>chrN:start:end:strand`,
+multi-FASTA ESTs with `/gb=` and `/clone_end=` header fields, io-multifasta.c:279-504) plus the simulated exon
+structure of every EST (used only to derive DP job shapes for the device-path bench, never as a truth for parity).
+"""
+import numpy as np
+
+COMP = bytes.maketrans(b"ACGTNacgtn", b"TGCANtgcan")
+
+CONFIGS = {
+    # name: genome nt, genes, exons/gene, exon len range, intron len range, reads, read len range, mRNA fraction
+    "C3": dict(genome=200_000, genes=1, exons=60, exon_len=(20, 90), intron_len=(80, 6000), reads=100_000,
+               read_len=(300, 800), err=0.01, seed=1003),
+    "C4": dict(genome=2_000_000, genes=8, exons=40, exon_len=(25, 300), intron_len=(80, 60000), reads=1_000_000,
+               read_len=(300, 800), err=0.01, seed=1004, mrna_frac=0.2, mrna_len=(1000, 6000)),
+    "tiny": dict(genome=20_000, genes=1, exons=12, exon_len=(25, 160), intron_len=(80, 1500), reads=64,
+                 read_len=(200, 500), err=0.01, seed=7),
+}
+
+
+def _rand_seq(rng, n):
+    return np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)]
+
+
+def _log_uniform(rng, lo, hi):
+    return int(round(np.exp(rng.uniform(np.log(lo), np.log(hi)))))
+
+
+class Synth:
+    def __init__(self, name="C3", reads=None, seed=None):
+        cfg = dict(CONFIGS[name])
+        if reads is not None:
+            cfg["reads"] = reads
+        if seed is not None:
+            cfg["seed"] = seed
+        self.cfg, self.name = cfg, name
+        rng = self.rng = np.random.default_rng(cfg["seed"])
+        G = cfg["genome"]
+        g = _rand_seq(rng, G).copy()
+        # ~1 % planted low-complexity / tandem repeats
+        for _ in range(max(1, G // 20000)):
+            unit = _rand_seq(rng, int(rng.integers(1, 5)))
+            ln = int(rng.integers(60, 200))
+            pos = int(rng.integers(0, G - ln))
+            g[pos:pos + ln] = np.resize(unit, ln)
+        # gene models
+        self.genes = []
+        span = G // cfg["genes"]
+        for gi in range(cfg["genes"]):
+            for _attempt in range(200):
+                ex = [_log_uniform(rng, *cfg["exon_len"]) for _ in range(cfg["exons"])]
+                it = [_log_uniform(rng, *cfg["intron_len"]) for _ in range(cfg["exons"] - 1)]
+                if sum(ex) + sum(it) < span - 2000:
+                    break
+            else:
+                scale = (span - 2000 - sum(ex)) / max(1, sum(it))
+                it = [max(60, int(x * scale)) for x in it]
+            pos = gi * span + int(rng.integers(500, max(501, span - (sum(ex) + sum(it)) - 500)))
+            exons = []
+            for k, el in enumerate(ex):
+                exons.append((pos, pos + el))
+                pos += el
+                if k < len(it):
+                    r = rng.random()
+                    don, acc = (b"GT", b"AG") if r < 0.94 else ((b"GC", b"AG") if r < 0.99 else (b"AT", b"AC"))
+                    g[pos:pos + 2] = np.frombuffer(don, dtype=np.uint8)
+                    g[pos + it[k] - 2:pos + it[k]] = np.frombuffer(acc, dtype=np.uint8)
+                    pos += it[k]
+            self.genes.append(exons)
+        self.genome = g.tobytes()
+        self.transcripts = []
+        for exons in self.genes:
+            t = b"".join(self.genome[a:b] for a, b in exons)
+            bounds = np.cumsum([0] + [b - a for a, b in exons])
+            self.transcripts.append((t, bounds, exons))
+
+    def genome_fasta(self):
+        G = len(self.genome)
+        lines = [f">chr1:1000001:{1000000 + G}:1".encode()]
+        lines += [self.genome[i:i + 70] for i in range(0, G, 70)]
+        return b"\n".join(lines) + b"\n"
+
+    def _mutate(self, s, err):
+        rng = self.rng
+        n = len(s)
+        r = rng.random(n)
+        if not (r < err).any():
+            return s
+        out = bytearray()
+        for i, c in enumerate(s):
+            x = r[i]
+            if x >= err:
+                out.append(c)
+            elif x < 0.6 * err:
+                out.append(b"ACGT"[int(rng.integers(0, 4))])
+            elif x < 0.8 * err:
+                out.append(b"ACGT"[int(rng.integers(0, 4))]); out.append(c)
+        return bytes(out)
+
+    def reads(self, start=0, count=None):
+        """Yield (header, sequence, exon_pieces, forward_sequence); exon_pieces = [(genome_start, genome_end)] of the
+        error-free read, forward_sequence = the read before the optional reverse-complement."""
+        cfg, rng = self.cfg, np.random.default_rng(self.cfg["seed"] * 7919 + start)
+        self.rng = rng
+        count = cfg["reads"] - start if count is None else count
+        for idx in range(start, start + count):
+            t, bounds, exons = self.transcripts[int(rng.integers(0, len(self.transcripts)))]
+            lo, hi = cfg["read_len"]
+            if cfg.get("mrna_frac") and rng.random() < cfg["mrna_frac"]:
+                lo, hi = cfg["mrna_len"]
+            ln = min(int(rng.integers(lo, hi + 1)), len(t))
+            s0 = int(rng.integers(0, len(t) - ln + 1))
+            pieces = []
+            for k, (a, b) in enumerate(exons):
+                x0, x1 = max(s0, bounds[k]), min(s0 + ln, bounds[k + 1])
+                if x0 < x1:
+                    pieces.append((a + int(x0 - bounds[k]), a + int(x1 - bounds[k])))
+            seq = self._mutate(t[s0:s0 + ln], cfg["err"])
+            if rng.random() < 0.002 * 50:          # ~0.2 % N overall, concentrated in 10 % of the reads
+                sa = bytearray(seq)
+                for _ in range(max(1, len(sa) // 50)):
+                    sa[int(rng.integers(0, len(sa)))] = ord("N")
+                seq = bytes(sa)
+            if rng.random() < 0.3:
+                seq += b"A" * int(rng.integers(15, 41))
+            end, fwd = "3'", seq
+            if rng.random() < 0.5:
+                seq = seq.translate(COMP)[::-1]
+                end = "5'"
+            yield f">/gb=SYN{idx:07d}/clone_end={end}".encode(), seq, pieces, fwd
+
+    def ests_fasta(self, start=0, count=None):
+        out = []
+        for h, s, _, _ in self.reads(start, count):
+            out.append(h)
+            out += [s[i:i + 70] for i in range(0, len(s), 70)]
+        return b"\n".join(out) + b"\n"
