@@ -1,0 +1,431 @@
+/* sched.c — the EST batcher: worker threads, fibers, and the GPU batch round-trip.
+ *
+ * Replaces the sequential hot loop of the reference (src/main-est-fact.c:249-291): every EST runs the same
+ * sequential per-EST code (compute_est_fact, src/compute-est-fact.c:192) on its own fiber; whenever that code needs
+ * a DP it queues jobs and yields.  A worker thread owns two groups of fibers and one pc_stream per group: while
+ * the jobs of group A are on the GPU it runs the fibers of group B, then swaps.  ESTs are dealt to threads from a
+ * shared counter; threads are spread over the configured GPUs (genome + index replicated per GPU, no collective:
+ * SURVEY.md §8(e)).
+ */
+#define _GNU_SOURCE
+#include "ef.h"
+#include <errno.h>
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdatomic.h>
+#include <sys/mman.h>
+#include <sys/time.h>
+#include <ucontext.h>
+#include <unistd.h>
+
+#define FIBER_STACK (512u << 10)
+
+double ef_now(void) {
+  struct timeval tv;
+  gettimeofday(&tv, NULL);
+  return (double)tv.tv_sec + 1e-6 * (double)tv.tv_usec;
+}
+
+/* ---- arena / buffers ------------------------------------------------------------------------------- */
+void *ar_alloc(ef_arena *a, size_t bytes) {
+  bytes = (bytes + 15u) & ~(size_t)15u;
+  ef_chunk *c = a->head;
+  if (!c || c->used + bytes > c->cap) {
+    size_t cap = 1u << 16;
+    if (c && c->cap * 2 > cap) cap = MIN2(c->cap * 2, (size_t)8 << 20);
+    if (cap < bytes + sizeof(ef_chunk) + 16) cap = bytes + sizeof(ef_chunk) + 16;
+    ef_chunk *n = malloc(cap);
+    if (!n) { fprintf(stderr, "* FATAL est-fact: out of memory\n"); exit(1); }
+    n->next = c; n->cap = cap; n->used = (sizeof(ef_chunk) + 15u) & ~(size_t)15u;
+    a->head = c = n;
+  }
+  void *p = (char *)c + c->used;
+  c->used += bytes;
+  memset(p, 0, bytes);
+  return p;
+}
+
+void ar_reset(ef_arena *a) {
+  while (a->head && a->head->next) { ef_chunk *n = a->head->next; free(a->head); a->head = n; }
+  if (a->head) a->head->used = (sizeof(ef_chunk) + 15u) & ~(size_t)15u;
+}
+
+void ar_free_all(ef_arena *a) {
+  while (a->head) { ef_chunk *n = a->head->next; free(a->head); a->head = n; }
+}
+
+static void buf_reserve(ef_buf *b, size_t extra) {
+  if (b->len + extra + 1 <= b->cap) return;
+  size_t cap = b->cap ? b->cap * 2 : 256;
+  while (cap < b->len + extra + 1) cap *= 2;
+  b->p = realloc(b->p, cap);
+  if (!b->p) { fprintf(stderr, "* FATAL est-fact: out of memory\n"); exit(1); }
+  b->cap = cap;
+}
+
+void buf_write(ef_buf *b, const void *src, size_t n) {
+  buf_reserve(b, n);
+  memcpy(b->p + b->len, src, n);
+  b->len += n;
+  b->p[b->len] = 0;
+}
+
+void buf_printf(ef_buf *b, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  char tmp[256];
+  int n = vsnprintf(tmp, sizeof tmp, fmt, ap);
+  va_end(ap);
+  if (n < (int)sizeof tmp) { buf_write(b, tmp, (size_t)n); return; }
+  buf_reserve(b, (size_t)n);
+  va_start(ap, fmt);
+  vsnprintf(b->p + b->len, (size_t)n + 1, fmt, ap);
+  va_end(ap);
+  b->len += (size_t)n;
+}
+
+void buf_free(ef_buf *b) { free(b->p); b->p = NULL; b->len = b->cap = 0; }
+
+/* ---- fibers ---------------------------------------------------------------------------------------- */
+enum { F_FREE = 0, F_RUNNABLE, F_WAITING, F_DONE };
+
+typedef struct ef_req { int op; ef_str a, b; int p0, p1, p2, out_cap; } ef_req;
+
+typedef struct fiber {
+  ucontext_t ctx;
+  void *stack;
+  int state;
+  size_t index;
+  ef_task task;
+  ef_req *reqs;
+  int nreq, capreq;
+  int base;                 /* index of this fiber's first job in the group's batch */
+  bool has_results;
+  struct group *grp;
+} fiber;
+
+typedef struct group {
+  pc_stream *st;
+  fiber *fibers;
+  int nfibers;
+  bool pending;
+  /* batch buffers (pinned) */
+  uint8_t *arena; size_t arena_cap, arena_len;
+  pc_job *jobs; int jobs_cap, njobs;
+  int32_t *res; size_t res_cap;
+  uint8_t *var; size_t var_cap, var_len;
+  struct worker *w;
+} group;
+
+typedef struct worker {
+  pthread_t th;
+  int id, device;
+  pc_ctx *ctx;
+  group g[2];
+  ucontext_t main_ctx;
+  const ef_config *cfg;
+  const ef_seq *gen;
+  ef_task_fn fn;
+  void *user;
+  uint64_t batches, jobs;
+  double gpu_wait;
+} worker;
+
+static _Atomic size_t g_next_item;
+static size_t g_n_items;
+static __thread fiber *tl_fiber;
+static __thread worker *tl_worker;
+static uint64_t g_batches, g_jobs;
+static double g_gpu_wait;
+static pthread_mutex_t g_stat_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static void die_pc(const char *what) {
+  fprintf(stderr, "* FATAL est-fact: %s: %s\n", what, pc_last_error());
+  exit(1);
+}
+
+static void *pinned_grow(void *old, size_t old_bytes, size_t new_bytes) {
+  void *p = pc_host_alloc(new_bytes);
+  if (!p) die_pc("pc_host_alloc");
+  if (old) { memcpy(p, old, old_bytes); pc_host_free(old); }
+  return p;
+}
+
+static void fiber_entry(void) {
+  fiber *f = tl_fiber;
+  worker *w = tl_worker;
+  w->fn(&f->task, f->index, w->user);
+  f->state = F_DONE;
+  swapcontext(&f->ctx, &w->main_ctx);
+}
+
+static void fiber_start(worker *w, group *g, fiber *f, size_t index) {
+  if (!f->stack) {
+    f->stack = mmap(NULL, FIBER_STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
+    if (f->stack == MAP_FAILED) { perror("mmap fiber stack"); exit(1); }
+    mprotect(f->stack, 4096, PROT_NONE);
+  }
+  getcontext(&f->ctx);
+  f->ctx.uc_stack.ss_sp = f->stack;
+  f->ctx.uc_stack.ss_size = FIBER_STACK;
+  f->ctx.uc_link = NULL;
+  makecontext(&f->ctx, fiber_entry, 0);
+  f->index = index;
+  f->state = F_RUNNABLE;
+  f->nreq = 0;
+  f->has_results = false;
+  f->grp = g;
+  ar_reset(&f->task.ar);
+  f->task.cfg = w->cfg;
+  f->task.gen = w->gen;
+}
+
+int dp_push(int op, ef_str a, ef_str b, int p0, int p1, int p2, int out_cap) {
+  fiber *f = tl_fiber;
+  if (f->has_results) { f->nreq = 0; f->has_results = false; }
+  if (f->nreq == f->capreq) {
+    f->capreq = f->capreq ? f->capreq * 2 : 16;
+    f->reqs = realloc(f->reqs, sizeof(ef_req) * (size_t)f->capreq);
+  }
+  ef_req *r = &f->reqs[f->nreq];
+  r->op = op; r->a = a; r->b = b; r->p0 = p0; r->p1 = p1; r->p2 = p2; r->out_cap = out_cap;
+  return f->nreq++;
+}
+
+void dp_wait(void) {
+  fiber *f = tl_fiber;
+  if (f->nreq == 0 || f->has_results) return;
+  f->state = F_WAITING;
+  swapcontext(&f->ctx, &tl_worker->main_ctx);
+  /* resumed: results are in the group's batch buffers */
+  for (int i = 0; i < f->nreq; ++i) {
+    const int32_t st = f->grp->res[(size_t)(f->base + i) * PC_RES_INTS];
+    if (st < 0 && st != PC_E_OUTCAP) {
+      fprintf(stderr, "* FATAL est-fact: device job (op %d) failed with status %d\n", f->reqs[i].op, st);
+      exit(1);
+    }
+  }
+}
+
+const int32_t *dp_res(int h) { fiber *f = tl_fiber; return f->grp->res + (size_t)(f->base + h) * PC_RES_INTS; }
+const uint8_t *dp_var(int h) { fiber *f = tl_fiber; return f->grp->var + f->grp->jobs[f->base + h].out_off; }
+
+unsigned dp_edit(const char *a, int la, const char *b, int lb) {
+  int h = dp_push(PC_OP_EDIT, S_(a, la), S_(b, lb), 0, 0, 0, 0);
+  dp_wait();
+  return (unsigned)dp_res(h)[1];
+}
+
+bool dp_borders(const char *p, int len_p, int min_cut, int max_cut, const char *t, int len_t, unsigned max_errs,
+                int *off_p, int *off_t1, int *off_t2, unsigned *ed) {
+  int h = dp_push(PC_OP_BORDERS, S_(p, len_p), S_(t, len_t), (int)max_errs, min_cut, max_cut, 0);
+  dp_wait();
+  const int32_t *r = dp_res(h);
+  *off_p = r[2]; *off_t1 = r[3]; *off_t2 = r[4]; *ed = (unsigned)r[5];
+  return r[1] != 0;
+}
+
+void dp_lcs(const char *s1, long l1, const char *s2, long l2, long *occ1, long *occ2, long *len) {
+  int h = dp_push(PC_OP_LCS, S_(s2, (int)l2), S_(s1, (int)l1), 0, 0, 0, 0);
+  dp_wait();
+  const int32_t *r = dp_res(h);
+  *len = r[1]; *occ1 = r[2]; *occ2 = r[3];
+}
+
+ef_aln aln_from_ops(ef_task *T, const uint8_t *ops, int n, const char *est, const char *gen) {
+  ef_aln A;
+  char *m = ar_alloc(&T->ar, 2 * ((size_t)n + 48));
+  A.est = m + 16; A.gen = m + n + 48 + 16; A.dim = n; A.score = 0;
+  int i = 0, j = 0;
+  for (int k = 0; k < n; ++k) {
+    if (ops[k] == 0) { A.est[k] = est[i++]; A.gen[k] = gen[j++]; }
+    else if (ops[k] == 1) { A.est[k] = est[i++]; A.gen[k] = '-'; }
+    else { A.est[k] = '-'; A.gen[k] = gen[j++]; }
+  }
+  return A;
+}
+
+/* ---- batching -------------------------------------------------------------------------------------------- */
+static void gather(group *g) {
+  g->arena_len = 0; g->njobs = 0; g->var_len = 0;
+  for (int k = 0; k < g->nfibers; ++k) {
+    fiber *f = &g->fibers[k];
+    if (f->state != F_WAITING) continue;
+    f->base = g->njobs;
+    for (int i = 0; i < f->nreq; ++i) {
+      const ef_req *r = &f->reqs[i];
+      const size_t need = (size_t)r->a.len + (size_t)(r->b.in_genome ? 0 : r->b.len) + 8;
+      if (g->arena_len + need > g->arena_cap) {
+        size_t nc = MAX2(g->arena_cap * 2, g->arena_len + need + (1u << 20));
+        g->arena = pinned_grow(g->arena, g->arena_len, nc);
+        g->arena_cap = nc;
+      }
+      if (g->njobs == g->jobs_cap) {
+        int nc = g->jobs_cap ? g->jobs_cap * 2 : 4096;
+        g->jobs = pinned_grow(g->jobs, sizeof(pc_job) * (size_t)g->njobs, sizeof(pc_job) * (size_t)nc);
+        g->jobs_cap = nc;
+      }
+      pc_job *j = &g->jobs[g->njobs++];
+      memset(j, 0, sizeof *j);
+      j->op = (uint32_t)r->op;
+      j->a_off = (uint32_t)g->arena_len; j->a_len = (uint32_t)r->a.len;
+      if (r->a.len) memcpy(g->arena + g->arena_len, r->a.p, (size_t)r->a.len);
+      g->arena_len += (size_t)r->a.len;
+      if (r->b.in_genome) { j->flags = PC_B_IN_GENOME; j->b_off = (uint32_t)r->b.gen_off; j->b_len = (uint32_t)r->b.len; }
+      else {
+        j->b_off = (uint32_t)g->arena_len; j->b_len = (uint32_t)r->b.len;
+        /* BORDERS reads the byte that follows t (refine.c:362-374); callers keep it addressable */
+        const size_t nb = (size_t)r->b.len + (r->op == PC_OP_BORDERS ? 1u : 0u);
+        if (nb) memcpy(g->arena + g->arena_len, r->b.p, nb);
+        g->arena_len += nb;
+      }
+      j->p0 = r->p0; j->p1 = r->p1; j->p2 = r->p2;
+      if (r->op == PC_OP_ALIGN || r->op == PC_OP_GAP) {
+        j->out_cap = (uint32_t)(r->a.len + r->b.len);
+        j->out_off = (uint32_t)g->var_len; g->var_len += j->out_cap;
+      } else if (r->op == PC_OP_SEED) {
+        g->var_len = (g->var_len + 3u) & ~(size_t)3u;
+        j->out_cap = (uint32_t)r->out_cap;
+        j->out_off = (uint32_t)g->var_len; g->var_len += 12u * (size_t)r->out_cap;
+      }
+    }
+  }
+  if (g->njobs == 0) return;
+  if ((size_t)g->njobs * PC_RES_INTS > g->res_cap) {
+    size_t nc = MAX2(g->res_cap * 2, (size_t)g->njobs * PC_RES_INTS + 4096);
+    if (g->res) pc_host_free(g->res);
+    g->res = pc_host_alloc(nc * sizeof(int32_t));
+    if (!g->res) die_pc("pc_host_alloc");
+    g->res_cap = nc;
+  }
+  if (g->var_len > g->var_cap) {
+    size_t nc = MAX2(g->var_cap * 2, g->var_len + (1u << 20));
+    if (g->var) pc_host_free(g->var);
+    g->var = pc_host_alloc(nc);
+    if (!g->var) die_pc("pc_host_alloc");
+    g->var_cap = nc;
+  }
+  if (g->arena_len >= 0xfff00000u || g->var_len >= 0xfff00000u) {
+    fprintf(stderr, "* FATAL est-fact: one batch exceeds 4 GiB; lower --fibers\n");
+    exit(1);
+  }
+}
+
+static bool run_group(worker *w, group *g) {
+  /* returns false when the group has nothing left to do and no new item could be started */
+  if (g->pending) {
+    const double t0 = ef_now();
+    if (pc_stream_sync(g->st)) die_pc("pc_stream_sync");
+    w->gpu_wait += ef_now() - t0;
+    g->pending = false;
+    for (int k = 0; k < g->nfibers; ++k)
+      if (g->fibers[k].state == F_WAITING) { g->fibers[k].state = F_RUNNABLE; g->fibers[k].has_results = true; }
+  }
+  bool any = false;
+  for (int k = 0; k < g->nfibers; ++k) {
+    fiber *f = &g->fibers[k];
+    for (;;) {
+      if (f->state == F_FREE || f->state == F_DONE) {
+        size_t idx = atomic_fetch_add(&g_next_item, 1);
+        if (idx >= g_n_items) { f->state = F_FREE; break; }
+        fiber_start(w, g, f, idx);
+      }
+      if (f->state != F_RUNNABLE) break;
+      tl_fiber = f;
+      swapcontext(&w->main_ctx, &f->ctx);
+      tl_fiber = NULL;
+      if (f->state == F_WAITING) break;       /* F_DONE: loop to pick the next item */
+    }
+    if (f->state == F_WAITING) any = true;
+  }
+  if (!any) return false;
+  gather(g);
+  if (g->njobs) {
+    if (pc_submit(g->st, g->arena, g->arena_len, g->jobs, g->njobs, g->res, g->var, g->var_len)) die_pc("pc_submit");
+    g->pending = true;
+    w->batches++; w->jobs += (uint64_t)g->njobs;
+  }
+  return true;
+}
+
+static void *worker_main(void *arg) {
+  worker *w = arg;
+  tl_worker = w;
+  for (int i = 0; i < 2; ++i) {
+    w->g[i].st = pc_stream_create(w->ctx);
+    if (!w->g[i].st) die_pc("pc_stream_create");
+    w->g[i].w = w;
+  }
+  bool alive[2] = {true, true};
+  while (alive[0] || alive[1]) {
+    for (int i = 0; i < 2; ++i)
+      if (alive[i] || w->g[i].pending) alive[i] = run_group(w, &w->g[i]);
+  }
+  for (int i = 0; i < 2; ++i) {
+    group *g = &w->g[i];
+    for (int k = 0; k < g->nfibers; ++k) {
+      fiber *f = &g->fibers[k];
+      if (f->stack) munmap(f->stack, FIBER_STACK);
+      ar_free_all(&f->task.ar);
+      free(f->reqs);
+    }
+    free(g->fibers);
+    pc_host_free(g->arena); pc_host_free(g->jobs); pc_host_free(g->res); pc_host_free(g->var);
+    pc_stream_destroy(g->st);
+  }
+  pthread_mutex_lock(&g_stat_mu);
+  g_batches += w->batches; g_jobs += w->jobs; g_gpu_wait += w->gpu_wait;
+  pthread_mutex_unlock(&g_stat_mu);
+  return NULL;
+}
+
+void sched_stats(double *gpu_wait_s, uint64_t *batches, uint64_t *jobs) {
+  if (gpu_wait_s) *gpu_wait_s = g_gpu_wait;
+  if (batches) *batches = g_batches;
+  if (jobs) *jobs = g_jobs;
+}
+
+int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_fn fn, void *user) {
+  int ndev = pc_device_count();
+  if (ndev <= 0) {
+    fprintf(stderr, "* FATAL est-fact: no CUDA device available (%s). This build has no CPU path.\n", pc_last_error());
+    return 1;
+  }
+  int use[16], nuse = 0;
+  if (cfg->n_devices > 0) {
+    for (int i = 0; i < cfg->n_devices; ++i) {
+      if (cfg->devices[i] < 0 || cfg->devices[i] >= ndev) { fprintf(stderr, "* FATAL est-fact: device %d not present\n", cfg->devices[i]); return 1; }
+      use[nuse++] = cfg->devices[i];
+    }
+  } else use[nuse++] = 0;
+  pc_ctx *ctxs[16];
+  for (int i = 0; i < nuse; ++i) {
+    ctxs[i] = pc_ctx_create(use[i]);
+    if (!ctxs[i]) die_pc("pc_ctx_create");
+    if (pc_genome_upload(ctxs[i], gen->seq, (size_t)gen->len, (int)cfg->min_factor_len, cfg->min_string_depth_rate))
+      die_pc("pc_genome_upload");
+  }
+  int nthreads = cfg->threads > 0 ? cfg->threads : (int)sysconf(_SC_NPROCESSORS_ONLN);
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > n_items) nthreads = n_items ? (int)n_items : 1;
+  int per_group = cfg->fibers > 0 ? cfg->fibers : 256;
+  if ((size_t)per_group * 2 * (size_t)nthreads > n_items) per_group = (int)(n_items / (2 * (size_t)nthreads)) + 1;
+  atomic_store(&g_next_item, 0);
+  g_n_items = n_items;
+  g_batches = g_jobs = 0; g_gpu_wait = 0;
+  worker *ws = calloc((size_t)nthreads, sizeof(worker));
+  for (int i = 0; i < nthreads; ++i) {
+    worker *w = &ws[i];
+    w->id = i; w->device = use[i % nuse]; w->ctx = ctxs[i % nuse];
+    w->cfg = cfg; w->gen = gen; w->fn = fn; w->user = user;
+    for (int k = 0; k < 2; ++k) {
+      w->g[k].nfibers = per_group;
+      w->g[k].fibers = calloc((size_t)per_group, sizeof(fiber));
+    }
+    if (pthread_create(&w->th, NULL, worker_main, w)) { perror("pthread_create"); return 1; }
+  }
+  for (int i = 0; i < nthreads; ++i) pthread_join(ws[i].th, NULL);
+  free(ws);
+  for (int i = 0; i < nuse; ++i) pc_ctx_destroy(ctxs[i]);
+  return 0;
+}
