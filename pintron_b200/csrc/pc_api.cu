@@ -194,6 +194,13 @@ static cudaEvent_t get_event(pc_stream *st) {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 
+// GAP jobs that fit the packed register kernel (k_gap.cu): class by the number of EST rows; 3 = generic kernel.
+static int gap_class(const pc_job &j) {
+  if (j.op != PC_OP_GAP) return 0;
+  if (j.a_len < 1 || j.b_len < 1 || j.b_len > 4096 || j.a_len > 256) return 3;
+  return j.a_len <= 64 ? 0 : (j.a_len <= 128 ? 1 : 2);
+}
+
 static double job_cost(const pc_job &j) {
   switch (j.op) {
     case PC_OP_LCS: case PC_OP_SEED: return (double)j.a_len + j.b_len;
@@ -210,16 +217,22 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
   std::vector<uint32_t> &order = st->h_idx;
   order.resize(sel.size());
   {
-    const int NB = PC_OP_COUNT * 64;
+    const int NB = PC_OP_COUNT * 4 * 64;
     std::vector<uint32_t> bins(NB + 1, 0);
     std::vector<uint16_t> key(sel.size());
     for (size_t q = 0; q < sel.size(); ++q) {
       const pc_job &j = h_jobs[sel[q]];
       if (j.op >= PC_OP_COUNT) return fail(PC_E_ARG, "%s", "pc_submit: unknown op");
+      const int cls = gap_class(j);
       int lg = 0;
-      unsigned long long c = (unsigned long long)job_cost(j) + 1;
-      while (c >>= 1) ++lg;
-      key[q] = (uint16_t)(j.op * 64 + (63 - lg));
+      if (j.op == PC_OP_GAP && cls < 3) {        // paired jobs run max(m) steps: order by m, finely
+        const uint32_t m = j.b_len;
+        lg = m < 512 ? (int)(m >> 4) : 32 + (int)std::min<uint32_t>(31, (m - 512) >> 7);
+      } else {
+        unsigned long long c = (unsigned long long)job_cost(j) + 1;
+        while (c >>= 1) ++lg;
+      }
+      key[q] = (uint16_t)((j.op * 4 + cls) * 64 + (63 - lg));
       ++bins[key[q] + 1];
     }
     for (int b = 0; b < NB; ++b) bins[b + 1] += bins[b];
@@ -237,9 +250,10 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
   size_t i = 0;
   while (i < order.size()) {
     const uint32_t op = h_jobs[order[i]].op;
+    const int cls = gap_class(h_jobs[order[i]]);
     size_t j = i;
     long long max_l1 = 0; int max_l2 = 0;
-    while (j < order.size() && h_jobs[order[j]].op == op) {
+    while (j < order.size() && h_jobs[order[j]].op == op && gap_class(h_jobs[order[j]]) == cls) {
       max_l1 = std::max<long long>(max_l1, h_jobs[order[j]].b_len);
       max_l2 = std::max<int>(max_l2, (int)h_jobs[order[j]].a_len);
       ++j;
@@ -256,6 +270,8 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
     } else if (op == PC_OP_LCS) {
       if (st->lcs_best.reserve(8ull * B.n)) return PC_E_NOMEM;
       pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, max_l1, max_l2, st->s);
+    } else if (op == PC_OP_GAP && cls < 3) {
+      pc_launch_gap_pairs(cls, B, (int)max_l1, st->s, c->sm_count);
     } else {
       pc_launch_dp((int)op, B, st->s, c->sm_count);
     }

@@ -214,3 +214,30 @@ def test_properties_at_scale(cu):
     assert s0 == 0 and set(ops0) == {0}
     ln, o1, o2 = cu.find_longest_common_factor_dp(a, a[30000:30040])
     assert ln == 40 and a[o1:o1 + ln] == a[30000:30040] and o2 == 0
+
+
+def test_gap_packed_classes_vs_port(cu, port):
+    """The 16x2-packed gap kernel: every row class (n <= 64 / 128 / 256), the generic fallback (n > 256), ragged pairs
+    (odd job counts, very different n and m inside a pair), N wildcards and lower case, against the oracle."""
+    g = Gen(777)
+    r = g.rnd
+    b, cases = Batch(), []
+    for it in range(1501):
+        n = r.choice([1, 2, 7, 8, 9, 30, 59, 60, 61, 64, 65, 100, 128, 129, 200, 256, 257, 300])
+        m = r.choice([1, 2, 3, 50, 100, 199, 200, 201, 260, 400])
+        if it % 4 == 0:
+            est, gen = g.gap_case()
+        else:
+            ex1, ex2 = g.rs(n // 2), g.rs(n - n // 2)
+            est = g.mutate(ex1 + ex2, r.choice([0, 0.03, 0.15]), alpha="ACGTNn") or b"A"
+            gen = (ex1 + g.rs(max(0, m - n)) + ex2)[:max(1, m)] if m >= n else g.rs(m)
+            if it % 9 == 0:
+                gen = gen.lower()[:len(gen) // 2] + gen[len(gen) // 2:]
+        b.add(PC_OP.GAP, est, gen); cases.append((est, gen))
+    res, var = cu.run(b)
+    _, jobs = b.arrays()
+    for (est, gen), rr, j in zip(cases, res, jobs):
+        ops, pos = port.gap(est, gen)
+        assert rr[0] == 0, (len(est), len(gen), list(rr))
+        assert var[j["out_off"]:j["out_off"] + rr[1]].tobytes() == ops, (len(est), len(gen))
+        assert list(rr[2:7]) == pos, (len(est), len(gen))
