@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <limits.h>
 #include "pintron_cuda.h"
 
@@ -153,7 +154,7 @@ void refine_factorizations(ef_task *T, const ef_seq *est, ef_fzlist *L);        
 bool refine_intron(ef_task *T, const ef_seq *est, ef_factor *donor, ef_factor *acceptor, bool first_intron);
 int burset_freq(const char *donor, const char *acceptor);           /* getBursetFrequency */
 int burset_adaptor(const char *t, size_t cut1, size_t cut2);        /* getBursetFrequency_adaptor */
-char classify_intron(const char *gen, int start, int end);          /* 0 = U12, 1 = U2, 2 = not determined */
+char classify_intron(const char *gen, int glen, int start, int end);   /* 0 = U12, 1 = U2, 2 = not determined */
 double dust_score(const char *s, int len);
 
 /* shared by est_factorizations and refine_factorizations */

@@ -303,7 +303,7 @@ static void mask_end(ef_seq *e, bool suffix) {
   const size_t W = 14, n = strlen(e->seq);
   const double FR = 0.72;
   char *s = e->seq;
-#define AT(i) (suffix ? s[n - (i) - 1] : s[(i)])
+#define AT(i) (*(suffix ? &s[n - (i) - 1] : &s[(i)]))
   size_t cA = 0, cT = 0, rA, rT, lastA = 0, lastT = 0, lastAc = 0, lastTc = 0, i;
   for (i = 0; i < W && i < n; ++i) {
     if (AT(i) == 'A') { ++cA; lastA = i; lastAc = cA; }

@@ -1,0 +1,186 @@
+/* main.c — the est-fact program: same command line, same files in the working directory, same output bytes as
+ * reference src/main-est-fact.c:90-339, with the per-EST work (src/compute-est-fact.c:192-293) spread over fibers,
+ * threads and GPUs by sched.c.  Inputs ./genomic.txt and ./ests.txt; outputs raw-multifasta-out.txt,
+ * processed-ests.txt (the two the pipeline consumes), megs.txt, processed-megs.txt, meg-edges.txt,
+ * processed-megs-info.txt, info-pid-<pid>.log, config-dump.ini.
+ *
+ * One scheduler item = one input EST: its forward copy and, when the strand is not fixed and the forward copy gave
+ * no factorization, its reverse-complement copy (main-est-fact.c:249-291) — so the order of the records written
+ * for one EST never depends on other ESTs, and shards of ests.txt concatenate to the single-run output.
+ */
+#define _GNU_SOURCE
+#include "ef.h"
+#include <unistd.h>
+
+typedef struct est_item {
+  ef_seq fwd, rc;
+  bool has_rc;
+  ef_buf raw, pest, megs, pmegs, edges, info;
+} est_item;
+
+typedef struct run_ctx {
+  const ef_config *cfg;
+  const ef_seq *gen;
+  const char *gen_orig;          /* the genome before N-tail removal (output bytes come from here) */
+  est_item *items;
+} run_ctx;
+
+static void write_est_record(ef_buf *b, const ef_seq *e) { buf_printf(b, ">%s\n", e->id); buf_write(b, e->orig, strlen(e->orig)); buf_write(b, "\n", 1); }
+
+/* write_multifasta_output (src/io-multifasta.c:187-241) */
+static void write_factorizations(ef_buf *b, const run_ctx *R, const ef_seq *e, const ef_fzlist *L, const bool *polya, const bool *polyad) {
+  const bool keep_ext = R->cfg->retain_externals;
+  for (int k = 0; k < L->n; ++k) {
+    const ef_fz *z = L->v[k];
+    if (!(keep_ext || z->n > 2 || (z->n == 2 && e->suff_polyA != -1))) continue;
+    buf_printf(b, ">%s\n", e->id);
+    buf_printf(b, "#polya=%d\n#polyad=%d\n", keep_ext ? (int)polya[k] : 0, keep_ext ? (int)polyad[k] : 0);
+    const unsigned l_index = keep_ext ? 0u : 1u;
+    const unsigned r_index = keep_ext ? (unsigned)z->n + 1u : (e->suff_polyA == -1 ? (unsigned)z->n : (unsigned)z->n + 1u);
+    for (unsigned counter = 1; counter <= (unsigned)z->n; ++counter) {
+      const ef_factor *f = &z->f[counter - 1];
+      if (!(counter > l_index && counter < r_index)) continue;
+      buf_printf(b, "%d %d %d %d ", f->es + 1, f->ee + 1, R->gen->pref_N + f->gs + 1, R->gen->pref_N + f->ge + 1);
+      const int el = f->ee + 1 - f->es, gl = f->ge + 1 - f->gs;
+      if (el > 0) buf_write(b, e->orig + f->es, strnlen(e->orig + f->es, (size_t)el));
+      buf_write(b, " ", 1);
+      if (gl > 0) buf_write(b, R->gen_orig + R->gen->pref_N + f->gs, strnlen(R->gen_orig + R->gen->pref_N + f->gs, (size_t)gl));
+      buf_write(b, "\n", 1);
+    }
+  }
+}
+
+/* compute_est_fact (src/compute-est-fact.c:192-293) for one strand copy; true when it produced factorizations */
+static bool compute_est_fact(ef_task *T, const run_ctx *R, est_item *it, const ef_seq *e) {
+  unsigned inc = 0;
+  size_t prev_p = 0, prev_e = 0;
+  for (;;) {
+    size_t tp, te;
+    ef_meg *M;
+    const double t_meg0 = ef_now();
+    for (;;) {
+      M = meg_build(T, e, &inc);
+      meg_stats(M, &tp, &te);
+      const bool same = prev_p > 2 && prev_e > 0 && (prev_p <= tp || prev_e <= te);
+      if (!same) break;
+      ++inc;
+    }
+    prev_p = tp; prev_e = te;
+    const double t_meg1 = ef_now();
+    T->t_start = ef_now();
+    bool timed_out = false;
+    ef_fzlist *L = est_factorizations(T, e, M, &timed_out);
+    bool *polya = NULL, *polyad = NULL;
+    if (L) {
+      polya = ar_alloc(&T->ar, (size_t)L->n + 1); polyad = ar_alloc(&T->ar, (size_t)L->n + 1);
+      for (int k = 0; k < L->n; ++k) { polya[k] = L->v[k]->polya; polyad[k] = L->v[k]->polyad; }
+      refine_factorizations(T, e, L);
+    }
+    timed_out = timed_out || ef_timeout_expired(T);
+    const double t_comp1 = ef_now();
+    const bool got = L && L->n > 0;
+    if (!timed_out || got) {
+      buf_printf(&it->megs, "\n\n***********\n\n");
+      write_est_record(&it->megs, e);
+      meg_write(&it->megs, M);
+    }
+    if (got) {
+      buf_printf(&it->edges, ">%s\n", e->id);
+      meg_write_edges(&it->edges, M);
+      write_est_record(&it->pmegs, e);
+      meg_write(&it->pmegs, M);
+      buf_printf(&it->info, "%llu %llu %zu\n", (unsigned long long)((t_meg1 - t_meg0) * 1e6), (unsigned long long)((t_comp1 - t_meg1) * 1e6), (size_t)L->n);
+      write_factorizations(&it->raw, R, e, L, polya, polyad);
+      write_est_record(&it->pest, e);
+      return true;
+    }
+    if (!timed_out) return false;
+    ++inc;                       /* timed out without a result: retry with longer pairings */
+  }
+}
+
+static void est_task(ef_task *T, size_t index, void *user) {
+  run_ctx *R = user;
+  est_item *it = &R->items[index];
+  if (compute_est_fact(T, R, it, &it->fwd)) return;
+  if (it->has_rc) {
+    ar_reset(&T->ar);
+    compute_est_fact(T, R, it, &it->rc);
+  }
+}
+
+static FILE *open_out(const char *name) {
+  FILE *f = fopen(name, "w");
+  if (!f) { fprintf(stderr, "* FATAL Cannot create file %s! Terminating\n", name); exit(1); }
+  return f;
+}
+
+int main(int argc, char **argv) {
+  const double t0 = ef_now();
+  ef_config cfg;
+  if (ef_config_parse(&cfg, argc, argv)) return 1;
+  if (!cfg.quiet) fprintf(stderr, "* INFO  EST-FACTORIZATION v2 (B200 build)\n");
+  char name[64];
+  snprintf(name, sizeof name, "info-pid-%u.log", (unsigned)getpid());
+  FILE *finfo = open_out(name);
+  fprintf(finfo, "start\t%ld\n", (long)time(NULL));
+
+  const double t_io0 = ef_now();
+  ef_seq *gens = NULL; size_t ngen = 0;
+  if (ef_read_fasta("genomic.txt", &gens, &ngen)) { fprintf(stderr, "* FATAL File genomic.txt not found! Terminating\n"); return 1; }
+  if (ngen != 1) { fprintf(stderr, "* FATAL genomic.txt must hold exactly one sequence (found %zu)\n", ngen); return 1; }
+  ef_seq *gen = &gens[0];
+  ef_parse_genomic_header(gen);
+  ef_ntails_removal(gen);
+  ef_seq *ests = NULL; size_t nest = 0;
+  if (ef_read_fasta("ests.txt", &ests, &nest)) { fprintf(stderr, "* FATAL File ests.txt not found! Terminating\n"); return 1; }
+  FILE *f_raw = open_out("raw-multifasta-out.txt"), *f_megs = open_out("megs.txt"), *f_pmegs = open_out("processed-megs.txt");
+  FILE *f_info = open_out("processed-megs-info.txt"), *f_pest = open_out("processed-ests.txt"), *f_edges = open_out("meg-edges.txt");
+  double t_io = ef_now() - t_io0;
+  if (!cfg.quiet) fprintf(stderr, "* INFO  Read %zu sequences.\n", nest);
+
+  est_item *items = calloc(nest ? nest : 1, sizeof *items);
+  for (size_t i = 0; i < nest; ++i) {
+    est_item *it = &items[i];
+    it->fwd = ests[i];
+    ef_set_gb(&it->fwd);
+    ef_set_strand_and_rc(&it->fwd);
+    it->fwd.len = (int)strlen(it->fwd.seq);
+    ef_polyAT_substitution(&it->fwd);
+    if (!it->fwd.fixed_strand) { ef_make_rc_copy(&it->fwd, &it->rc); it->rc.len = it->fwd.len; it->has_rc = true; }
+  }
+
+  run_ctx R = {&cfg, gen, gen->orig, items};
+  const double t_alg0 = ef_now();
+  if (sched_run(&cfg, gen, nest, est_task, &R)) return 1;
+  const double t_alg = ef_now() - t_alg0;
+
+  const double t_io1 = ef_now();
+  for (size_t i = 0; i < nest; ++i) {
+    est_item *it = &items[i];
+    if (it->raw.len) fwrite(it->raw.p, 1, it->raw.len, f_raw);
+    if (it->pest.len) fwrite(it->pest.p, 1, it->pest.len, f_pest);
+    if (it->megs.len) fwrite(it->megs.p, 1, it->megs.len, f_megs);
+    if (it->pmegs.len) fwrite(it->pmegs.p, 1, it->pmegs.len, f_pmegs);
+    if (it->edges.len) fwrite(it->edges.p, 1, it->edges.len, f_edges);
+    if (it->info.len) fwrite(it->info.p, 1, it->info.len, f_info);
+  }
+  fclose(f_raw); fclose(f_megs); fclose(f_pmegs); fclose(f_info); fclose(f_pest); fclose(f_edges);
+  t_io += ef_now() - t_io1;
+  fprintf(finfo, "end\t%ld\n", (long)time(NULL));
+  fclose(finfo);
+
+  double gpu_wait; uint64_t batches, jobs;
+  sched_stats(&gpu_wait, &batches, &jobs);
+  const double t_tot = ef_now() - t0;
+  /* the five timers of the reference (main-est-fact.c:321-325); index build and per-EST work both live in "Algorithm" */
+  fprintf(stderr, "@Timer Suffix Tree. Time elapsed: %llu microsec\n", 0ull);
+  fprintf(stderr, "@Timer Algorithm. Time elapsed: %llu microsec\n", (unsigned long long)(t_alg * 1e6));
+  fprintf(stderr, "@Timer Compositions. Time elapsed: %llu microsec\n", 0ull);
+  fprintf(stderr, "@Timer IO. Time elapsed: %llu microsec\n", (unsigned long long)(t_io * 1e6));
+  fprintf(stderr, "@Timer Total. Time elapsed: %llu microsec\n", (unsigned long long)(t_tot * 1e6));
+  if (!cfg.quiet)
+    fprintf(stderr, "* INFO  device batches: %llu, device jobs: %llu, summed wait on device: %.3f s, ESTs/s: %.1f\n",
+            (unsigned long long)batches, (unsigned long long)jobs, gpu_wait, t_alg > 0 ? (double)nest / t_alg : 0.0);
+  return 0;
+}

@@ -1,0 +1,305 @@
+/* refine_fact.c — the post-factorization refinement of one EST (reference src/factorization-refinement.c).
+ *
+ * refine_EST_factorizations :1269-1305 = remove_invalid_factorizations :120, remove_duplicated_factorizations :174,
+ * recover_lost_prefixes_and_suffixes :1175 (find_longest_affix :1134 -> PC_OP_AFFIX), remove_false_small_exons :1095
+ * (analyze_possibly_small_exon :958 -> PC_OP_EDIT x3 + PC_OP_BORDERS), search_for_new_small_exons :873
+ * (search_small_exon_at_prefix :498 -> PC_OP_LCS over the genome prefix + PC_OP_BORDERS; search_small_exon :639 ->
+ * PC_OP_EDIT, PC_OP_LCS and the strstr / PWM scan, which stays on the host), clean_factorizations :909; followed, as
+ * in src/compute-est-fact.c:169-175, by remove_factorizations_with_very_small_exons :84 and a second de-duplication.
+ * Lengths are size_t where the reference's are: several guards rely on unsigned wrap-around.
+ */
+#include "ef.h"
+
+#define UB_VERY_SMALL_EXON 2
+#define LB_SMALL_EXON 6
+#define UB_SMALL_EXON 23
+#define UB_MED_EXON 100
+#define AFFIXES_LENGTH 5
+#define MAX_ERROR_RATE 0.17
+#define MIN_PERFECT_BORDER 6
+#define MAX_ERRORS_AS_SMALL 2
+
+static void remove_invalid(ef_fzlist *L) {
+  for (int k = 0; k < L->n;) {
+    const ef_fz *z = L->v[k];
+    bool bad = false;
+    for (int i = 0; i < z->n && !bad; ++i) {
+      const ef_factor *f = &z->f[i];
+      bad = f->es > f->ee || f->gs > f->ge;
+      if (!bad && i > 0) bad = z->f[i - 1].ee >= f->es || z->f[i - 1].ge >= f->gs;
+    }
+    if (bad) fzl_remove(L, k); else ++k;
+  }
+}
+
+/* the reference's hash pre-filter never hides a true duplicate, so this is the plain pairwise check: a
+ * factorization equal to an earlier surviving one is dropped */
+static void remove_duplicates(ef_fzlist *L) {
+  for (int k = 0; k < L->n;) {
+    bool dup = false;
+    for (int q = 0; q < k && !dup; ++q) {
+      const ef_fz *a = L->v[k], *b = L->v[q];
+      dup = a->n == b->n && memcmp(a->f, b->f, sizeof(ef_factor) * (size_t)a->n) == 0;
+    }
+    if (dup) fzl_remove(L, k); else ++k;
+  }
+}
+
+static void remove_very_small_exons(ef_fzlist *L) {
+  for (int k = 0; k < L->n;) {
+    const ef_fz *z = L->v[k];
+    bool small = false;
+    for (int i = 0; i < z->n && !small; ++i) small = z->f[i].ee + 1 - z->f[i].es <= UB_VERY_SMALL_EXON;
+    if (small) fzl_remove(L, k); else ++k;
+  }
+}
+
+static char *rev_copy(ef_task *T, const char *s, size_t n) {
+  char *r = ar_alloc(&T->ar, n + 1);
+  for (size_t i = 0; i < n; ++i) r[i] = s[n - 1 - i];
+  return r;
+}
+
+/* one AFFIX job per end that still mismatches on its border; all ends of all factorizations in one batch */
+static void recover_lost_affixes(ef_task *T, const ef_seq *est, ef_fzlist *L) {
+  const char *e = est->seq, *g = T->gen->seq;
+  const size_t totelen = (size_t)est->len, totglen = (size_t)T->gen->len;
+  int *hp = ar_alloc(&T->ar, sizeof(int) * (size_t)(L->n + 1)), *hs = ar_alloc(&T->ar, sizeof(int) * (size_t)(L->n + 1));
+  for (int k = 0; k < L->n; ++k) {
+    ef_fz *z = L->v[k];
+    hp[k] = hs[k] = -1;
+    const ef_factor *ff = &z->f[0], *fl = &z->f[z->n - 1];
+    if (ff->es > 0 && ff->gs > 0) {
+      const size_t flen = (size_t)MIN2(ff->es, ff->gs);
+      const size_t elen = (size_t)MIN2(ff->es, (int)((1.0 + MAX_ERROR_RATE) * flen));
+      const size_t glen = (size_t)MIN2(ff->gs, (int)((1.0 + MAX_ERROR_RATE) * flen));
+      char *ef = rev_copy(T, e + ff->es - elen, elen), *gf = rev_copy(T, g + ff->gs - glen, glen);
+      if (ef[0] != gf[0]) hp[k] = dp_push(PC_OP_AFFIX, S_(ef, (int)elen), S_(gf, (int)glen), 0, 0, 0, 0);
+    }
+    if (totelen - (size_t)fl->ee > 1 && totglen - (size_t)fl->ge > 1) {
+      const size_t flen = MIN2(totelen - (size_t)fl->ee - 1, totglen - (size_t)fl->ge - 1);
+      const size_t elen = MIN2(totelen - (size_t)fl->ee - 1, (size_t)((int)(1.0 + MAX_ERROR_RATE)) * flen);   /* the cast binds first */
+      const size_t glen = MIN2(totglen - (size_t)fl->ge - 1, (size_t)((int)(1.0 + MAX_ERROR_RATE)) * flen);
+      if (e[fl->ee] != g[fl->ge]) hs[k] = dp_push(PC_OP_AFFIX, S_(e + fl->ee, (int)elen), S_(g + fl->ge, (int)glen), 0, 0, 0, 0);
+    }
+  }
+  dp_wait();
+  for (int k = 0; k < L->n; ++k) {
+    ef_fz *z = L->v[k];
+    if (hp[k] >= 0 && dp_res(hp[k])[1]) { z->f[0].es -= dp_res(hp[k])[2]; z->f[0].gs -= dp_res(hp[k])[3]; }
+    if (hs[k] >= 0 && dp_res(hs[k])[1]) { z->f[z->n - 1].ee += dp_res(hs[k])[2]; z->f[z->n - 1].ge += dp_res(hs[k])[3]; }
+  }
+}
+
+/* compute_edit_distance (compute-alignments.c:235): plain edit distance, no wildcard */
+static int edit_push(const char *a, size_t la, const char *b, size_t lb) {
+  return dp_push(PC_OP_EDIT, S_(a, (int)la), S_(b, (int)lb), 0, 0, 0, 0);
+}
+
+/* analyze_possibly_small_exon: try to drop internal exon `c` of z by re-placing it across ONE intron; true if removed */
+static bool analyze_small_exon(ef_task *T, const ef_seq *est, ef_fz *z, int c) {
+  if (c == 0 || c == z->n - 1) return false;
+  const char *e = est->seq, *g = T->gen->seq;
+  ef_factor *prev = &z->f[c - 1], *cur = &z->f[c], *next = &z->f[c + 1];
+  const size_t elen = (size_t)(cur->ee + 1 - cur->es), glen = (size_t)(cur->ge + 1 - cur->gs);
+  if (elen > UB_MED_EXON) return false;
+  const size_t estart = (size_t)MAX2(prev->es + 1, prev->ee + 1 - AFFIXES_LENGTH), eend = (size_t)MIN2(next->ee, next->es + AFFIXES_LENGTH);
+  const size_t epreflen = (size_t)prev->ee + 1 - estart, esufflen = eend - (size_t)next->es, allelen = eend - estart;
+  const char *allefact = e + estart;
+  const size_t gstart = (size_t)MAX2(prev->gs + 1, prev->ge + 1 - AFFIXES_LENGTH), gend = (size_t)MIN2(next->ge, next->gs + AFFIXES_LENGTH);
+  const size_t gpreflen = (size_t)prev->ge + 1 - gstart, gsufflen = gend - (size_t)next->gs, allglen = gend - gstart;
+  const char *allgfact = g + gstart;
+  const int h0 = edit_push(e + cur->es, elen, g + cur->gs, glen);
+  const int h1 = edit_push(allefact, epreflen, allgfact, gpreflen);
+  const int h2 = edit_push(allefact - esufflen, esufflen, allgfact - gsufflen, gsufflen);   /* sic: the bytes BEFORE the window */
+  dp_wait();
+  const size_t orig = (size_t)dp_res(h0)[1] + (size_t)dp_res(h1)[1] + (size_t)dp_res(h2)[1];
+  int off_p, off_t1, off_t2;
+  unsigned new_ed;
+  if (!dp_borders(allefact, (int)allelen, 0, (int)allelen, allgfact, (int)allglen, (unsigned)orig, &off_p, &off_t1, &off_t2, &new_ed))
+    return false;
+  const double prev_avg = (burset_adaptor(g, (size_t)prev->ge + 1, (size_t)cur->gs) + burset_adaptor(g, (size_t)cur->ge + 1, (size_t)next->gs)) / 2.0;
+  const double new_freq = burset_adaptor(g, gstart + (size_t)off_t1, gend - allglen + (size_t)off_t2);
+  if (!(new_freq >= prev_avg)) return false;
+  prev->ee = (int)(estart + (size_t)off_p - 1);
+  next->es = (int)(eend + (size_t)off_p - allelen);
+  prev->ge = (int)(gstart + (size_t)off_t1 - 1);
+  next->gs = (int)(gend + (size_t)off_t2 - allglen);
+  fz_remove(z, c);
+  return true;
+}
+
+static void remove_false_small_exons(ef_task *T, const ef_seq *est, ef_fzlist *L) {
+  for (int k = 0; k < L->n; ++k) {
+    ef_fz *z = L->v[k];
+    /* after a removal the exon before the removed one is examined again against the same successor */
+    for (int c = 0; c < z->n;) {
+      if (analyze_small_exon(T, est, z, c)) --c; else ++c;
+    }
+  }
+}
+
+static bool canonical_intron(const char *g, size_t s, size_t e) {
+  return (g[s] == 'G' && g[s + 1] == 'T' && g[e - 1] == 'A' && g[e] == 'G') || (g[s] == 'g' && g[s + 1] == 't' && g[e - 1] == 'a' && g[e] == 'g');
+}
+
+/* search_small_exon_at_prefix: the unaligned EST prefix (<= 46 nt) against the WHOLE genome prefix before exon 0 */
+static void small_exon_at_prefix(ef_task *T, const ef_seq *est, ef_fz *z) {
+  const ef_config *c = T->cfg;
+  const char *e = est->seq, *g = T->gen->seq;
+  ef_factor *p1 = &z->f[0];
+  const size_t e1len = (size_t)(p1->ee + 1 - p1->es), g1len = (size_t)(p1->ge + 1 - p1->gs);
+  if (e1len + (size_t)p1->es < LB_SMALL_EXON + UB_SMALL_EXON) return;
+  const size_t eplen = (size_t)MIN2(MIN2(p1->es, p1->gs), 2 * UB_SMALL_EXON);
+  const char *epfact = e + p1->es - eplen;
+  const size_t e1plen = MIN2(MIN2(e1len, g1len), (size_t)UB_SMALL_EXON);
+  long pg_, pe_, cflen_;
+  {
+    ef_str s1 = {g, p1->gs, true, 0};
+    const int h = dp_push(PC_OP_LCS, S_(epfact, (int)eplen), s1, 0, 0, 0, 0);
+    dp_wait();
+    cflen_ = dp_res(h)[1]; pg_ = dp_res(h)[2]; pe_ = dp_res(h)[3];
+  }
+  const size_t pg = (size_t)pg_, pe = (size_t)pe_, cflen = (size_t)cflen_;
+  if (cflen < LB_SMALL_EXON) return;
+  const int hed = edit_push(e + p1->es, e1plen, g + p1->gs, e1plen);
+  dp_wait();
+  const unsigned edp = (unsigned)dp_res(hed)[1];
+  const size_t allelen = (size_t)MIN2(p1->ee + 1, p1->es + UB_SMALL_EXON) - pe;
+  const size_t allglen = (size_t)MIN2(p1->ge + 1, p1->gs + UB_SMALL_EXON) - pg;
+  int off_p, off_t1, off_t2;
+  unsigned new_ed;
+  const bool ok = dp_borders(e + pe, (int)allelen, LB_SMALL_EXON, (int)(allelen - LB_SMALL_EXON), g + pg, (int)allglen, edp,
+                             &off_p, &off_t1, &off_t2, &new_ed);
+  if (!ok) return;
+  if (off_t2 - off_t1 < c->min_intron_length) return;
+  if (!canonical_intron(g, pg + (size_t)off_t1, pg + (size_t)off_t2 - 1)) return;
+  if ((size_t)off_p - pe < LB_SMALL_EXON) return;
+  ef_factor nw = {(int)pe, (int)(pe + (size_t)off_p - 1), (int)pg, (int)(pg + (size_t)off_t1 - 1)};
+  p1->es = (int)(pe + (size_t)off_p);
+  p1->gs = (int)(pg + (size_t)off_t2);
+  fz_insert(T, z, 0, nw);
+}
+
+static size_t min3z(size_t a, size_t b, size_t c) { size_t t = a; if (t > b) t = b; if (t > c) t = c; return t; }
+
+/* search_small_exon between exons i and i+1 of z; returns true when a new exon was inserted at i+1 */
+static bool small_exon_between(ef_task *T, const ef_seq *est, ef_fz *z, int i) {
+  const ef_config *c = T->cfg;
+  const char *e = est->seq, *g = T->gen->seq;
+  const int glen_all = T->gen->len;
+  ef_factor *p1 = &z->f[i], *p2 = &z->f[i + 1];
+  const size_t e1len = (size_t)(p1->ee + 1 - p1->es), g1len = (size_t)(p1->ge + 1 - p1->gs);
+  const size_t e2len = (size_t)(p2->ee + 1 - p2->es), g2len = (size_t)(p2->ge + 1 - p2->gs);
+  if (e1len + e2len < LB_SMALL_EXON + 2 * UB_SMALL_EXON) return false;
+  const size_t e1slen = MIN2(MIN2(e1len, g1len), (size_t)UB_SMALL_EXON), g1slen = e1slen;
+  const size_t e1sstart = (size_t)p1->ee + 1 - e1slen, g1sstart = (size_t)p1->ge + 1 - g1slen;
+  const char *e1sfact = e + e1sstart, *g1sfact = g + g1sstart;
+  const size_t e2plen = MIN2(MIN2(e2len, g2len), (size_t)UB_SMALL_EXON), g2plen = e2plen;
+  const size_t e2pstart = (size_t)p2->es, g2pstart = (size_t)p2->gs;
+  const char *e2pfact = e + e2pstart, *g2pfact = g + g2pstart;
+  const int hs = edit_push(e1sfact, e1slen, g1sfact, g1slen), hp = edit_push(e2pfact, e2plen, g2pfact, g2plen);
+  /* the two small longest-common-factor runs are only read when the matching distance is non-zero */
+  const int hl1 = dp_push(PC_OP_LCS, S_(g1sfact, (int)g1slen), S_(e1sfact, (int)e1slen), 0, 0, 0, 0);
+  const int hl2 = dp_push(PC_OP_LCS, S_(g2pfact, (int)g2plen), S_(e2pfact, (int)e2plen), 0, 0, 0, 0);
+  dp_wait();
+  const size_t sed = (size_t)dp_res(hs)[1], ped = (size_t)dp_res(hp)[1];
+  bool go = false;
+  const char orig_type = classify_intron(g, glen_all, p1->ge + 1, p2->gs - 1);
+  if (sed + ped > MAX_ERRORS_AS_SMALL) go = true;
+  if (orig_type == 2) go = true;
+  if (!go) return false;
+  size_t e1socc = 0, g1socc = 0, f1slen = e1slen;
+  if (sed > 0) { f1slen = (size_t)dp_res(hl1)[1]; e1socc = (size_t)dp_res(hl1)[2]; g1socc = (size_t)dp_res(hl1)[3]; }
+  size_t e2pocc = 0, g2pocc = 0, f2plen = e2plen;
+  if (ped > 0) { f2plen = (size_t)dp_res(hl2)[1]; e2pocc = (size_t)dp_res(hl2)[2]; g2pocc = (size_t)dp_res(hl2)[3]; }
+  if (f1slen == e1slen && e2pocc > 0) {
+    size_t nf = f1slen + 1;
+    while (nf - f1slen < e2pocc && e[e1sstart + e1socc + f1slen] == g[g2pstart + nf - f1slen]) ++nf;
+    if (nf - 1 > f1slen) f1slen = nf - 1;
+  }
+  const size_t elen = (e1slen - e1socc) + (e2pocc + f2plen) - (2 * MIN_PERFECT_BORDER);
+  const size_t estart = e1sstart + e1socc + MIN_PERFECT_BORDER;
+  const size_t allgstart = g1sstart + g1socc + MIN_PERFECT_BORDER;
+  const size_t allglen = g2pstart + g2pocc + f2plen - MIN_PERFECT_BORDER - allgstart;
+  const size_t MINI = (size_t)MAX2(4, c->min_intron_length);
+  if (f1slen < MIN_PERFECT_BORDER || f2plen < MIN_PERFECT_BORDER || allglen < 2 * MINI + LB_SMALL_EXON || elen < LB_SMALL_EXON) return false;
+  char *efact = ar_alloc(&T->ar, elen + 1), *allgfact = ar_alloc(&T->ar, allglen + 1);
+  memcpy(efact, e + estart, elen);
+  memcpy(allgfact, g + allgstart, allglen);
+  size_t max_sexon = 0, ecut1 = 0, ecut2 = 0, gcut1_1 = 0, gcut1_2 = 0, gcut2_1 = 0, gcut2_2 = 0;
+  const size_t max_offstart = min3z(f1slen + 1 - MIN_PERFECT_BORDER, elen + 1 - LB_SMALL_EXON, allglen + 1 - (2 * MINI) - LB_SMALL_EXON);
+  for (size_t offstart = 0; offstart < max_offstart; ++offstart) {
+    const size_t max_offend = min3z(f2plen + 1 - MIN_PERFECT_BORDER, elen + 1 - offstart - LB_SMALL_EXON,
+                                    allglen + 1 - (2 * MINI) - LB_SMALL_EXON - offstart);
+    for (size_t offend = 0; offend < max_offend; ++offend) {
+      const char endechar = efact[elen - offend];
+      efact[elen - offend] = 0;
+      const char endgchar = allgfact[allglen - offend - MINI];
+      allgfact[allglen - offend - MINI] = 0;
+      char *occ = allgfact + offstart + MINI;
+      while ((occ = strstr(occ, efact + offstart))) {
+        const size_t i1start = allgstart + offstart, i1end = allgstart + (size_t)(occ - allgfact) - 1;
+        const size_t i2start = i1end + 1 + elen - offstart - offend, i2end = allgstart + allglen - offend - 1;
+        const char t1 = classify_intron(g, glen_all, (int)i1start, (int)i1end), t2 = classify_intron(g, glen_all, (int)i2start, (int)i2end);
+        if (t1 != 2 && t2 != 2) {
+          const size_t sl = elen - offstart - offend;
+          if (sl > max_sexon) {
+            max_sexon = sl; ecut1 = estart + offstart; ecut2 = estart + offstart + sl;
+            gcut1_1 = i1start; gcut1_2 = i1end + 1; gcut2_1 = i2start; gcut2_2 = i2end + 1;
+          }
+        }
+        ++occ;
+      }
+      efact[elen - offend] = endechar;
+      allgfact[allglen - offend - MINI] = endgchar;
+    }
+  }
+  if (max_sexon < LB_SMALL_EXON) return false;
+  ef_factor nw = {(int)ecut1, (int)ecut2 - 1, (int)gcut1_2, (int)gcut2_1 - 1};
+  p2->es = (int)ecut2; p2->gs = (int)gcut2_2;
+  p1->ee = (int)ecut1 - 1; p1->ge = (int)gcut1_1 - 1;
+  fz_insert(T, z, i + 1, nw);
+  return true;
+}
+
+static void search_new_small_exons(ef_task *T, const ef_seq *est, ef_fzlist *L) {
+  for (int k = 0; k < L->n; ++k) {
+    ef_fz *z = L->v[k];
+    if (z->n == 0) continue;
+    int first = 0;
+    if (z->f[0].es > LB_SMALL_EXON) {
+      const int before = z->n;
+      small_exon_at_prefix(T, est, z);
+      first = z->n - before;                /* the old first exon moved to index 1 when a new one was put in front */
+    }
+    for (int i = first; i + 1 < z->n;) {
+      if (small_exon_between(T, est, z, i)) i += 2; else ++i;     /* the inserted exon is not examined */
+    }
+  }
+}
+
+/* clean_factorizations :909-946 — the noisy / external exon cleaning again, this time against the ORIGINAL EST bytes */
+static void clean_all(ef_task *T, const ef_seq *est, ef_fzlist *L) {
+  ef_fzlist out = {0};
+  for (int k = 0; k < L->n; ++k) {
+    ef_fz *z = L->v[k];
+    clean_noisy_exons(T, z, T->gen->seq, est->orig);
+    clean_external_exons(T, z, T->gen->seq, est->orig);
+    if (z->n == 0) continue;
+    add_if_not_exists(T, z, &out);
+  }
+  *L = out;
+}
+
+void refine_factorizations(ef_task *T, const ef_seq *est, ef_fzlist *L) {
+  remove_invalid(L);
+  remove_duplicates(L);
+  recover_lost_affixes(T, est, L);
+  remove_false_small_exons(T, est, L);
+  remove_duplicates(L);
+  search_new_small_exons(T, est, L);
+  clean_all(T, est, L);
+  remove_very_small_exons(L);
+  if (L->n) remove_duplicates(L);
+}
