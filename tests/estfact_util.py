@@ -1,0 +1,62 @@
+"""Shared helpers for the est-fact level parity tests: unpack a golden case, run a binary on it, compare md5s."""
+import hashlib
+import json
+import lzma
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden", "estfact")
+FILES = ["raw-multifasta-out.txt", "processed-ests.txt", "megs.txt", "processed-megs.txt", "meg-edges.txt"]
+CPU_BIN = os.path.join(HERE, "_build", "est-fact-oracle-backend")
+GPU_BIN = os.path.join(ROOT, "pintron_b200", "bin", "est-fact")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "est-fact")
+
+
+def cases():
+    return sorted(d for d in os.listdir(GOLD) if os.path.exists(os.path.join(GOLD, d, "expected.json")))
+
+
+def unpack(case, dst):
+    for f in ("genomic.txt", "ests.txt"):
+        with lzma.open(os.path.join(GOLD, case, f + ".xz")) as i, open(os.path.join(dst, f), "wb") as o:
+            o.write(i.read())
+    return json.load(open(os.path.join(GOLD, case, "expected.json")))
+
+
+def run(binary, cwd, *args, timeout=1200):
+    p = subprocess.run([binary, *args], cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+    assert p.returncode == 0, p.stderr.decode("latin1")[-2000:]
+    return p.stderr.decode("latin1")
+
+
+def md5s(cwd):
+    out = {}
+    for f in FILES:
+        data = open(os.path.join(cwd, f), "rb").read()
+        out[f] = {"md5": hashlib.md5(data).hexdigest(), "bytes": len(data)}
+    return out
+
+
+def check_case(binary, case, tmp_path, *args):
+    exp = unpack(case, str(tmp_path))
+    run(binary, str(tmp_path), *args)
+    got = md5s(str(tmp_path))
+    for f in FILES:
+        if got[f] != exp[f]:
+            hint = ""
+            full = os.path.join(GOLD, case, f + ".xz")
+            if os.path.exists(full):
+                want = lzma.open(full).read().split(b"\n")
+                have = open(os.path.join(str(tmp_path), f), "rb").read().split(b"\n")
+                for n, (a, b) in enumerate(zip(want, have)):
+                    if a != b:
+                        hint = f" first differing line {n + 1}: expected {a[:120]!r} got {b[:120]!r}"
+                        break
+            raise AssertionError(f"{case}/{f}: {got[f]} != {exp[f]}{hint}")
+
+
+def build_cpu_binary():
+    subprocess.run(["make", "-s", "-C", HERE], check=True)
+    return CPU_BIN

@@ -1,0 +1,62 @@
+"""CPU (-m "not gpu"): the C host program of est-fact (pintron_b200/host/: FASTA prep, MEG, embeddings, filters, splice-
+site and post-factorization refinement, output format) must reproduce the UNMODIFIED reference byte for byte on the
+reference's own regression inputs.  The GPU is not available here, so the host is linked against the CPU oracle
+through tests/cpu_backend/ (test infrastructure); the same cases run against the CUDA library in test_estfact_gpu.py.
+Expected md5s come from oracle/_ref/est-fact via tests/golden/make_estfact_golden.py."""
+import os
+import subprocess
+
+import pytest
+
+import estfact_util as U
+
+SMALL = ["test-AMBN", "test-788", "test-mattia1", "test-mattia3", "test-CPB2"]
+
+
+@pytest.fixture(scope="module")
+def cpu_bin():
+    return U.build_cpu_binary()
+
+
+@pytest.mark.parametrize("case", SMALL)
+def test_regression_case_byte_identical(cpu_bin, case, tmp_path):
+    U.check_case(cpu_bin, case, tmp_path, "--quiet", "--threads", "4")
+
+
+def test_single_thread_and_many_fibers_give_the_same_bytes(cpu_bin, tmp_path):
+    """Scheduling (threads, fibers in flight) must not change a byte."""
+    d1 = tmp_path / "a"; d1.mkdir()
+    U.check_case(cpu_bin, "test-AMBN", d1, "--quiet", "--threads", "1", "--fibers", "1")
+    d2 = tmp_path / "b"; d2.mkdir()
+    U.check_case(cpu_bin, "test-AMBN", d2, "--quiet", "--threads", "3", "--fibers", "7")
+
+
+def test_cli_contract(cpu_bin, tmp_path):
+    """Option names / defaults of src/options.ggo, config-dump.ini, precedence CLI > config.ini."""
+    U.unpack("test-mattia3", str(tmp_path))
+    open(tmp_path / "config.ini", "w").write("min-factor-length=16\nmax-prefix-discarded=40\n")
+    U.run(cpu_bin, str(tmp_path), "--quiet", "-l", "15", "--threads", "2")
+    dump = open(tmp_path / "config-dump.ini").read()
+    assert 'min-factor-length="15"' in dump and 'max-prefix-discarded="40"' in dump
+    assert 'min-string-depth-rate="0.2"' in dump and 'retain-externals="true"' in dump
+    p = subprocess.run([cpu_bin, "--retain-externals=maybe"], cwd=str(tmp_path), capture_output=True)
+    assert p.returncode != 0
+    p = subprocess.run([cpu_bin, "--version"], cwd=str(tmp_path), capture_output=True)
+    assert p.returncode == 0 and b"est-fact 0.1" in p.stdout
+
+
+def test_missing_inputs_fail_loudly(cpu_bin, tmp_path):
+    p = subprocess.run([cpu_bin], cwd=str(tmp_path), capture_output=True)
+    assert p.returncode != 0 and b"genomic.txt" in p.stderr
+
+
+def test_product_binary_has_no_cpu_path(tmp_path):
+    """The shipped est-fact links only libpintron_cuda.so; without a CUDA device it must refuse to run."""
+    import torch
+    if torch.cuda.is_available() or not os.path.exists(U.GPU_BIN):
+        pytest.skip("needs a GPU-less box and a built pintron_b200/bin/est-fact")
+    U.unpack("test-mattia3", str(tmp_path))
+    p = subprocess.run([U.GPU_BIN], cwd=str(tmp_path), capture_output=True)
+    assert p.returncode != 0 and b"no CUDA device" in p.stderr
+    syms = subprocess.run(["nm", "-D", "--undefined-only", U.GPU_BIN], capture_output=True, text=True).stdout
+    assert "pc_submit" in syms and "po_" not in syms
