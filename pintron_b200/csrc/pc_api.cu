@@ -7,6 +7,12 @@
 #include <vector>
 
 unsigned long long g_pc_launches = 0;
+#include <chrono>
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static const bool g_prof = getenv("PC_PROFILE") != nullptr;
+static double g_t[8];      /* check, reserve, h2d, sort, launch, d2h, sync (racy sums: diagnostics only) */
+struct ProfDump { ~ProfDump() { if (g_prof) fprintf(stderr, "[pc profile] check %.3f reserve %.3f h2d %.3f sort %.3f launch %.3f d2h %.3f sync %.3f s\n", g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5], g_t[6]); } } g_prof_dump;
+#define PROF(slot, t0) do { if (g_prof) { double t1_ = now_s(); g_t[slot] += t1_ - (t0); (t0) = t1_; } } while (0)
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char *fmt, const char *detail = "") {
@@ -130,6 +136,9 @@ extern "C" pc_stream *pc_stream_create(pc_ctx *c) {
     return nullptr;
   }
   if (st->pool.reserve(256ull << 20)) { delete st; return nullptr; }
+  /* staging sized up front: cudaMalloc / cudaFree while other streams run serialises the whole device */
+  if (st->arena.reserve(8u << 20) || st->var.reserve(8u << 20) || st->jobs.reserve(sizeof(pc_job) << 16) ||
+      st->res.reserve((sizeof(int32_t) * PC_RES_INTS) << 16) || st->idx.reserve(4u << 16) || st->lcs_best.reserve(8u << 14)) { delete st; return nullptr; }
   return st;
 }
 
@@ -212,6 +221,7 @@ static double job_cost(const pc_job &j) {
 static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vector<uint32_t> &sel, const uint8_t *d_arena,
                            const pc_job *d_jobs, int32_t *d_res, uint8_t *d_var) {
   pc_ctx *c = st->ctx;
+  double tp = g_prof ? now_s() : 0;
   // partition by op, heaviest first inside each op
   // counting sort on (op, log2 cost class descending): O(n), good enough for load balance
   std::vector<uint32_t> &order = st->h_idx;
@@ -238,6 +248,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
     for (int b = 0; b < NB; ++b) bins[b + 1] += bins[b];
     for (size_t q = 0; q < sel.size(); ++q) order[bins[key[q]]++] = sel[q];
   }
+  PROF(3, tp);
   if (st->idx.reserve(order.size() * 4 + 4)) return PC_E_NOMEM;
   CU(cudaMemcpyAsync(st->idx.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, st->s));
   CU(cudaMemsetAsync(st->d_pool_need, 0, 8, st->s));
@@ -281,6 +292,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
   }
   CU(cudaMemcpyAsync(st->h_pool_need, st->d_pool_need, 8, cudaMemcpyDeviceToHost, st->s));
   CU(cudaGetLastError());
+  PROF(4, tp);
   return 0;
 }
 
@@ -308,16 +320,20 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
   if (!st || njobs < 0 || (njobs && (!jobs || !res))) return fail(PC_E_ARG, "%s", "pc_submit: bad argument");
   if (st->pend.active) return fail(PC_E_ARG, "%s", "pc_submit: previous batch not synced");
   if (njobs == 0) return 0;
+  double tp = g_prof ? now_s() : 0;
   CU(cudaSetDevice(st->ctx->device));
   int rc = check_jobs(st, jobs, njobs, arena_bytes, var_out_bytes);
   if (rc) return rc;
+  PROF(0, tp);
   // one spare readable byte after the arena: general_refine_borders reads t[len_t] (refine.c:362-374 adaptor)
   if (st->arena.reserve(arena_bytes + 16) || st->jobs.reserve(sizeof(pc_job) * (size_t)njobs) ||
       st->res.reserve(sizeof(int32_t) * PC_RES_INTS * (size_t)njobs) || st->var.reserve(var_out_bytes + 16))
     return PC_E_NOMEM;
+  PROF(1, tp);
   if (arena_bytes) CU(cudaMemcpyAsync(st->arena.p, arena, arena_bytes, cudaMemcpyHostToDevice, st->s));
   CU(cudaMemsetAsync((uint8_t *)st->arena.p + arena_bytes, 0, 16, st->s));
   CU(cudaMemcpyAsync(st->jobs.p, jobs, sizeof(pc_job) * (size_t)njobs, cudaMemcpyHostToDevice, st->s));
+  PROF(2, tp);
   std::vector<uint32_t> all((size_t)njobs);
   for (int i = 0; i < njobs; ++i) all[i] = (uint32_t)i;
   rc = launch_selected(st, jobs, all, (const uint8_t *)st->arena.p, (const pc_job *)st->jobs.p, (int32_t *)st->res.p,
@@ -327,8 +343,10 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
   P.active = true; P.device_mode = false; P.jobs = jobs; P.njobs = njobs; P.res = res; P.var_out = var_out;
   P.var_out_bytes = var_out_bytes; P.d_arena = (const uint8_t *)st->arena.p; P.d_jobs = (const pc_job *)st->jobs.p;
   P.d_res = (int32_t *)st->res.p; P.d_var = (uint8_t *)st->var.p;
+  if (g_prof) tp = now_s();
   CU(cudaMemcpyAsync(res, st->res.p, sizeof(int32_t) * PC_RES_INTS * (size_t)njobs, cudaMemcpyDeviceToHost, st->s));
   if (var_out_bytes) CU(cudaMemcpyAsync(var_out, st->var.p, var_out_bytes, cudaMemcpyDeviceToHost, st->s));
+  PROF(5, tp);
   return 0;
 }
 
@@ -353,7 +371,9 @@ extern "C" int pc_submit_device(pc_stream *st, const uint8_t *d_arena, size_t ar
 extern "C" int pc_stream_sync(pc_stream *st) {
   if (!st) return fail(PC_E_ARG, "%s", "pc_stream_sync: null stream");
   CU(cudaSetDevice(st->ctx->device));
+  double tp = g_prof ? now_s() : 0;
   CU(cudaStreamSynchronize(st->s));
+  PROF(6, tp);
   Pending &P = st->pend;
   if (!P.active) return 0;
   // Jobs whose scratch did not fit their warp's pool slot are re-run with fewer warps (= larger slots); the pool

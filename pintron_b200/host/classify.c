@@ -10,6 +10,7 @@
 #include "ef.h"
 #include <math.h>
 #include <pthread.h>
+#include <stdatomic.h>
 #include "pwm_data.h"
 
 enum { M_BPS9 = 0, M_BPS10, M_5GTAG_U12, M_5ATAC_U12, M_5GTAG_U2, M_5GCAG_U2, M_COUNT };
@@ -91,8 +92,32 @@ static bool two(const char *p, int len, const char *lo, const char *upc) {
   return len == 2 && ((p[0] == lo[0] && p[1] == lo[1]) || (p[0] == upc[0] && p[1] == upc[1]));
 }
 
-/* 0 = U12, 1 = U2, 2 = not determined (include/classify-intron.h:55-57) */
+/* The type of an intron depends on (genome, start, end) only, and the ESTs of a locus keep asking about the same
+ * few introns: a fixed-size shared memo (one 64-bit word per entry: start | end | type; racing writers store the
+ * same value) takes the PWM arithmetic off the per-EST path.  One genome per process (main.c). */
+#define MEMO_BITS 18
+static _Atomic uint64_t memo[1u << MEMO_BITS];
+static char classify_intron_compute(const char *gen, int glen, int start, int end);
+
 char classify_intron(const char *gen, int glen, int start, int end) {
+  if (start < 0 || end < 0 || start >= (1 << 30) || end >= (1 << 30)) return classify_intron_compute(gen, glen, start, end);
+  const uint64_t key = ((uint64_t)(uint32_t)start << 33) | ((uint64_t)(uint32_t)end << 2) | 0x8000000000000000ull;
+  uint64_t h = key * 0x9E3779B97F4A7C15ull;
+  for (int probe = 0; probe < 8; ++probe) {
+    const uint32_t slot = (uint32_t)((h >> (64 - MEMO_BITS)) + (uint32_t)probe) & ((1u << MEMO_BITS) - 1u);
+    const uint64_t v = atomic_load_explicit(&memo[slot], memory_order_relaxed);
+    if ((v & ~3ull) == key) return (char)(v & 3u);
+    if (v == 0) {
+      const char t = classify_intron_compute(gen, glen, start, end);
+      atomic_store_explicit(&memo[slot], key | (uint64_t)(t & 3), memory_order_relaxed);
+      return t;
+    }
+  }
+  return classify_intron_compute(gen, glen, start, end);
+}
+
+/* 0 = U12, 1 = U2, 2 = not determined (include/classify-intron.h:55-57) */
+static char classify_intron_compute(const char *gen, int glen, int start, int end) {
   pthread_once(&pw_once, pw_init);
   /* the intron as real_substring(start, end-start+1) sees it */
   int s = start, length = end - start + 1;

@@ -55,6 +55,7 @@ void ar_free_all(ef_arena *a);
 typedef struct ef_buf { char *p; size_t len, cap; } ef_buf;
 void buf_printf(ef_buf *b, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 void buf_write(ef_buf *b, const void *src, size_t n);
+void buf_ints(ef_buf *b, const char *open, const int *v, int n, char sep, const char *close);
 void buf_free(ef_buf *b);
 
 /* ---- sequences ------------------------------------------------------------------------------------ */
@@ -165,6 +166,11 @@ bool add_if_not_exists(ef_task *T, ef_fz *z, ef_fzlist *L);
 bool ef_timeout_expired(ef_task *T);
 double ef_now(void);
 
+/* CPU-time accounting of the per-EST code (diagnostics; printed with the timers) */
+enum { EF_PH_OTHER = 0, EF_PH_SEED, EF_PH_MEG, EF_PH_EMBED, EF_PH_CAND, EF_PH_FILTER, EF_PH_INTRON, EF_PH_REFINE, EF_PH_SMALLEX, EF_PH_OUTPUT, EF_PH_COUNT };
+int ef_phase(int ph);                       /* returns the previous phase */
+const double *sched_phase_seconds(void);
+
 /* ---- scheduler entry ------------------------------------------------------------------------------------ */
 typedef struct ef_job_result {          /* per input EST, filled by the workers */
   ef_buf raw, pest, megs, pmegs, edges;
@@ -175,5 +181,6 @@ typedef struct ef_job_result {          /* per input EST, filled by the workers 
 typedef void (*ef_task_fn)(ef_task *T, size_t index, void *user);
 int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_fn fn, void *user);
 void sched_stats(double *gpu_wait_s, uint64_t *batches, uint64_t *jobs);
+void sched_breakdown(double *fibers_s, double *gather_s, double *submit_s);   /* summed over worker threads */
 
 #endif

@@ -624,8 +624,11 @@ ef_fzlist *est_factorizations(ef_task *T, const ef_seq *est, ef_meg *M, bool *ti
       if (!E) { *timed_out = true; return NULL; }
       ef_fzlist cand = {0};
       for (int x = 0; x < E->n; ++x) fzl_push(T, &cand, factorization_of(T, E->v[x]));
+      ef_phase(EF_PH_CAND);
       candidate_phases(T, est, &cand, L);
+      ef_phase(EF_PH_EMBED);
     }
+  ef_phase(EF_PH_FILTER);
   /* FILTER 1: coverage on P relative to the best one */
   double *cov = ar_alloc(&T->ar, sizeof(double) * (size_t)(L->n + 1)), maxc = 0.0;
   for (int k = 0; k < L->n; ++k) {
@@ -663,6 +666,7 @@ ef_fzlist *est_factorizations(ef_task *T, const ef_seq *est, ef_meg *M, bool *ti
     L->n = w;
   }
   if (cfg->max_number_of_factorizations != 0 && L->n > cfg->max_number_of_factorizations) L->n = 0;
+  ef_phase(EF_PH_INTRON);
   /* splice-site refinement, intron by intron (the donor of intron k+1 is the acceptor refined by intron k) */
   for (int k = 0; k < L->n; ++k) {
     ef_fz *z = L->v[k];

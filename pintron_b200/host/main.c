@@ -40,7 +40,7 @@ static void write_factorizations(ef_buf *b, const run_ctx *R, const ef_seq *e, c
     for (unsigned counter = 1; counter <= (unsigned)z->n; ++counter) {
       const ef_factor *f = &z->f[counter - 1];
       if (!(counter > l_index && counter < r_index)) continue;
-      buf_printf(b, "%d %d %d %d ", f->es + 1, f->ee + 1, R->gen->pref_N + f->gs + 1, R->gen->pref_N + f->ge + 1);
+      { const int v[4] = {f->es + 1, f->ee + 1, R->gen->pref_N + f->gs + 1, R->gen->pref_N + f->ge + 1}; buf_ints(b, "", v, 4, ' ', " "); }
       const int el = f->ee + 1 - f->es, gl = f->ge + 1 - f->gs;
       if (el > 0) buf_write(b, e->orig + f->es, strnlen(e->orig + f->es, (size_t)el));
       buf_write(b, " ", 1);
@@ -59,6 +59,7 @@ static bool compute_est_fact(ef_task *T, const run_ctx *R, est_item *it, const e
     ef_meg *M;
     const double t_meg0 = ef_now();
     for (;;) {
+      ef_phase(EF_PH_MEG);
       M = meg_build(T, e, &inc);
       meg_stats(M, &tp, &te);
       const bool same = prev_p > 2 && prev_e > 0 && (prev_p <= tp || prev_e <= te);
@@ -69,26 +70,31 @@ static bool compute_est_fact(ef_task *T, const run_ctx *R, est_item *it, const e
     const double t_meg1 = ef_now();
     T->t_start = ef_now();
     bool timed_out = false;
+    ef_phase(EF_PH_EMBED);
     ef_fzlist *L = est_factorizations(T, e, M, &timed_out);
     bool *polya = NULL, *polyad = NULL;
     if (L) {
       polya = ar_alloc(&T->ar, (size_t)L->n + 1); polyad = ar_alloc(&T->ar, (size_t)L->n + 1);
       for (int k = 0; k < L->n; ++k) { polya[k] = L->v[k]->polya; polyad[k] = L->v[k]->polyad; }
+      ef_phase(EF_PH_REFINE);
       refine_factorizations(T, e, L);
     }
+    ef_phase(EF_PH_OUTPUT);
     timed_out = timed_out || ef_timeout_expired(T);
     const double t_comp1 = ef_now();
     const bool got = L && L->n > 0;
-    if (!timed_out || got) {
+    if ((!timed_out || got) && R->cfg->aux_outputs) {
       buf_printf(&it->megs, "\n\n***********\n\n");
       write_est_record(&it->megs, e);
       meg_write(&it->megs, M);
     }
     if (got) {
-      buf_printf(&it->edges, ">%s\n", e->id);
-      meg_write_edges(&it->edges, M);
-      write_est_record(&it->pmegs, e);
-      meg_write(&it->pmegs, M);
+      if (R->cfg->aux_outputs) {
+        buf_printf(&it->edges, ">%s\n", e->id);
+        meg_write_edges(&it->edges, M);
+        write_est_record(&it->pmegs, e);
+        meg_write(&it->pmegs, M);
+      }
       buf_printf(&it->info, "%llu %llu %zu\n", (unsigned long long)((t_meg1 - t_meg0) * 1e6), (unsigned long long)((t_comp1 - t_meg1) * 1e6), (size_t)L->n);
       write_factorizations(&it->raw, R, e, L, polya, polyad);
       write_est_record(&it->pest, e);
@@ -179,6 +185,17 @@ int main(int argc, char **argv) {
   fprintf(stderr, "@Timer Compositions. Time elapsed: %llu microsec\n", 0ull);
   fprintf(stderr, "@Timer IO. Time elapsed: %llu microsec\n", (unsigned long long)(t_io * 1e6));
   fprintf(stderr, "@Timer Total. Time elapsed: %llu microsec\n", (unsigned long long)(t_tot * 1e6));
+  double tfib, tgat, tsub;
+  sched_breakdown(&tfib, &tgat, &tsub);
+  if (!cfg.quiet)
+    fprintf(stderr, "* INFO  host thread-seconds: per-EST code %.3f, batch gather %.3f, submit %.3f, wait on device %.3f\n", tfib, tgat, tsub, gpu_wait);
+  if (!cfg.quiet) {
+    static const char *nm[EF_PH_COUNT] = {"other", "vertex-set", "meg", "embeddings", "candidates", "filters", "intron-refine", "fact-refine", "small-exons", "output"};
+    const double *ph = sched_phase_seconds();
+    fprintf(stderr, "* INFO  per-EST code by phase (s):");
+    for (int i = 0; i < EF_PH_COUNT; ++i) fprintf(stderr, " %s %.3f", nm[i], ph[i]);
+    fprintf(stderr, "\n");
+  }
   if (!cfg.quiet)
     fprintf(stderr, "* INFO  device batches: %llu, device jobs: %llu, summed wait on device: %.3f s, ESTs/s: %.1f\n",
             (unsigned long long)batches, (unsigned long long)jobs, gpu_wait, t_alg > 0 ? (double)nest / t_alg : 0.0);

@@ -255,7 +255,8 @@ static bool too_complex(const ef_meg *M, int l, const ef_config *c) {     /* is_
 
 /* ---- vertex set from the device ------------------------------------------------------------------------------ */
 static ef_meg *vertex_set(ef_task *T, const ef_seq *est, int mfl) {
-  int cap = 2048, h;
+  const int ph_ = ef_phase(EF_PH_SEED);
+  int cap = 256, h;      /* triples; the kernel reports the needed count when this is too small */
   const int32_t *r;
   for (;;) {
     h = dp_push(PC_OP_SEED, S_(est->seq, est->len), S_(NULL, 0), mfl, 0, 0, cap);
@@ -271,6 +272,7 @@ static ef_meg *vertex_set(ef_task *T, const ef_seq *est, int mfl) {
   pl_push(T, &M->V[0], new_pairing(T, SRC_START, SRC_START, SENTINEL_LEN));
   for (int k = 0; k < r[1]; ++k) pl_push(T, &M->V[tri[3 * k] + 1], new_pairing(T, tri[3 * k], tri[3 * k + 1], tri[3 * k + 2]));
   pl_push(T, &M->V[M->n - 1], new_pairing(T, SINK_START, SINK_START, SENTINEL_LEN));
+  ef_phase(ph_);
   return M;
 }
 
@@ -299,14 +301,14 @@ void meg_write(ef_buf *b, ef_meg *M) {
   for (int i = 0; i < M->n; ++i)
     for (int k = 0; k < M->V[i].n; ++k) {
       ef_pairing *p = M->V[i].v[k];
-      buf_printf(b, "(%d,%d,%d)\n", p->p, p->t, p->l);
+      { const int v[3] = {p->p, p->t, p->l}; buf_ints(b, "(", v, 3, ',', ")\n"); }
       p->id = id++;
     }
   buf_printf(b, "#adj#\n");
   for (int i = 0; i < M->n; ++i)
     for (int k = 0; k < M->V[i].n; ++k) {
       const ef_pairing *p = M->V[i].v[k];
-      for (int a = 0; a < p->adjs.n; ++a) buf_printf(b, "%d-%d\n", p->id, p->adjs.v[a]->id);
+      for (int a = 0; a < p->adjs.n; ++a) { const int v[2] = {p->id, p->adjs.v[a]->id}; buf_ints(b, "", v, 2, '-', "\n"); }
     }
 }
 
@@ -318,10 +320,9 @@ void meg_write_edges(ef_buf *b, const ef_meg *M) {
       for (int a = 0; a < p->adjs.n; ++a) {
         const ef_pairing *q = p->adjs.v[a];
         if (q->p == SINK_START) continue;
-        buf_printf(b, "%d %d %d %d %d %d %d %d %d", p->t + p->l, q->t, p->p + p->l, q->p, q->t - p->t - p->l, q->p - p->p - p->l,
-                   (q->t - p->t) - (q->p - p->p), p->l, q->l);
-        if ((q->t - p->t) - (q->p - p->p) >= 50) buf_printf(b, " intronic");
-        buf_printf(b, "\n");
+        const int v[9] = {p->t + p->l, q->t, p->p + p->l, q->p, q->t - p->t - p->l, q->p - p->p - p->l,
+                          (q->t - p->t) - (q->p - p->p), p->l, q->l};
+        buf_ints(b, "", v, 9, ' ', v[6] >= 50 ? " intronic\n" : "\n");
       }
     }
 }

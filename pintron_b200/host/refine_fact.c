@@ -298,7 +298,9 @@ void refine_factorizations(ef_task *T, const ef_seq *est, ef_fzlist *L) {
   recover_lost_affixes(T, est, L);
   remove_false_small_exons(T, est, L);
   remove_duplicates(L);
+  ef_phase(EF_PH_SMALLEX);
   search_new_small_exons(T, est, L);
+  ef_phase(EF_PH_REFINE);
   clean_all(T, est, L);
   remove_very_small_exons(L);
   if (L->n) remove_duplicates(L);

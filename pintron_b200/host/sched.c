@@ -84,6 +84,24 @@ void buf_printf(ef_buf *b, const char *fmt, ...) {
   b->len += (size_t)n;
 }
 
+/* decimal integers separated / terminated by single characters, without going through printf */
+void buf_ints(ef_buf *b, const char *open, const int *v, int n, char sep, const char *close) {
+  buf_reserve(b, (size_t)n * 12 + 16);
+  char *p = b->p + b->len;
+  while (*open) *p++ = *open++;
+  for (int i = 0; i < n; ++i) {
+    if (i) *p++ = sep;
+    long long x = v[i];
+    if (x < 0) { *p++ = '-'; x = -x; }
+    char tmp[12]; int k = 0;
+    do { tmp[k++] = (char)('0' + x % 10); x /= 10; } while (x);
+    while (k) *p++ = tmp[--k];
+  }
+  while (*close) *p++ = *close++;
+  *p = 0;
+  b->len = (size_t)(p - b->p);
+}
+
 void buf_free(ef_buf *b) { free(b->p); b->p = NULL; b->len = b->cap = 0; }
 
 /* ---- fibers ---------------------------------------------------------------------------------------- */
@@ -100,6 +118,7 @@ typedef struct fiber {
   ef_req *reqs;
   int nreq, capreq;
   int base;                 /* index of this fiber's first job in the group's batch */
+  int phase;
   bool has_results;
   struct group *grp;
 } fiber;
@@ -128,7 +147,7 @@ typedef struct worker {
   ef_task_fn fn;
   void *user;
   uint64_t batches, jobs;
-  double gpu_wait;
+  double gpu_wait, t_fibers, t_gather, t_submit;
 } worker;
 
 static _Atomic size_t g_next_item;
@@ -136,8 +155,21 @@ static size_t g_n_items;
 static __thread fiber *tl_fiber;
 static __thread worker *tl_worker;
 static uint64_t g_batches, g_jobs;
-static double g_gpu_wait;
+static double g_gpu_wait, g_t_fibers, g_t_gather, g_t_submit, g_t_init, g_t_fini;
 static pthread_mutex_t g_stat_mu = PTHREAD_MUTEX_INITIALIZER;
+
+/* ---- where the host time goes: CPU seconds per phase of the per-EST code (fibers only run between yields) ------ */
+static __thread int tl_phase;
+static __thread double tl_mark;
+static __thread double tl_phase_s[EF_PH_COUNT];
+static double g_phase_s[EF_PH_COUNT];
+static inline void phase_account(void) {
+  const double t = ef_now();
+  tl_phase_s[tl_phase] += t - tl_mark;
+  tl_mark = t;
+}
+int ef_phase(int ph) { phase_account(); const int old = tl_phase; tl_phase = ph; return old; }
+const double *sched_phase_seconds(void) { return g_phase_s; }
 
 static void die_pc(const char *what) {
   fprintf(stderr, "* FATAL est-fact: %s: %s\n", what, pc_last_error());
@@ -154,7 +186,9 @@ static void *pinned_grow(void *old, size_t old_bytes, size_t new_bytes) {
 static void fiber_entry(void) {
   fiber *f = tl_fiber;
   worker *w = tl_worker;
+  tl_phase = EF_PH_OTHER; tl_mark = ef_now();
   w->fn(&f->task, f->index, w->user);
+  phase_account();
   f->state = F_DONE;
   swapcontext(&f->ctx, &w->main_ctx);
 }
@@ -196,8 +230,11 @@ void dp_wait(void) {
   fiber *f = tl_fiber;
   if (f->nreq == 0 || f->has_results) return;
   f->state = F_WAITING;
+  phase_account();
+  f->phase = tl_phase;
   swapcontext(&f->ctx, &tl_worker->main_ctx);
   /* resumed: results are in the group's batch buffers */
+  tl_phase = f->phase; tl_mark = ef_now();
   for (int i = 0; i < f->nreq; ++i) {
     const int32_t st = f->grp->res[(size_t)(f->base + i) * PC_RES_INTS];
     if (st < 0 && st != PC_E_OUTCAP) {
@@ -322,6 +359,7 @@ static bool run_group(worker *w, group *g) {
       if (g->fibers[k].state == F_WAITING) { g->fibers[k].state = F_RUNNABLE; g->fibers[k].has_results = true; }
   }
   bool any = false;
+  const double tf0 = ef_now();
   for (int k = 0; k < g->nfibers; ++k) {
     fiber *f = &g->fibers[k];
     for (;;) {
@@ -338,29 +376,49 @@ static bool run_group(worker *w, group *g) {
     }
     if (f->state == F_WAITING) any = true;
   }
+  const double tf1 = ef_now();
+  w->t_fibers += tf1 - tf0;
   if (!any) return false;
   gather(g);
+  const double tf2 = ef_now();
+  w->t_gather += tf2 - tf1;
   if (g->njobs) {
     if (pc_submit(g->st, g->arena, g->arena_len, g->jobs, g->njobs, g->res, g->var, g->var_len)) die_pc("pc_submit");
     g->pending = true;
     w->batches++; w->jobs += (uint64_t)g->njobs;
   }
+  w->t_submit += ef_now() - tf2;
   return true;
 }
 
 static void *worker_main(void *arg) {
   worker *w = arg;
   tl_worker = w;
+  const double tw0 = ef_now();
   for (int i = 0; i < 2; ++i) {
-    w->g[i].st = pc_stream_create(w->ctx);
-    if (!w->g[i].st) die_pc("pc_stream_create");
-    w->g[i].w = w;
+    group *g = &w->g[i];
+    g->st = pc_stream_create(w->ctx);
+    if (!g->st) die_pc("pc_stream_create");
+    g->w = w;
+    /* pinned staging sized up front: growing pinned memory later stalls every thread of the process */
+    const size_t per_fiber = 4096;
+    g->arena_cap = MAX2((size_t)1 << 20, (size_t)g->nfibers * per_fiber);
+    g->arena = pinned_grow(NULL, 0, g->arena_cap);
+    g->jobs_cap = MAX2(4096, g->nfibers * 16);
+    g->jobs = pinned_grow(NULL, 0, sizeof(pc_job) * (size_t)g->jobs_cap);
+    g->res_cap = (size_t)g->jobs_cap * PC_RES_INTS;
+    g->res = pc_host_alloc(g->res_cap * sizeof(int32_t));
+    g->var_cap = g->arena_cap;
+    g->var = pc_host_alloc(g->var_cap);
+    if (!g->res || !g->var) die_pc("pc_host_alloc");
   }
+  const double tw1 = ef_now();
   bool alive[2] = {true, true};
   while (alive[0] || alive[1]) {
     for (int i = 0; i < 2; ++i)
       if (alive[i] || w->g[i].pending) alive[i] = run_group(w, &w->g[i]);
   }
+  const double tw2 = ef_now();
   for (int i = 0; i < 2; ++i) {
     group *g = &w->g[i];
     for (int k = 0; k < g->nfibers; ++k) {
@@ -375,8 +433,15 @@ static void *worker_main(void *arg) {
   }
   pthread_mutex_lock(&g_stat_mu);
   g_batches += w->batches; g_jobs += w->jobs; g_gpu_wait += w->gpu_wait;
+  g_t_fibers += w->t_fibers; g_t_gather += w->t_gather; g_t_submit += w->t_submit;
+  g_t_init += tw1 - tw0; g_t_fini += ef_now() - tw2;
+  for (int i = 0; i < EF_PH_COUNT; ++i) g_phase_s[i] += tl_phase_s[i];
   pthread_mutex_unlock(&g_stat_mu);
   return NULL;
+}
+
+void sched_breakdown(double *fibers_s, double *gather_s, double *submit_s) {
+  *fibers_s = g_t_fibers; *gather_s = g_t_gather; *submit_s = g_t_submit;
 }
 
 void sched_stats(double *gpu_wait_s, uint64_t *batches, uint64_t *jobs) {
@@ -386,6 +451,7 @@ void sched_stats(double *gpu_wait_s, uint64_t *batches, uint64_t *jobs) {
 }
 
 int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_fn fn, void *user) {
+  const double ts0 = ef_now();
   int ndev = pc_device_count();
   if (ndev <= 0) {
     fprintf(stderr, "* FATAL est-fact: no CUDA device available (%s). This build has no CPU path.\n", pc_last_error());
@@ -412,7 +478,8 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
   if ((size_t)per_group * 2 * (size_t)nthreads > n_items) per_group = (int)(n_items / (2 * (size_t)nthreads)) + 1;
   atomic_store(&g_next_item, 0);
   g_n_items = n_items;
-  g_batches = g_jobs = 0; g_gpu_wait = 0;
+  g_batches = g_jobs = 0; g_gpu_wait = 0; g_t_fibers = g_t_gather = g_t_submit = g_t_init = g_t_fini = 0;
+  const double ts1 = ef_now();
   worker *ws = calloc((size_t)nthreads, sizeof(worker));
   for (int i = 0; i < nthreads; ++i) {
     worker *w = &ws[i];
@@ -425,7 +492,12 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
     if (pthread_create(&w->th, NULL, worker_main, w)) { perror("pthread_create"); return 1; }
   }
   for (int i = 0; i < nthreads; ++i) pthread_join(ws[i].th, NULL);
+  const double ts2 = ef_now();
   free(ws);
   for (int i = 0; i < nuse; ++i) pc_ctx_destroy(ctxs[i]);
+  if (!cfg->quiet)
+    fprintf(stderr, "* INFO  scheduler: %d thread(s) x 2 x %d fibers on %d GPU(s); context + genome index %.3f s, workers %.3f s "
+            "(stream set-up %.3f s, tear-down %.3f s per thread on average), context tear-down %.3f s\n",
+            nthreads, per_group, nuse, ts1 - ts0, ts2 - ts1, g_t_init / nthreads, g_t_fini / nthreads, ef_now() - ts2);
   return 0;
 }
