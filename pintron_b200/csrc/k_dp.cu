@@ -438,7 +438,7 @@ void launch_wpj(const PcDevBatch &B, cudaStream_t s, int sm_count) {
   PcDevBatch C = B;
   C.slots = grid * PC_WARPS_PER_CTA;
   k_warp_per_job<OP><<<grid, PC_WARPS_PER_CTA * 32, 0, s>>>(C);
-  ++g_pc_launches;
+  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
 }
 
 }  // namespace
@@ -480,7 +480,7 @@ double pc_int_peak_run(cudaStream_t s, int sm_count, float *ms_out) {
   k_int_peak<<<grid, 256, 0, s>>>(iters, 3, 1 << 30, sink);
   cudaEventRecord(e1, s);
   cudaEventSynchronize(e1);
-  g_pc_launches += 2;
+  __atomic_fetch_add(&g_pc_launches, 2ull, __ATOMIC_RELAXED);
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
   if (ms_out) *ms_out = ms;

@@ -234,7 +234,7 @@ void launch_pairs(const PcDevBatch &B, int mcap, cudaStream_t s, int sm_count) {
   PcDevBatch C = B;
   C.slots = grid * 4;
   k_gap_pairs<LANES><<<grid, 128, sh, s>>>(C, mcap);
-  ++g_pc_launches;
+  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
 }
 
 }  // namespace

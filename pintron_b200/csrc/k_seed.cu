@@ -247,7 +247,7 @@ void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count) {
   PcDevBatch C = B;
   C.slots = grid * 4;
   k_seed<<<grid, 128, 0, s>>>(C);
-  ++g_pc_launches;
+  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
 }
 
 // best: device array of B.n 64-bit slots (zeroed here); max_l1/max_l2 over the jobs of the batch
@@ -261,10 +261,10 @@ int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, long long max_l
     C.idx = B.idx + off;
     C.n = B.n - off < 65535 ? B.n - off : 65535;
     dim3 grid((unsigned)((ndiag + LCS_TPB - 1) / LCS_TPB), (unsigned)C.n);
-    if (grid.x > 0) { k_lcs<<<grid, LCS_TPB, sh, s>>>(C, best + off); ++g_pc_launches; }
+    if (grid.x > 0) { k_lcs<<<grid, LCS_TPB, sh, s>>>(C, best + off); __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED); }
   }
   k_lcs_finish<<<(B.n + 127) / 128, 128, 0, s>>>(B, best);
-  ++g_pc_launches;
+  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
   return 0;
 }
 
@@ -277,7 +277,7 @@ int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned lon
   if (cudaMalloc(&k_in, 8ull * n) || cudaMalloc(&k_out, 8ull * n) || cudaMalloc(&p_in, 4ull * n) || cudaMalloc(&p_out, 4ull * n))
     return PC_E_NOMEM;
   k_hash_windows<<<(n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048, 256, 0, s>>>(d_genome, n, word, k_in, p_in);
-  ++g_pc_launches;
+  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, 64, s);
   void *tmp;

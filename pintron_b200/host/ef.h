@@ -179,8 +179,10 @@ typedef struct ef_job_result {          /* per input EST, filled by the workers 
 } ef_job_result;
 
 typedef void (*ef_task_fn)(ef_task *T, size_t index, void *user);
+void sched_prepare(const ef_config *cfg, const ef_seq *gen);   /* optional: start device set-up early, in the background */
 int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_fn fn, void *user);
 void sched_stats(double *gpu_wait_s, uint64_t *batches, uint64_t *jobs);
+void sched_bytes(uint64_t *h2d, uint64_t *d2h);                    /* bytes staged to / from the devices */
 void sched_breakdown(double *fibers_s, double *gather_s, double *submit_s);   /* summed over worker threads */
 
 #endif

@@ -108,6 +108,12 @@ static bool compute_est_fact(ef_task *T, const run_ctx *R, est_item *it, const e
 static void est_task(ef_task *T, size_t index, void *user) {
   run_ctx *R = user;
   est_item *it = &R->items[index];
+  /* EST preparation (main-est-fact.c:190-213) */
+  ef_set_gb(&it->fwd);
+  ef_set_strand_and_rc(&it->fwd);
+  it->fwd.len = (int)strlen(it->fwd.seq);
+  ef_polyAT_substitution(&it->fwd);
+  if (!it->fwd.fixed_strand) { ef_make_rc_copy(&it->fwd, &it->rc); it->rc.len = it->fwd.len; it->has_rc = true; }
   if (compute_est_fact(T, R, it, &it->fwd)) return;
   if (it->has_rc) {
     ar_reset(&T->ar);
@@ -138,6 +144,7 @@ int main(int argc, char **argv) {
   ef_seq *gen = &gens[0];
   ef_parse_genomic_header(gen);
   ef_ntails_removal(gen);
+  sched_prepare(&cfg, gen);
   ef_seq *ests = NULL; size_t nest = 0;
   if (ef_read_fasta("ests.txt", &ests, &nest)) { fprintf(stderr, "* FATAL File ests.txt not found! Terminating\n"); return 1; }
   FILE *f_raw = open_out("raw-multifasta-out.txt"), *f_megs = open_out("megs.txt"), *f_pmegs = open_out("processed-megs.txt");
@@ -148,12 +155,7 @@ int main(int argc, char **argv) {
   est_item *items = calloc(nest ? nest : 1, sizeof *items);
   for (size_t i = 0; i < nest; ++i) {
     est_item *it = &items[i];
-    it->fwd = ests[i];
-    ef_set_gb(&it->fwd);
-    ef_set_strand_and_rc(&it->fwd);
-    it->fwd.len = (int)strlen(it->fwd.seq);
-    ef_polyAT_substitution(&it->fwd);
-    if (!it->fwd.fixed_strand) { ef_make_rc_copy(&it->fwd, &it->rc); it->rc.len = it->fwd.len; it->has_rc = true; }
+    it->fwd = ests[i];       /* strand / reverse-complement / polyA masking happen in est_task, on the worker threads */
   }
 
   run_ctx R = {&cfg, gen, gen->orig, items};
@@ -196,8 +198,12 @@ int main(int argc, char **argv) {
     for (int i = 0; i < EF_PH_COUNT; ++i) fprintf(stderr, " %s %.3f", nm[i], ph[i]);
     fprintf(stderr, "\n");
   }
+  uint64_t h2d, d2h;
+  sched_bytes(&h2d, &d2h);
+  if (!cfg.quiet) fprintf(stderr, "* INFO  bytes host->device: %llu, device->host: %llu\n", (unsigned long long)h2d, (unsigned long long)d2h);
   if (!cfg.quiet)
-    fprintf(stderr, "* INFO  device batches: %llu, device jobs: %llu, summed wait on device: %.3f s, ESTs/s: %.1f\n",
-            (unsigned long long)batches, (unsigned long long)jobs, gpu_wait, t_alg > 0 ? (double)nest / t_alg : 0.0);
+    fprintf(stderr, "* INFO  device batches: %llu, device jobs: %llu, kernel launches: %llu, summed wait on device: %.3f s, ESTs/s: %.1f\n",
+            (unsigned long long)batches, (unsigned long long)jobs, (unsigned long long)pc_launch_count(), gpu_wait,
+            t_alg > 0 ? (double)nest / t_alg : 0.0);
   return 0;
 }
