@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--e2e-reads", type=int, default=100000, help="ESTs per GPU per step, whole-program leg")
     ap.add_argument("--ref-reads-per-core", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the whole-program leg (profiling runs: ncu would follow the child)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -273,9 +274,10 @@ def main():
     if not os.path.exists(exe):
         raise SystemExit("bench.py: pintron_b200/bin/est-fact is not built (python __graft_entry__.py)")
     work = tempfile.mkdtemp(prefix=f"pintron_e2e_r{rank}_")
-    e2e_synth = Synth("C3", reads=args.e2e_reads * world)
-    open(os.path.join(work, "genomic.txt"), "wb").write(e2e_synth.genome_fasta())
-    open(os.path.join(work, "ests.txt"), "wb").write(e2e_synth.ests_fasta(rank * args.e2e_reads, args.e2e_reads))
+    if not args.no_e2e:
+        e2e_synth = Synth("C3", reads=args.e2e_reads * world)
+        open(os.path.join(work, "genomic.txt"), "wb").write(e2e_synth.genome_fasta())
+        open(os.path.join(work, "ests.txt"), "wb").write(e2e_synth.ests_fasta(rank * args.e2e_reads, args.e2e_reads))
     cores = os.cpu_count() or 1
     threads = max(1, (cores // world) * 3 // 4)
     e2e_info = {}
@@ -322,12 +324,16 @@ def main():
     barrier()
     ms_host = timed(step_host, args.steps)                  # the same device batch, submitted from pinned host buffers
     barrier()
-    for _ in range(args.warmup):
-        step_program()
-    barrier()
-    ms_e2e = [step_program() * 1e3 for _ in range(args.steps)]
-    barrier()
-    n_out = sum(1 for _ in open(os.path.join(work, "processed-ests.txt"), "rb")) // 2
+    n_out = None
+    if args.no_e2e:
+        ms_e2e = [float("nan")]
+    else:
+        for _ in range(args.warmup):
+            step_program()
+        barrier()
+        ms_e2e = [step_program() * 1e3 for _ in range(args.steps)]
+        barrier()
+        n_out = sum(1 for _ in open(os.path.join(work, "processed-ests.txt"), "rb")) // 2
     shutil.rmtree(work, ignore_errors=True)
     sampler.stop_flag = True
     sampler.join(timeout=2)
