@@ -226,8 +226,9 @@ void launch_pairs(const PcDevBatch &B, int mcap, cudaStream_t s, int sm_count) {
   const size_t sh = (size_t)4 * G * (mcap + 1) * sizeof(uint32_t);
   static bool attr_done = false;
   if (!attr_done) { cudaFuncSetAttribute(k_gap_pairs<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; }
-  int per_sm = 4;
-  if (sh * per_sm > 200 * 1024) per_sm = (int)((200 * 1024) / sh) > 0 ? (int)((200 * 1024) / sh) : 1;
+  // persistent CTAs: exactly as many as are resident at once (registers limit this kernel), else the rest runs as a tail wave
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gap_pairs<LANES>, 128, sh) != cudaSuccess || per_sm < 1) per_sm = 1;
   int grid = ctas_needed < sm_count * per_sm ? ctas_needed : sm_count * per_sm;
   if (B.max_warps > 0 && grid > (B.max_warps + 3) / 4) grid = (B.max_warps + 3) / 4;
   if (grid < 1) grid = 1;
