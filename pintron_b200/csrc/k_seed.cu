@@ -8,6 +8,7 @@
 // time, never correctness.
 #include "pc_device.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <climits>
 
 namespace {
 
@@ -24,13 +25,14 @@ __global__ void k_hash_windows(const uint8_t *g, uint32_t n_win, int word, unsig
   }
 }
 
-__device__ __forceinline__ uint32_t lower_bound(const unsigned long long *keys, uint32_t n, unsigned long long h) {
-  uint32_t lo = 0, hi = n;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (keys[mid] < h) lo = mid + 1; else hi = mid;
+// bucket b = top `bits` bits of the hash; bstart[b] = first sorted entry of bucket b (bstart[nb] = n): two loads
+// replace a 17-step dependent binary search
+__global__ void k_bucket_starts(const unsigned long long *keys, uint32_t n, int shift, uint32_t nb, uint32_t *bstart) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
+    const uint32_t b_prev = i == 0 ? 0u : (uint32_t)(keys[i - 1] >> shift) + 1u;
+    const uint32_t b_cur = i == n ? nb : (uint32_t)(keys[i] >> shift);
+    for (uint32_t b = b_prev; b <= b_cur; ++b) bstart[b] = i;     // buckets (b_prev-1, b_cur] start at i
   }
-  return lo;
 }
 
 __device__ __forceinline__ int lcp(const uint8_t *P, int n, int p, const uint8_t *T, uint32_t G, uint32_t t) {
@@ -74,17 +76,20 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane) {
   const int np = n - word + 1;               // positions that can start a word
   if (np <= 0 || G < (uint32_t)word) { if (lane == 0) { res[0] = PC_OK; res[1] = 0; } return; }
   // per-position arrays: bucket start, bucket end, D / offsets, counts
-  int *arr = (int *)pc_pool_alloc(B, wp, 5ull * np * sizeof(int), lane);
+  int *arr = (int *)pc_pool_alloc(B, wp, 6ull * np * sizeof(int), lane);
   if (!arr) { if (lane == 0) res[0] = PC_E_POOL; return; }
-  int *b_lo = arr, *b_hi = arr + np, *offs = arr + 2 * np, *cnt = arr + 3 * np, *thr_a = arr + 4 * np;
+  int *b_lo = arr, *b_hi = arr + np, *offs = arr + 2 * np, *cnt = arr + 3 * np, *thr_a = arr + 4 * np, *ncand = arr + 5 * np;
   // S1: bucket, D(p), number of candidates >= mfl
   for (int p = lane; p < np; p += 32) {
     const unsigned long long h = hash_word(P + p, word);
-    uint32_t k = lower_bound(B.ix_keys, B.ix_n, h);
+    const uint32_t bk = (uint32_t)(h >> B.ix_shift);
+    uint32_t k = B.ix_bstart[bk];
+    const uint32_t kend = B.ix_bstart[bk + 1];
+    while (k < kend && B.ix_keys[k] != h) ++k;               // entries of one word are contiguous inside the bucket
     const uint32_t k0 = k;
     int c = 0, D = 0;
     const uint8_t prev = p > 0 ? P[p - 1] : 0;
-    for (; k < B.ix_n && B.ix_keys[k] == h; ++k) {
+    for (; k < kend && B.ix_keys[k] == h; ++k) {
       const uint32_t t = B.ix_pos[k];
       if (p > 0 && t > 0 && T[t - 1] == prev) continue;
       const int l = lcp(P, n, p, T, G, t);
@@ -93,7 +98,7 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane) {
     b_lo[p] = (int)k0; b_hi[p] = (int)k;
     int thr = (int)(size_t)((double)D * B.depth_rate);
     thr_a[p] = max(thr, mfl);
-    offs[p] = c;
+    offs[p] = c; ncand[p] = c;
   }
   __syncwarp();
   const int total = warp_exscan(offs, np, lane);
@@ -110,22 +115,22 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane) {
     const int thr = thr_a[p];
     const uint8_t prev = p > 0 ? P[p - 1] : 0;
     int c = 0;
+    if (ncand[p] == 0) { cnt[p] = 0; continue; }
     for (int k = b_lo[p]; k < b_hi[p]; ++k) {
       const uint32_t t = B.ix_pos[k];
       if (p > 0 && t > 0 && T[t - 1] == prev) continue;
       const int l = lcp(P, n, p, T, G, t);
       if (l >= thr) { v[c].t = (int)t; v[c].l = l; ++c; }
     }
-    // filter A is judged against the unfiltered list: mark first, compact after
-    uint8_t *kp = keep + offs[p];
+    // filter A, judged against the UNfiltered list.  The list is strictly ascending in t, so "an earlier entry ends
+    // at or after this one" is a running maximum of t+l, and "t == earlier t + 1" can only be the direct predecessor.
+    int q = 0, max_end = INT_MIN, pt = INT_MIN, pl = -1;
     for (int j = 0; j < c; ++j) {
-      bool drop = false;
-      for (int i = 0; i < j && !drop; ++i)
-        drop = (v[j].t > v[i].t && v[j].t + v[j].l <= v[i].t + v[i].l) || (v[j].t == v[i].t + 1 && v[j].l == v[i].l);
-      kp[j] = !drop;
+      const int t = v[j].t, l = v[j].l;
+      const bool drop = (j > 0 && t + l <= max_end) || (t == pt + 1 && l == pl);
+      max_end = max(max_end, t + l); pt = t; pl = l;
+      if (!drop) { v[q].t = t; v[q].l = l; ++q; }
     }
-    int q = 0;
-    for (int j = 0; j < c; ++j) if (kp[j]) v[q++] = v[j];
     cnt[p] = q;
   }
   __syncwarp();
@@ -134,13 +139,12 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane) {
   for (int p = lane; p < np; p += 32) {
     const TL *v = cand + offs[p];
     uint8_t *kp = keep + offs[p];
-    int q = 0;
-    for (int x = 0; x < cnt[p]; ++x) {
-      bool drop = false;
-      if (p > 0) {
-        const TL *u = cand + offs[p - 1];
-        for (int y = 0; y < cnt[p - 1] && !drop; ++y) drop = u[y].t == v[x].t && u[y].l >= v[x].l;
-      }
+    int q = 0, y = 0;
+    const TL *u = p > 0 ? cand + offs[p - 1] : nullptr;
+    const int nu = p > 0 ? cnt[p - 1] : 0;
+    for (int x = 0; x < cnt[p]; ++x) {                       // both lists ascend in t: one merge pass
+      while (y < nu && u[y].t < v[x].t) ++y;
+      const bool drop = y < nu && u[y].t == v[x].t && u[y].l >= v[x].l;
       kp[x] = !drop; q += !drop;
     }
     outc[p] = q;
@@ -269,9 +273,12 @@ int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, long long max_l
 }
 
 int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned long long **keys_out, uint32_t **pos_out,
-                   uint32_t *n_out, cudaStream_t s) {
-  *keys_out = nullptr; *pos_out = nullptr; *n_out = 0;
-  if (len < (uint32_t)word) return 0;
+                   uint32_t *n_out, uint32_t **bstart_out, int *shift_out, cudaStream_t s) {
+  *keys_out = nullptr; *pos_out = nullptr; *n_out = 0; *bstart_out = nullptr; *shift_out = 63;
+  if (len < (uint32_t)word) {                        // empty index: one empty bucket pair
+    if (cudaMalloc(bstart_out, 3 * sizeof(uint32_t)) || cudaMemset(*bstart_out, 0, 3 * sizeof(uint32_t))) return PC_E_NOMEM;
+    return 0;
+  }
   const uint32_t n = len - word + 1;
   unsigned long long *k_in, *k_out; uint32_t *p_in, *p_out;
   if (cudaMalloc(&k_in, 8ull * n) || cudaMalloc(&k_out, 8ull * n) || cudaMalloc(&p_in, 4ull * n) || cudaMalloc(&p_out, 4ull * n))
@@ -285,6 +292,14 @@ int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned lon
   cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, 64, s);   // stable: equal keys keep ascending t
   if (cudaStreamSynchronize(s) != cudaSuccess) return PC_E_CUDA;
   cudaFree(tmp); cudaFree(k_in); cudaFree(p_in);
-  *keys_out = k_out; *pos_out = p_out; *n_out = n;
+  int bits = 12;
+  while (bits < 24 && (1u << bits) < 2u * n) ++bits;          // about half an entry per bucket
+  const uint32_t nb = 1u << bits;
+  uint32_t *bstart;
+  if (cudaMalloc(&bstart, (nb + 2ull) * sizeof(uint32_t))) return PC_E_NOMEM;
+  k_bucket_starts<<<(n + 256) / 256 < 2048 ? (n + 256) / 256 : 2048, 256, 0, s>>>(k_out, n, 64 - bits, nb, bstart);
+  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  if (cudaStreamSynchronize(s) != cudaSuccess) return PC_E_CUDA;
+  *keys_out = k_out; *pos_out = p_out; *n_out = n; *bstart_out = bstart; *shift_out = 64 - bits;
   return 0;
 }

@@ -26,7 +26,8 @@ struct pc_ctx {
   uint8_t *d_genome = nullptr;
   uint32_t genome_len = 0;
   unsigned long long *ix_keys = nullptr;
-  uint32_t *ix_pos = nullptr;
+  uint32_t *ix_pos = nullptr, *ix_bstart = nullptr;
+  int ix_shift = 63;
   uint32_t ix_n = 0;
   int ix_word = 0;
   double depth_rate = 0.2;
@@ -102,22 +103,22 @@ extern "C" pc_ctx *pc_ctx_create(int device) {
 extern "C" void pc_ctx_destroy(pc_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_genome); cudaFree(c->ix_keys); cudaFree(c->ix_pos);
+  cudaFree(c->d_genome); cudaFree(c->ix_keys); cudaFree(c->ix_pos); cudaFree(c->ix_bstart);
   delete c;
 }
 
 extern "C" int pc_genome_upload(pc_ctx *c, const char *genome, size_t len, int word_len, double depth_rate) {
   if (!c || !genome || word_len <= 0 || len >= 0xfffffff0ull) return fail(PC_E_ARG, "%s", "pc_genome_upload: bad argument");
   CU(cudaSetDevice(c->device));
-  cudaFree(c->d_genome); cudaFree(c->ix_keys); cudaFree(c->ix_pos);
-  c->d_genome = nullptr; c->ix_keys = nullptr; c->ix_pos = nullptr;
+  cudaFree(c->d_genome); cudaFree(c->ix_keys); cudaFree(c->ix_pos); cudaFree(c->ix_bstart);
+  c->d_genome = nullptr; c->ix_keys = nullptr; c->ix_pos = nullptr; c->ix_bstart = nullptr;
   CU(cudaMalloc(&c->d_genome, len + 16));
   CU(cudaMemset(c->d_genome, 0, len + 16));
   CU(cudaMemcpy(c->d_genome, genome, len, cudaMemcpyHostToDevice));
   c->genome_len = (uint32_t)len;
   c->ix_word = word_len;
   c->depth_rate = depth_rate;
-  int rc = pc_build_index(c->d_genome, c->genome_len, word_len, &c->ix_keys, &c->ix_pos, &c->ix_n, 0);
+  int rc = pc_build_index(c->d_genome, c->genome_len, word_len, &c->ix_keys, &c->ix_pos, &c->ix_n, &c->ix_bstart, &c->ix_shift, 0);
   if (rc) return fail(rc, "%s", "pc_genome_upload: index build failed");
   CU(cudaDeviceSynchronize());
   return 0;
@@ -257,7 +258,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
   B.jobs = d_jobs; B.res = d_res; B.var_out = d_var;
   B.pool = (uint8_t *)st->pool.p; B.pool_cap = st->pool.cap; B.pool_need = st->d_pool_need;
   B.slots = 1; B.max_warps = st->max_warps;
-  B.ix_keys = c->ix_keys; B.ix_pos = c->ix_pos; B.ix_n = c->ix_n; B.ix_word = c->ix_word; B.depth_rate = c->depth_rate;
+  B.ix_keys = c->ix_keys; B.ix_pos = c->ix_pos; B.ix_bstart = c->ix_bstart; B.ix_shift = c->ix_shift; B.ix_n = c->ix_n; B.ix_word = c->ix_word; B.depth_rate = c->depth_rate;
   size_t i = 0;
   while (i < order.size()) {
     const uint32_t op = h_jobs[order[i]].op;

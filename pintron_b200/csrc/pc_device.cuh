@@ -25,6 +25,8 @@ struct PcDevBatch {
   /* k-mer index (SEED) */
   const unsigned long long *ix_keys;
   const uint32_t *ix_pos;
+  const uint32_t *ix_bstart;  /* bucket starts: bucket = hash >> ix_shift */
+  int ix_shift;
   uint32_t ix_n;
   int ix_word;
   double depth_rate;
@@ -59,5 +61,5 @@ void pc_launch_gap_pairs(int cls, const PcDevBatch &B, int max_m, cudaStream_t s
 void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count);
 int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, long long max_l1, int max_l2, cudaStream_t s);
 int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned long long **keys, uint32_t **pos,
-                   uint32_t *n_out, cudaStream_t s);
+                   uint32_t *n_out, uint32_t **bstart, int *shift, cudaStream_t s);
 extern unsigned long long g_pc_launches;
