@@ -356,7 +356,7 @@ def main():
         pass
     if dom in OPS_PER_CELL:
         ach = cells[dom] * OPS_PER_CELL[dom] / (op_ms[dom] * 1e-3) / 1e12
-        roof = {"bound": "int_alu", "kernel": f"k_warp_per_job<{dom}>", "achieved": ach, "peak": int_peak / 1e12,
+        roof = {"bound": "int_alu", "kernel": "k_gap_pairs<8> (compute_gap_alignment)" if dom == "GAP" else f"k_warp_per_job<{dom}>", "achieved": ach, "peak": int_peak / 1e12,
                 "unit": "Tlane-op/s", "frac": ach / (int_peak / 1e12) if int_peak else None, "traffic": None,
                 "peak_source": "pc_measure_int_peak (VIADDMNMX chains, measured live on this GPU)",
                 "gcups": cells[dom] / (op_ms[dom] * 1e-3) / 1e9, "ops_per_cell": OPS_PER_CELL[dom]}

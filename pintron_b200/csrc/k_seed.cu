@@ -187,19 +187,83 @@ __device__ __forceinline__ unsigned long long lcs_key(int len, uint32_t i1, int 
          (unsigned long long)(0xffffu - (uint32_t)i2);
 }
 
-__global__ void __launch_bounds__(LCS_TPB) k_lcs(PcDevBatch B, unsigned long long *best) {
-  const int w = blockIdx.y;
-  const uint32_t ji = B.idx[w];
-  const pc_job *job = B.jobs + ji;
-  const uint8_t *s2 = B.arena + job->a_off;
-  const int l2 = (int)job->a_len;
-  const uint8_t *s1 = ((job->flags & PC_B_IN_GENOME) ? B.genome : B.arena) + job->b_off;
-  const long long l1 = job->b_len;
-  if (l2 > LCS_MAX_S2) return;                              // reported by k_lcs_finish
-  // diagonals d = i1 - i2 in [-(l2-1), l1-1]; this block owns LCS_TPB consecutive ones
-  const long long d0 = (long long)blockIdx.x * LCS_TPB - (l2 - 1);
-  if (d0 > l1 - 1) return;
-  extern __shared__ uint8_t sh[];
+// Bit-parallel form for s2 of at most 64 bytes (the est-fact callers pass <= 46): the cells of one diagonal become one
+// 64-bit mask = (bytes equal) | (s1 byte is N) | (s2 byte is N), built four cells per step with packed byte compares;
+// the longest run of ones and its first position come from x &= x << 1.
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t a, uint32_t b) {         // 0x80 in every byte where a == b
+  const uint32_t x = a ^ b;
+  return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+}
+
+__device__ __forceinline__ void lcs_block_bits(const uint8_t *s1, long long l1, const uint8_t *s2, int l2, long long d0,
+                                               uint8_t *sh, unsigned long long *best_w) {
+  // shared: t1 words (slice of s1, zero outside [0,l1)), N-flag bits of the slice, s2 words
+  uint32_t *t1w = reinterpret_cast<uint32_t *>(sh);                 // (LCS_TPB + 64 + 8) bytes
+  uint32_t *n1 = t1w + (LCS_TPB + 64 + 8) / 4;                       // (LCS_TPB + 64) / 32 + 1 words
+  uint32_t *s2w = n1 + (LCS_TPB + 64) / 32 + 2;                      // 16 words of s2 + 2 words of its N mask
+  uint8_t *t1 = reinterpret_cast<uint8_t *>(t1w);
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int base = 0; base < 2 * LCS_TPB; base += LCS_TPB) {           // every thread runs both rounds: the ballots need whole warps
+    const int i = base + tid;
+    const long long g = d0 + i;
+    const uint8_t c = (g >= 0 && g < l1 && i < LCS_TPB + 64) ? s1[g] : 0;
+    if (i < LCS_TPB + 64 + 8) t1[i] = c;
+    const uint32_t nb = __ballot_sync(0xffffffffu, pc_is_n(c));
+    if (lane == 0 && i < LCS_TPB + 64 + 64) n1[i >> 5] = nb;         // words 10, 11 come out zero
+  }
+  if (tid < 16) {
+    uint32_t w = 0;
+    for (int b = 0; b < 4; ++b) { const int i = tid * 4 + b; w |= (uint32_t)(i < l2 ? s2[i] : 0xffu) << (8 * b); }   // 0xff never equals the 0 padding
+    s2w[tid] = w;
+  }
+  if (tid < 32) {                                                    // N positions of s2 as a 64-bit mask (two ballots of warp 0)
+    const uint32_t f0 = __ballot_sync(0xffffffffu, tid < l2 && pc_is_n(s2[tid]));
+    const uint32_t f1 = __ballot_sync(0xffffffffu, tid + 32 < l2 && pc_is_n(s2[tid + 32]));
+    if (tid == 0) { s2w[16] = f0; s2w[17] = f1; }
+  }
+  __syncthreads();
+  const long long d = d0 + tid;
+  unsigned long long key = 0;
+  if (d <= l1 - 1) {
+    const unsigned long long n2 = (unsigned long long)s2w[16] | ((unsigned long long)s2w[17] << 32);
+    const int r8 = (tid & 3) * 8, wbase = tid >> 2;
+    unsigned long long eq = 0;
+    uint32_t lo = t1w[wbase];
+    const int nw = (l2 + 3) >> 2;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k < nw) {
+        const uint32_t hi = t1w[wbase + k + 1];
+        const uint32_t w1 = __funnelshift_r(lo, hi, r8);
+        lo = hi;
+        const uint32_t f = eq_bytes(w1, s2w[k]);
+        eq |= (unsigned long long)((((f >> 7) * 0x00204081u) >> 21) & 15u) << (4 * k);
+      }
+    }
+    // N flags of s1 along the diagonal: 64 bits of the slice's flag array starting at bit tid
+    const int wq = tid >> 5, bq = tid & 31;
+    const uint32_t a0 = n1[wq], a1 = n1[wq + 1], a2 = n1[wq + 2];
+    const unsigned long long nfl = (unsigned long long)__funnelshift_r(a0, a1, bq) | ((unsigned long long)__funnelshift_r(a1, a2, bq) << 32);
+    // valid cells: 0 <= d + i2 < l1 and i2 < l2
+    const int v_lo = d < 0 ? (int)-d : 0;
+    const long long room = l1 - d;
+    const int v_hi = (int)(room < l2 ? room : l2);                 // exclusive
+    unsigned long long valid = v_hi >= 64 ? ~0ull : ((1ull << v_hi) - 1ull);
+    valid = v_lo >= 64 ? 0ull : (valid & (~0ull << v_lo));
+    unsigned long long x = (eq | nfl | n2) & valid, prev = 0;
+    int len = 0;
+    while (x) { prev = x; x &= x << 1; ++len; }
+    if (len > 0) {
+      const int e = __ffsll((long long)prev) - 1;                 // END of the first longest run on this diagonal
+      key = lcs_key(len, (uint32_t)(d + e), e);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); key = max(key, k2); }
+  if (lane == 0 && key) atomicMax(best_w, key);
+}
+
+__device__ __forceinline__ void lcs_block_generic(const uint8_t *s1, long long l1, const uint8_t *s2, int l2, long long d0,
+                                                  uint8_t *sh, unsigned long long *best_w) {
   uint8_t *t1 = sh;                 // s1[d0 .. d0 + LCS_TPB + l2 - 1)
   uint8_t *t2 = sh + LCS_TPB + l2;  // s2
   for (int i = threadIdx.x; i < LCS_TPB + l2 - 1; i += LCS_TPB) {
@@ -223,7 +287,24 @@ __global__ void __launch_bounds__(LCS_TPB) k_lcs(PcDevBatch B, unsigned long lon
     if (bl > 0) key = lcs_key(bl, (uint32_t)(d + bi2), bi2);
   }
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); key = max(key, k2); }
-  if ((threadIdx.x & 31) == 0 && key) atomicMax(best + w, key);
+  if ((threadIdx.x & 31) == 0 && key) atomicMax(best_w, key);
+}
+
+__global__ void __launch_bounds__(LCS_TPB) k_lcs(PcDevBatch B, unsigned long long *best) {
+  const int w = blockIdx.y;
+  const uint32_t ji = B.idx[w];
+  const pc_job *job = B.jobs + ji;
+  const uint8_t *s2 = B.arena + job->a_off;
+  const int l2 = (int)job->a_len;
+  const uint8_t *s1 = ((job->flags & PC_B_IN_GENOME) ? B.genome : B.arena) + job->b_off;
+  const long long l1 = job->b_len;
+  if (l2 > LCS_MAX_S2) return;                              // reported by k_lcs_finish
+  // diagonals d = i1 - i2 in [-(l2-1), l1-1]; this block owns LCS_TPB consecutive ones
+  const long long d0 = (long long)blockIdx.x * LCS_TPB - (l2 - 1);
+  if (d0 > l1 - 1) return;
+  extern __shared__ __align__(16) uint8_t sh[];
+  if (l2 <= 64) lcs_block_bits(s1, l1, s2, l2, d0, sh, best + w);
+  else lcs_block_generic(s1, l1, s2, l2, d0, sh, best + w);
 }
 
 __global__ void k_lcs_finish(PcDevBatch B, const unsigned long long *best) {
@@ -259,7 +340,8 @@ int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, long long max_l
   if (max_l2 > LCS_MAX_S2) max_l2 = LCS_MAX_S2;
   cudaMemsetAsync(best, 0, sizeof(unsigned long long) * B.n, s);
   const long long ndiag = max_l1 + max_l2;
-  const size_t sh = LCS_TPB + 2 * (size_t)max_l2 + 8;
+  size_t sh = LCS_TPB + 2 * (size_t)max_l2 + 8;
+  if (sh < LCS_TPB + 64 + 8 + 4 * ((LCS_TPB + 64) / 32 + 2) + 72 + 16) sh = LCS_TPB + 64 + 8 + 4 * ((LCS_TPB + 64) / 32 + 2) + 72 + 16;
   for (int off = 0; off < B.n; off += 65535) {               // gridDim.y limit
     PcDevBatch C = B;
     C.idx = B.idx + off;

@@ -241,3 +241,28 @@ def test_gap_packed_classes_vs_port(cu, port):
         assert rr[0] == 0, (len(est), len(gen), list(rr))
         assert var[j["out_off"]:j["out_off"] + rr[1]].tobytes() == ops, (len(est), len(gen))
         assert list(rr[2:7]) == pos, (len(est), len(gen))
+
+
+def test_lcs_bit_parallel_vs_port(cu, port):
+    """The 64-bit mask form of find_longest_common_factor_dp (s2 <= 64 bytes): N wildcards on both sides, lower case,
+    ties between equally long runs (first in (i1, i2) order wins), every s2 length 1..64 and the generic path beyond."""
+    g = Gen(31337)
+    r = g.rnd
+    b, cases = Batch(), []
+    for it in range(600):
+        l2 = (it % 70) + 1
+        l1 = r.choice([1, 2, 5, 31, 32, 33, 63, 64, 65, 255, 256, 257, 300, 1000, 5000])
+        s1 = bytearray(g.rs(l1, "ACGT" if it % 3 else "ACGTNn"))
+        s2 = bytearray(g.rs(l2, "ACGT" if it % 2 else "ACGTN"))
+        if it % 4 == 0 and l1 > l2 + 2:                       # plant s2 (or a piece of it) twice: ties
+            piece = s2[: max(1, l2 // 2)]
+            for _ in range(2):
+                at = r.randint(0, l1 - len(piece))
+                s1[at:at + len(piece)] = piece
+        if it % 5 == 0:
+            s1 = bytearray(bytes(s1).lower()[: len(s1) // 2] + bytes(s1)[len(s1) // 2:])
+        b.add(PC_OP.LCS, bytes(s2), bytes(s1)); cases.append((bytes(s1), bytes(s2)))
+    res, _ = cu.run(b)
+    for (s1, s2), rr in zip(cases, res):
+        assert rr[0] == 0
+        assert tuple(rr[1:4]) == port.lcs(s1, s2), (len(s1), len(s2), s1[:80], s2)
