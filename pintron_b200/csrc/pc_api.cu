@@ -36,17 +36,19 @@ struct pc_ctx {
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
+  bool in_slab = false;        /* carved from the stream's single start-up allocation: never freed on its own */
+  void carve(uint8_t *&cursor, size_t bytes) { p = cursor; cap = bytes; in_slab = true; cursor += (bytes + 255u) & ~(size_t)255u; }
   int reserve(size_t bytes) {
     if (bytes <= cap) return 0;
-    if (p) cudaFree(p);
-    p = nullptr;
+    if (p && !in_slab) cudaFree(p);
+    p = nullptr; in_slab = false;
     size_t want = std::max(bytes, cap * 2);
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) { cap = 0; return fail(PC_E_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
     cap = want;
     return 0;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p && !in_slab) cudaFree(p); p = nullptr; cap = 0; in_slab = false; }
 };
 
 struct Pending {          // what pc_stream_sync needs to re-run jobs that ran out of pool
@@ -66,6 +68,7 @@ struct pc_stream {
   pc_ctx *ctx = nullptr;
   cudaStream_t s = nullptr;
   DevBuf arena, jobs, idx, res, var, pool, lcs_best;
+  void *slab = nullptr;
   unsigned long long *d_pool_need = nullptr, *h_pool_need = nullptr;   /* device counter + pinned mirror */
   int max_warps = 0;
   std::vector<uint32_t> h_idx;
@@ -136,10 +139,15 @@ extern "C" pc_stream *pc_stream_create(pc_ctx *c) {
     delete st;
     return nullptr;
   }
-  if (st->pool.reserve(256ull << 20)) { delete st; return nullptr; }
-  /* staging sized up front: cudaMalloc / cudaFree while other streams run serialises the whole device */
-  if (st->arena.reserve(8u << 20) || st->var.reserve(8u << 20) || st->jobs.reserve(sizeof(pc_job) << 16) ||
-      st->res.reserve((sizeof(int32_t) * PC_RES_INTS) << 16) || st->idx.reserve(4u << 16) || st->lcs_best.reserve(8u << 14)) { delete st; return nullptr; }
+  /* scratch pool and staging as ONE allocation made up front: cudaMalloc / cudaFree while other streams run
+   * serialise the whole device.  Buffers that outgrow their share later get their own allocation. */
+  const size_t sizes[7] = {256ull << 20, 8u << 20, 8u << 20, sizeof(pc_job) << 16, (sizeof(int32_t) * PC_RES_INTS) << 16, 4u << 16, 8u << 14};
+  size_t total = 0;
+  for (size_t z : sizes) total += (z + 255u) & ~(size_t)255u;
+  if (cudaMalloc(&st->slab, total) != cudaSuccess) { fail(PC_E_NOMEM, "%s", "pc_stream_create: device allocation failed"); delete st; return nullptr; }
+  uint8_t *cur = (uint8_t *)st->slab;
+  DevBuf *bufs[7] = {&st->pool, &st->arena, &st->var, &st->jobs, &st->res, &st->idx, &st->lcs_best};
+  for (int i = 0; i < 7; ++i) bufs[i]->carve(cur, sizes[i]);
   return st;
 }
 
@@ -148,6 +156,7 @@ extern "C" void pc_stream_destroy(pc_stream *st) {
   cudaSetDevice(st->ctx->device);
   cudaStreamSynchronize(st->s);
   for (DevBuf *b : {&st->arena, &st->jobs, &st->idx, &st->res, &st->var, &st->pool, &st->lcs_best}) b->release();
+  cudaFree(st->slab);
   cudaFree(st->d_pool_need); cudaFreeHost(st->h_pool_need);
   for (auto &e : st->ev_pending) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
   for (auto e : st->ev_free) cudaEventDestroy(e);

@@ -134,6 +134,7 @@ typedef struct group {
   int32_t *res; size_t res_cap;
   uint8_t *var; size_t var_cap, var_len;
   struct worker *w;
+  uint8_t *slab, *slab_end;   /* the initial pinned slab the four buffers above were carved from */
 } group;
 
 typedef struct worker {
@@ -176,10 +177,14 @@ static void die_pc(const char *what) {
   exit(1);
 }
 
+static __thread uint8_t *tl_slab, *tl_slab_end;      /* pointers inside the group's slab are never freed one by one */
+static void pinned_release(void *p) {
+  if (p && !((uint8_t *)p >= tl_slab && (uint8_t *)p < tl_slab_end)) pc_host_free(p);
+}
 static void *pinned_grow(void *old, size_t old_bytes, size_t new_bytes) {
   void *p = pc_host_alloc(new_bytes);
   if (!p) die_pc("pc_host_alloc");
-  if (old) { memcpy(p, old, old_bytes); pc_host_free(old); }
+  if (old) { memcpy(p, old, old_bytes); pinned_release(old); }
   return p;
 }
 
@@ -284,6 +289,7 @@ ef_aln aln_from_ops(ef_task *T, const uint8_t *ops, int n, const char *est, cons
 
 /* ---- batching -------------------------------------------------------------------------------------------- */
 static void gather(group *g) {
+  tl_slab = g->slab; tl_slab_end = g->slab_end;
   g->arena_len = 0; g->njobs = 0; g->var_len = 0;
   for (int k = 0; k < g->nfibers; ++k) {
     fiber *f = &g->fibers[k];
@@ -330,14 +336,14 @@ static void gather(group *g) {
   if (g->njobs == 0) return;
   if ((size_t)g->njobs * PC_RES_INTS > g->res_cap) {
     size_t nc = MAX2(g->res_cap * 2, (size_t)g->njobs * PC_RES_INTS + 4096);
-    if (g->res) pc_host_free(g->res);
+    pinned_release(g->res);
     g->res = pc_host_alloc(nc * sizeof(int32_t));
     if (!g->res) die_pc("pc_host_alloc");
     g->res_cap = nc;
   }
   if (g->var_len > g->var_cap) {
     size_t nc = MAX2(g->var_cap * 2, g->var_len + (1u << 20));
-    if (g->var) pc_host_free(g->var);
+    pinned_release(g->var);
     g->var = pc_host_alloc(nc);
     if (!g->var) die_pc("pc_host_alloc");
     g->var_cap = nc;
@@ -402,17 +408,19 @@ static void *worker_main(void *arg) {
     g->st = pc_stream_create(w->ctx);
     if (!g->st) die_pc("pc_stream_create");
     g->w = w;
-    /* pinned staging sized up front: growing pinned memory later stalls every thread of the process */
+    /* pinned staging sized up front and taken as ONE slab: pinning memory stalls every thread of the process, so it
+     * is done once per group; a buffer that outgrows its share later moves to its own allocation */
     const size_t per_fiber = 4096;
     g->arena_cap = MAX2((size_t)1 << 20, (size_t)g->nfibers * per_fiber);
-    g->arena = pinned_grow(NULL, 0, g->arena_cap);
     g->jobs_cap = MAX2(4096, g->nfibers * 16);
-    g->jobs = pinned_grow(NULL, 0, sizeof(pc_job) * (size_t)g->jobs_cap);
     g->res_cap = (size_t)g->jobs_cap * PC_RES_INTS;
-    g->res = pc_host_alloc(g->res_cap * sizeof(int32_t));
     g->var_cap = g->arena_cap;
-    g->var = pc_host_alloc(g->var_cap);
-    if (!g->res || !g->var) die_pc("pc_host_alloc");
+    const size_t jobs_b = (sizeof(pc_job) * (size_t)g->jobs_cap + 255u) & ~(size_t)255u, res_b = g->res_cap * sizeof(int32_t);
+    uint8_t *slab = pc_host_alloc(g->arena_cap + jobs_b + res_b + g->var_cap);
+    if (!slab) die_pc("pc_host_alloc");
+    g->slab = slab; g->slab_end = slab + g->arena_cap + jobs_b + res_b + g->var_cap;
+    g->arena = slab; g->jobs = (pc_job *)(slab + g->arena_cap);
+    g->res = (int32_t *)(slab + g->arena_cap + jobs_b); g->var = slab + g->arena_cap + jobs_b + res_b;
   }
   const double tw1 = ef_now();
   bool alive[2] = {true, true};
@@ -421,18 +429,8 @@ static void *worker_main(void *arg) {
       if (alive[i] || w->g[i].pending) alive[i] = run_group(w, &w->g[i]);
   }
   const double tw2 = ef_now();
-  for (int i = 0; i < 2; ++i) {
-    group *g = &w->g[i];
-    for (int k = 0; k < g->nfibers; ++k) {
-      fiber *f = &g->fibers[k];
-      if (f->stack) munmap(f->stack, FIBER_STACK);
-      ar_free_all(&f->task.ar);
-      free(f->reqs);
-    }
-    free(g->fibers);
-    pc_host_free(g->arena); pc_host_free(g->jobs); pc_host_free(g->res); pc_host_free(g->var);
-    pc_stream_destroy(g->st);
-  }
+  /* No tear-down: est-fact exits right after the last EST, and freeing pinned / device memory (two dozen streams,
+   * each call synchronising the device) only delays the threads that are still working. */
   pthread_mutex_lock(&g_stat_mu);
   g_batches += w->batches; g_jobs += w->jobs; g_gpu_wait += w->gpu_wait; g_h2d += w->h2d; g_d2h += w->d2h;
   g_t_fibers += w->t_fibers; g_t_gather += w->t_gather; g_t_submit += w->t_submit;
@@ -525,7 +523,7 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
   for (int i = 0; i < nthreads; ++i) pthread_join(ws[i].th, NULL);
   const double ts2 = ef_now();
   free(ws);
-  for (int i = 0; i < nuse; ++i) pc_ctx_destroy(ctxs[i]);
+  (void)ctxs;      /* contexts are left to process exit, see worker_main */
   if (!cfg->quiet)
     fprintf(stderr, "* INFO  scheduler: %d thread(s) x 2 x %d fibers on %d GPU(s); context + genome index %.3f s (%.3f s of it still to wait for), workers %.3f s "
             "(stream set-up %.3f s, tear-down %.3f s per thread on average), context tear-down %.3f s\n",
