@@ -354,10 +354,20 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        key = "k_gap_pairs<8> (compute_gap_alignment)"
+        if dom == "GAP" and args.reads == 20000 and key in tr:
+            traffic = tr[key]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     if dom in OPS_PER_CELL:
         ach = cells[dom] * OPS_PER_CELL[dom] / (op_ms[dom] * 1e-3) / 1e12
         roof = {"bound": "int_alu", "kernel": "k_gap_pairs<8> (compute_gap_alignment)" if dom == "GAP" else f"k_warp_per_job<{dom}>", "achieved": ach, "peak": int_peak / 1e12,
-                "unit": "Tlane-op/s", "frac": ach / (int_peak / 1e12) if int_peak else None, "traffic": None,
+                "unit": "Tlane-op/s", "frac": ach / (int_peak / 1e12) if int_peak else None, "traffic": traffic,
+                "traffic_note": "DRAM bytes per launch from the committed ncu capture (profiles/r1_traffic.json); this kernel is INT-ALU bound, "
+                                "the traffic is its direction-byte scratch",
                 "peak_source": "pc_measure_int_peak (VIADDMNMX chains, measured live on this GPU)",
                 "gcups": cells[dom] / (op_ms[dom] * 1e-3) / 1e9, "ops_per_cell": OPS_PER_CELL[dom]}
     else:

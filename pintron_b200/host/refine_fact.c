@@ -199,9 +199,6 @@ static bool small_exon_between(ef_task *T, const ef_seq *est, ef_fz *z, int i) {
   const size_t e2pstart = (size_t)p2->es, g2pstart = (size_t)p2->gs;
   const char *e2pfact = e + e2pstart, *g2pfact = g + g2pstart;
   const int hs = edit_push(e1sfact, e1slen, g1sfact, g1slen), hp = edit_push(e2pfact, e2plen, g2pfact, g2plen);
-  /* the two small longest-common-factor runs are only read when the matching distance is non-zero */
-  const int hl1 = dp_push(PC_OP_LCS, S_(g1sfact, (int)g1slen), S_(e1sfact, (int)e1slen), 0, 0, 0, 0);
-  const int hl2 = dp_push(PC_OP_LCS, S_(g2pfact, (int)g2plen), S_(e2pfact, (int)e2plen), 0, 0, 0, 0);
   dp_wait();
   const size_t sed = (size_t)dp_res(hs)[1], ped = (size_t)dp_res(hp)[1];
   bool go = false;
@@ -209,6 +206,11 @@ static bool small_exon_between(ef_task *T, const ef_seq *est, ef_fz *z, int i) {
   if (sed + ped > MAX_ERRORS_AS_SMALL) go = true;
   if (orig_type == 2) go = true;
   if (!go) return false;
+  /* the longest common factors of the two borders are needed only from here on, and only for a border with errors */
+  int hl1 = -1, hl2 = -1;
+  if (sed > 0) hl1 = dp_push(PC_OP_LCS, S_(g1sfact, (int)g1slen), S_(e1sfact, (int)e1slen), 0, 0, 0, 0);
+  if (ped > 0) hl2 = dp_push(PC_OP_LCS, S_(g2pfact, (int)g2plen), S_(e2pfact, (int)e2plen), 0, 0, 0, 0);
+  if (hl1 >= 0 || hl2 >= 0) dp_wait();
   size_t e1socc = 0, g1socc = 0, f1slen = e1slen;
   if (sed > 0) { f1slen = (size_t)dp_res(hl1)[1]; e1socc = (size_t)dp_res(hl1)[2]; g1socc = (size_t)dp_res(hl1)[3]; }
   size_t e2pocc = 0, g2pocc = 0, f2plen = e2plen;

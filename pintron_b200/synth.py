@@ -14,6 +14,11 @@ CONFIGS = {
                read_len=(300, 800), err=0.01, seed=1003),
     "C4": dict(genome=2_000_000, genes=8, exons=40, exon_len=(25, 300), intron_len=(80, 60000), reads=1_000_000,
                read_len=(300, 800), err=0.01, seed=1004, mrna_frac=0.2, mrna_len=(1000, 6000)),
+    # reduced C4 / C5 shapes for parity tests (multi-gene locus with long 3' UTR exons and mRNAs; titin-like long exons)
+    "C4mini": dict(genome=400_000, genes=3, exons=25, exon_len=(25, 300), intron_len=(80, 15000), reads=400,
+                   read_len=(300, 800), err=0.01, seed=1104, mrna_frac=0.3, mrna_len=(1000, 5000), utr_len=(500, 3000)),
+    "C5mini": dict(genome=300_000, genes=1, exons=50, exon_len=(100, 600), intron_len=(80, 4000), reads=16,
+                   read_len=(8000, 20000), err=0.005, seed=1105, long_exons=(4, 3000, 9000)),
     "tiny": dict(genome=20_000, genes=1, exons=12, exon_len=(25, 160), intron_len=(80, 1500), reads=64,
                  read_len=(200, 500), err=0.01, seed=7),
 }
@@ -50,6 +55,12 @@ class Synth:
         for gi in range(cfg["genes"]):
             for _attempt in range(200):
                 ex = [_log_uniform(rng, *cfg["exon_len"]) for _ in range(cfg["exons"])]
+                if cfg.get("utr_len"):
+                    ex[-1] = int(rng.integers(*cfg["utr_len"]))
+                if cfg.get("long_exons"):
+                    k, lo_, hi_ = cfg["long_exons"]
+                    for q in rng.choice(cfg["exons"], size=k, replace=False):
+                        ex[int(q)] = int(rng.integers(lo_, hi_))
                 it = [_log_uniform(rng, *cfg["intron_len"]) for _ in range(cfg["exons"] - 1)]
                 if sum(ex) + sum(it) < span - 2000:
                     break

@@ -32,7 +32,7 @@ def _write_synth(d, name, reads, seed=None):
     open(os.path.join(d, "ests.txt"), "wb").write(s.ests_fasta(0, reads))
 
 
-@pytest.mark.parametrize("name,reads", [("tiny", 64), ("C3", 1500)])
+@pytest.mark.parametrize("name,reads", [("tiny", 64), ("C3", 1500), ("C4mini", 400), ("C5mini", 16)])
 def test_synthetic_vs_reference_binary(gpu_bin, name, reads, tmp_path):
     if not os.path.exists(U.REF_BIN):
         pytest.skip("oracle/_ref/est-fact not built")
