@@ -49,7 +49,9 @@ enum pc_op {
 };
 
 enum pc_flags {
-  PC_B_IN_GENOME = 1u   /* b_off/b_len index the genome uploaded with pc_genome_upload, not the arena */
+  PC_B_IN_GENOME = 1u,  /* b_off/b_len index the genome uploaded with pc_genome_upload, not the arena */
+  PC_B_NUL_AFTER = 2u   /* BORDERS: the byte after t reads as NUL (the reference passes a NUL-terminated copy of t,
+                           src/est-factorizations.c:1490), whatever follows it in the arena or the genome */
 };
 
 enum pc_status {

@@ -205,9 +205,11 @@ __constant__ uint8_t c_burset[58][5] = {
 
 __device__ __forceinline__ uint8_t up_c(uint8_t c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
 
-__device__ int burset_freq(const uint8_t *t, int cut1, int cut2) {
+// len_t >= 0: bytes at or after len_t read as NUL (PC_B_NUL_AFTER); len_t < 0: read whatever follows t
+__device__ int burset_freq(const uint8_t *t, int cut1, int cut2, int len_t) {
   if (cut2 < 2) return 0;
-  const uint8_t d0 = up_c(t[cut1]), d1 = d0 ? up_c(t[cut1 + 1]) : 0;
+  const uint8_t d0 = (len_t >= 0 && cut1 >= len_t) ? 0 : up_c(t[cut1]);
+  const uint8_t d1 = (!d0 || (len_t >= 0 && cut1 + 1 >= len_t)) ? 0 : up_c(t[cut1 + 1]);
   const uint8_t a0 = up_c(t[cut2 - 2]), a1 = up_c(t[cut2 - 1]);
   for (int e = 0; e < 58; ++e)
     if (c_burset[e][0] == d0 && c_burset[e][1] == d1 && c_burset[e][2] == a0 && c_burset[e][3] == a1)
@@ -250,9 +252,10 @@ __device__ void op_borders(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *s
     int off_p = min_cut;
     uint32_t off_t1 = pos_p[min_cut], off_t2 = pos_s[len_p - min_cut];
     uint32_t best = mn_p[min_cut] + mn_s[len_p - min_cut];
-    int best_freq = burset_freq(J.b, (int)off_t1, len_t - (int)off_t2);
+    const int nul_at = (J.job->flags & PC_B_NUL_AFTER) ? len_t : -1;
+    int best_freq = burset_freq(J.b, (int)off_t1, len_t - (int)off_t2, nul_at);
     for (int i = min_cut + 1; i <= max_cut; ++i) {
-      const int freq = burset_freq(J.b, (int)pos_p[i], len_t - (int)pos_s[len_p - i]);
+      const int freq = burset_freq(J.b, (int)pos_p[i], len_t - (int)pos_s[len_p - i], nul_at);
       const uint32_t c = mn_p[i] + mn_s[len_p - i];
       if (best > c || (best == c && freq > best_freq)) {
         best = c; off_p = i; off_t1 = pos_p[i]; off_t2 = pos_s[len_p - i]; best_freq = freq;

@@ -290,8 +290,18 @@ __device__ __forceinline__ void lcs_block_generic(const uint8_t *s1, long long l
   if ((threadIdx.x & 31) == 0 && key) atomicMax(best_w, key);
 }
 
-__global__ void __launch_bounds__(LCS_TPB) k_lcs(PcDevBatch B, unsigned long long *best) {
-  const int w = blockIdx.y;
+// One flat grid over the blocks of ALL jobs of the batch (blk_prefix[w] = first block of job w): a 2 Mbp genome scan
+// and hundreds of 23 x 23 jobs share a launch without the small jobs paying for the long one's grid.
+__global__ void __launch_bounds__(LCS_TPB) k_lcs(PcDevBatch B, unsigned long long *best, const uint32_t *blk_prefix) {
+  __shared__ int s_job;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = B.n - 1;                             // last job whose first block is <= blockIdx.x
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (blk_prefix[mid] <= blockIdx.x) lo = mid; else hi = mid - 1; }
+    s_job = lo;
+  }
+  __syncthreads();
+  const int w = s_job;
+  const uint32_t bx = blockIdx.x - blk_prefix[w];
   const uint32_t ji = B.idx[w];
   const pc_job *job = B.jobs + ji;
   const uint8_t *s2 = B.arena + job->a_off;
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(LCS_TPB) k_lcs(PcDevBatch B, unsigned long lon
   const long long l1 = job->b_len;
   if (l2 > LCS_MAX_S2) return;                              // reported by k_lcs_finish
   // diagonals d = i1 - i2 in [-(l2-1), l1-1]; this block owns LCS_TPB consecutive ones
-  const long long d0 = (long long)blockIdx.x * LCS_TPB - (l2 - 1);
+  const long long d0 = (long long)bx * LCS_TPB - (l2 - 1);
   if (d0 > l1 - 1) return;
   extern __shared__ __align__(16) uint8_t sh[];
   if (l2 <= 64) lcs_block_bits(s1, l1, s2, l2, d0, sh, best + w);
@@ -336,19 +346,18 @@ void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count) {
 }
 
 // best: device array of B.n 64-bit slots (zeroed here); max_l1/max_l2 over the jobs of the batch
-int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, long long max_l1, int max_l2, cudaStream_t s) {
+int pc_lcs_blocks(long long l1, int l2) {                       // blocks one job needs (0 for an oversized s2: reported by the finish kernel)
+  if (l2 > LCS_MAX_S2 || l2 <= 0 || l1 <= 0) return 0;
+  return (int)((l1 + l2 - 1 + LCS_TPB - 1) / LCS_TPB);
+}
+
+int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t *d_blk_prefix, uint32_t total_blocks, int max_l2,
+                  cudaStream_t s) {
   if (max_l2 > LCS_MAX_S2) max_l2 = LCS_MAX_S2;
   cudaMemsetAsync(best, 0, sizeof(unsigned long long) * B.n, s);
-  const long long ndiag = max_l1 + max_l2;
   size_t sh = LCS_TPB + 2 * (size_t)max_l2 + 8;
   if (sh < LCS_TPB + 64 + 8 + 4 * ((LCS_TPB + 64) / 32 + 2) + 72 + 16) sh = LCS_TPB + 64 + 8 + 4 * ((LCS_TPB + 64) / 32 + 2) + 72 + 16;
-  for (int off = 0; off < B.n; off += 65535) {               // gridDim.y limit
-    PcDevBatch C = B;
-    C.idx = B.idx + off;
-    C.n = B.n - off < 65535 ? B.n - off : 65535;
-    dim3 grid((unsigned)((ndiag + LCS_TPB - 1) / LCS_TPB), (unsigned)C.n);
-    if (grid.x > 0) { k_lcs<<<grid, LCS_TPB, sh, s>>>(C, best + off); __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED); }
-  }
+  if (total_blocks > 0) { k_lcs<<<total_blocks, LCS_TPB, sh, s>>>(B, best, d_blk_prefix); __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED); }
   k_lcs_finish<<<(B.n + 127) / 128, 128, 0, s>>>(B, best);
   __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
   return 0;

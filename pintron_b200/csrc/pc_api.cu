@@ -71,7 +71,7 @@ struct pc_stream {
   void *slab = nullptr;
   unsigned long long *d_pool_need = nullptr, *h_pool_need = nullptr;   /* device counter + pinned mirror */
   int max_warps = 0;
-  std::vector<uint32_t> h_idx;
+  std::vector<uint32_t> h_idx, h_lcs;
   std::vector<int32_t> h_status;
   Pending pend;
   bool timers = false;
@@ -289,8 +289,20 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
       if (!c->d_genome) return fail(PC_E_ARG, "%s", "PC_OP_SEED before pc_genome_upload");
       pc_launch_seed(B, st->s, c->sm_count);
     } else if (op == PC_OP_LCS) {
-      if (st->lcs_best.reserve(8ull * B.n)) return PC_E_NOMEM;
-      pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, max_l1, max_l2, st->s);
+      // [best slots | block prefix] in one device buffer; the prefix comes from the host copy of the jobs
+      const size_t best_b = (8ull * B.n + 255u) & ~(size_t)255u;
+      if (st->lcs_best.reserve(best_b + 4ull * (B.n + 1))) return PC_E_NOMEM;
+      st->h_lcs.resize((size_t)B.n + 1);
+      uint64_t tot = 0;
+      for (size_t q = i; q < j; ++q) {
+        st->h_lcs[q - i] = (uint32_t)tot;
+        tot += (uint64_t)pc_lcs_blocks(h_jobs[order[q]].b_len, (int)h_jobs[order[q]].a_len);
+      }
+      st->h_lcs[B.n] = (uint32_t)tot;
+      if (tot >= 0x7fffffffull) return fail(PC_E_RANGE, "%s", "LCS batch too large for one launch");
+      uint32_t *d_prefix = (uint32_t *)((uint8_t *)st->lcs_best.p + best_b);
+      CU(cudaMemcpyAsync(d_prefix, st->h_lcs.data(), 4ull * (B.n + 1), cudaMemcpyHostToDevice, st->s));
+      pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, d_prefix, (uint32_t)tot, max_l2, st->s);
     } else if (op == PC_OP_GAP && cls < 3) {
       pc_launch_gap_pairs(cls, B, (int)max_l1, st->s, c->sm_count);
     } else {

@@ -59,7 +59,9 @@ __device__ __forceinline__ bool pc_is_n(uint8_t c) { return c == 'n' || c == 'N'
 void pc_launch_dp(int op, const PcDevBatch &B, cudaStream_t s, int sm_count);
 void pc_launch_gap_pairs(int cls, const PcDevBatch &B, int max_m, cudaStream_t s, int sm_count);
 void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count);
-int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, long long max_l1, int max_l2, cudaStream_t s);
+int pc_lcs_blocks(long long l1, int l2);
+int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t *d_blk_prefix, uint32_t total_blocks, int max_l2,
+                  cudaStream_t s);
 int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned long long **keys, uint32_t **pos,
                    uint32_t *n_out, uint32_t **bstart, int *shift, cudaStream_t s);
 extern unsigned long long g_pc_launches;

@@ -127,8 +127,10 @@ void fzl_remove(ef_fzlist *L, int at);
 /* ---- DP requests (sched.c) ----------------------------------------------------------------------------
  * dp_push queues one job for the calling fiber and returns its handle; dp_wait suspends the fiber until every
  * queued job has a result; dp_res / dp_var then read them (valid until the fiber's next dp_push). */
-typedef struct ef_str { const char *p; int len; bool in_genome; int gen_off; } ef_str;
-static inline ef_str S_(const char *p, int len) { ef_str s = {p, len < 0 ? 0 : len, false, 0}; return s; }
+typedef struct ef_str { const char *p; int len; bool in_genome; int gen_off; bool nul_after; } ef_str;   /* b-side strings that lie inside
+                                           the genome are sent as references (dp_push detects them); nul_after: BORDERS only */
+static inline ef_str S_(const char *p, int len) { ef_str s = {p, len < 0 ? 0 : len, false, 0, false}; return s; }
+static inline ef_str SZ_(const char *p, int len) { ef_str s = {p, len < 0 ? 0 : len, false, 0, true}; return s; }   /* t[len] reads as NUL */
 int dp_push(int op, ef_str a, ef_str b, int p0, int p1, int p2, int out_cap);
 void dp_wait(void);
 const int32_t *dp_res(int handle);

@@ -266,7 +266,7 @@ static bool external_ok_pre(const ef_fz *z, bool head, const char *g, bool *need
 }
 
 static int edit_job(const ef_factor *x, const char *g, const char *e) {
-  return dp_push(PC_OP_EDIT, S_(g + x->gs, x->ge - x->gs + 1), S_(e + x->es, x->ee - x->es + 1), 0, 0, 0, 0);
+  return dp_push(PC_OP_EDIT, S_(e + x->es, x->ee - x->es + 1), S_(g + x->gs, x->ge - x->gs + 1), 0, 0, 0, 0);   /* symmetric */
 }
 
 void clean_external_exons(ef_task *T, ef_fz *z, const char *g, const char *e) {
@@ -313,8 +313,8 @@ static void kband_jobs(ef_fz *z, const char *g, const char *e, int *handles) {
     const ef_factor *x = &z->f[i];
     handles[i] = -1;
     if (x->gs <= x->ge)
-      handles[i] = dp_push(PC_OP_KBAND, S_(g + x->gs, x->ge - x->gs + 1), S_(e + x->es, x->ee - x->es + 1),
-                           (int)max_exon_errors(x->ge - x->gs + 1), 0, 0, 0);
+      handles[i] = dp_push(PC_OP_KBAND, S_(e + x->es, x->ee - x->es + 1), S_(g + x->gs, x->ge - x->gs + 1),
+                           (int)max_exon_errors(x->ge - x->gs + 1), 0, 0, 0);       /* symmetric: the genome side goes by reference */
   }
 }
 
@@ -428,10 +428,8 @@ static bool check_gap_errors(ef_task *T, ef_fz *z, const char *e, const char *g)
     if (gp > 0) {
       const size_t gt = (size_t)(a->gs - d->ge - 1);
       if (gp > gt) fprintf(stderr, "* FATAL ...the gap on P cannot be greater than the gap on T!\n");
-      /* the reference hands refine_borders NUL-terminated copies: the byte after t is 0 there */
-      char *tc = ar_alloc(&T->ar, gt + 2);
-      memcpy(tc, g + d->ge + 1, gt);
-      h[i] = dp_push(PC_OP_BORDERS, S_(e + d->ee + 1, (int)gp), S_(tc, (int)gt), (int)gp, 0, (int)gp, 0);
+      /* the reference hands refine_borders NUL-terminated copies: the byte after t reads as 0 there */
+      h[i] = dp_push(PC_OP_BORDERS, S_(e + d->ee + 1, (int)gp), SZ_(g + d->ge + 1, (int)gt), (int)gp, 0, (int)gp, 0);
     }
   }
   dp_wait();

@@ -155,7 +155,7 @@ static void small_exon_at_prefix(ef_task *T, const ef_seq *est, ef_fz *z) {
   const size_t e1plen = MIN2(MIN2(e1len, g1len), (size_t)UB_SMALL_EXON);
   long pg_, pe_, cflen_;
   {
-    ef_str s1 = {g, p1->gs, true, 0};
+    ef_str s1 = {g, p1->gs, true, 0, false};
     const int h = dp_push(PC_OP_LCS, S_(epfact, (int)eplen), s1, 0, 0, 0, 0);
     dp_wait();
     cflen_ = dp_res(h)[1]; pg_ = dp_res(h)[2]; pe_ = dp_res(h)[3];

@@ -227,6 +227,9 @@ int dp_push(int op, ef_str a, ef_str b, int p0, int p1, int p2, int out_cap) {
     f->reqs = realloc(f->reqs, sizeof(ef_req) * (size_t)f->capreq);
   }
   ef_req *r = &f->reqs[f->nreq];
+  /* a genome-side string that lies inside the genome travels as (offset, length) into the device-resident copy */
+  const ef_seq *gen = f->task.gen;
+  if (!b.in_genome && b.p && b.p >= gen->seq && b.p + b.len <= gen->seq + gen->len) { b.in_genome = true; b.gen_off = (int)(b.p - gen->seq); }
   r->op = op; r->a = a; r->b = b; r->p0 = p0; r->p1 = p1; r->p2 = p2; r->out_cap = out_cap;
   return f->nreq++;
 }
@@ -314,11 +317,12 @@ static void gather(group *g) {
       j->a_off = (uint32_t)g->arena_len; j->a_len = (uint32_t)r->a.len;
       if (r->a.len) memcpy(g->arena + g->arena_len, r->a.p, (size_t)r->a.len);
       g->arena_len += (size_t)r->a.len;
-      if (r->b.in_genome) { j->flags = PC_B_IN_GENOME; j->b_off = (uint32_t)r->b.gen_off; j->b_len = (uint32_t)r->b.len; }
+      if (r->b.nul_after) j->flags |= PC_B_NUL_AFTER;
+      if (r->b.in_genome) { j->flags |= PC_B_IN_GENOME; j->b_off = (uint32_t)r->b.gen_off; j->b_len = (uint32_t)r->b.len; }
       else {
         j->b_off = (uint32_t)g->arena_len; j->b_len = (uint32_t)r->b.len;
-        /* BORDERS reads the byte that follows t (refine.c:362-374); callers keep it addressable */
-        const size_t nb = (size_t)r->b.len + (r->op == PC_OP_BORDERS ? 1u : 0u);
+        /* BORDERS reads the byte that follows t (refine.c:362-374); callers keep it addressable unless nul_after */
+        const size_t nb = (size_t)r->b.len + ((r->op == PC_OP_BORDERS && !r->b.nul_after) ? 1u : 0u);
         if (nb) memcpy(g->arena + g->arena_len, r->b.p, nb);
         g->arena_len += nb;
       }

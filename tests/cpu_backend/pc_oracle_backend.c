@@ -66,7 +66,10 @@ int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes, const pc_
       case PC_OP_EDIT: r[1] = (int32_t)po_edit(a, la, b, lb); break;
       case PC_OP_BORDERS: {
         if (j->p1 < 0 || j->p1 > j->p2 || j->p2 > la) { r[0] = PC_E_ARG; break; }
+        char *tz = NULL;
+        if (j->flags & PC_B_NUL_AFTER) { tz = calloc((size_t)lb + 2, 1); memcpy(tz, b, (size_t)lb); b = tz; }
         int out[4]; r[1] = po_borders(a, la, j->p1, j->p2, b, lb, (unsigned)j->p0, out);
+        free(tz);
         r[2] = out[0]; r[3] = out[1]; r[4] = out[2]; r[5] = out[3]; break;
       }
       case PC_OP_GAP: {

@@ -6,7 +6,7 @@ python - <<PY
 import os
 from pintron_b200.synth import Synth
 os.makedirs("/tmp/c3", exist_ok=True)
-s = Synth("C3", reads=$READS)
+s = Synth(os.environ.get("WORKLOAD", "C3"), reads=$READS)
 open("/tmp/c3/genomic.txt","wb").write(s.genome_fasta())
 open("/tmp/c3/ests.txt","wb").write(s.ests_fasta(0,$READS))
 PY
