@@ -127,7 +127,8 @@ void pc_stream_enable_timers(pc_stream *st, int on);
 void *pc_stream_cuda_stream(pc_stream *st);
 /* INT32 ALU micro-benchmark: lane-operations per second of independent add/min chains (the roofline
  * denominator for the DP kernels; SURVEY.md §8(d) asks for a measured figure). */
-double pc_measure_int_peak(pc_ctx *ctx);      /* the cudaStream_t, for callers that interoperate */
+double pc_measure_int_peak(pc_ctx *ctx);
+void pc_debug_dump(void);                     /* prints library-side timings to stderr when PC_PROFILE is set */      /* the cudaStream_t, for callers that interoperate */
 
 #ifdef __cplusplus
 }

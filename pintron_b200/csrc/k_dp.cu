@@ -218,7 +218,34 @@ __device__ int burset_freq(const uint8_t *t, int cut1, int cut2, int len_t) {
 }
 
 // ---- DP C: general_refine_borders (src/refine.c:106-190) --------------------------------------------------
-// a = p, b = t (the byte b[lb] must be readable: it is what the reference reads after t).
+// a = p, b = t (the byte b[lb] must be readable unless PC_B_NUL_AFTER: it is what the reference reads after t).
+// The reference fills two (len_p+1) x (t_win+1) matrices and then takes, per row, the minimum and its FIRST column.
+// Along the wavefront the cells of one row arrive in increasing column order, so the same (minimum, first argmin)
+// pair is kept per row while the sweep runs and no matrix is stored: O(len_p) scratch instead of O(len_p * t_win).
+__device__ void rowmin_dp(Str rows, int nr, Str cols, int nc, uint32_t *H, uint32_t *mn, uint32_t *pos, int lane) {
+  const int lo = -nr, W = nr + nc + 1;
+  for (int x = lane; x < W; x += 32) H[x] = PC_INF;
+  for (int i = lane; i <= nr; i += 32) { mn[i] = PC_INF; pos[i] = 0; }
+  __syncwarp();
+  for (int s = 0; s <= nr + nc; ++s) {
+    const int i_lo = max(0, s - nc), i_hi = min(nr, s);
+    for (int i = i_lo + lane; i <= i_hi; i += 32) {
+      const int j = s - i, x = j - i - lo;
+      uint32_t v;
+      if (i == 0) v = (uint32_t)j;
+      else if (j == 0) v = (uint32_t)i;
+      else {
+        v = H[x] + (rows.at(i - 1) == cols.at(j - 1) ? 0u : 1u);
+        v = min(v, H[x + 1] + 1u);
+        v = min(v, H[x - 1] + 1u);
+      }
+      H[x] = v;
+      if (mn[i] > v) { mn[i] = v; pos[i] = (uint32_t)j; }      // strict: the first minimum of the row stays
+    }
+    __syncwarp();
+  }
+}
+
 __device__ void op_borders(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *smem, int lane) {
   JobView J = view(B, w);
   const int len_p = J.la, len_t = J.lb;
@@ -226,28 +253,16 @@ __device__ void op_borders(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *s
   const int min_cut = J.job->p1, max_cut = J.job->p2;
   if (min_cut < 0 || min_cut > max_cut || max_cut > len_p) PC_FAIL(PC_E_ARG);
   const int t_win = (int)min((unsigned long long)len_p + max_errs, (unsigned long long)len_t);
-  const size_t cells = (size_t)(len_p + 1) * (t_win + 1);
   bool ok;
-  uint32_t *H = state_mem(B, wp, smem, (size_t)len_p + t_win + 1, lane, ok);
+  uint32_t *H = state_mem(B, wp, smem, (size_t)len_p + t_win + 1 + 4ull * (len_p + 1), lane, ok);
   if (!ok) PC_FAIL(PC_E_POOL);
-  uint32_t *M = (uint32_t *)pc_pool_alloc(B, wp, (2 * cells + 4ull * (len_p + 1)) * 4ull, lane);
-  if (!M) PC_FAIL(PC_E_POOL);
-  uint32_t *Mp = M, *Ms = M + cells, *mn = M + 2 * cells, *pos = mn + 2 * (len_p + 1);
+  uint32_t *mn = H + (len_p + t_win + 1), *pos = mn + 2 * (len_p + 1);
   // rows over p, columns over the first t_win chars of t (prefix side) / of reversed t (suffix side)
-  banded_dp<false, ST_MAT>(Str{J.a, 1}, len_p, Str{J.b, 1}, t_win, -len_p, t_win, H, nullptr, Mp, lane);
-  banded_dp<false, ST_MAT>(Str{J.a + len_p - 1, -1}, len_p, Str{J.b + len_t - 1, -1}, t_win, -len_p, t_win, H,
-                           nullptr, Ms, lane);
-  __syncwarp();
-  for (int r = lane; r < 2 * (len_p + 1); r += 32) {      // per-row minimum, FIRST argmin
-    const int side = r / (len_p + 1), i = r % (len_p + 1);
-    const uint32_t *row = (side ? Ms : Mp) + (size_t)i * (t_win + 1);
-    uint32_t best = i == 0 ? 0u : row[0], bj = 0;
-    if (i > 0)
-      for (int j = 1; j <= t_win; ++j) if (best > row[j]) { best = row[j]; bj = (uint32_t)j; }
-    mn[r] = best; pos[r] = bj;
-  }
+  rowmin_dp(Str{J.a, 1}, len_p, Str{J.b, 1}, t_win, H, mn, pos, lane);
+  rowmin_dp(Str{J.a + len_p - 1, -1}, len_p, Str{J.b + len_t - 1, -1}, t_win, H, mn + len_p + 1, pos + len_p + 1, lane);
   __syncwarp();
   if (lane == 0) {
+    mn[0] = 0; pos[0] = 0; mn[len_p + 1] = 0; pos[len_p + 1] = 0;      // row 0: min_pp[0] = min_sp[0] = 0 at column 0
     const uint32_t *mn_p = mn, *mn_s = mn + len_p + 1, *pos_p = pos, *pos_s = pos + len_p + 1;
     int off_p = min_cut;
     uint32_t off_t1 = pos_p[min_cut], off_t2 = pos_s[len_p - min_cut];
@@ -255,8 +270,9 @@ __device__ void op_borders(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *s
     const int nul_at = (J.job->flags & PC_B_NUL_AFTER) ? len_t : -1;
     int best_freq = burset_freq(J.b, (int)off_t1, len_t - (int)off_t2, nul_at);
     for (int i = min_cut + 1; i <= max_cut; ++i) {
-      const int freq = burset_freq(J.b, (int)pos_p[i], len_t - (int)pos_s[len_p - i], nul_at);
       const uint32_t c = mn_p[i] + mn_s[len_p - i];
+      if (best < c) continue;                                  // a worse split never wins: skip its Burset lookup
+      const int freq = burset_freq(J.b, (int)pos_p[i], len_t - (int)pos_s[len_p - i], nul_at);
       if (best > c || (best == c && freq > best_freq)) {
         best = c; off_p = i; off_t1 = pos_p[i]; off_t2 = pos_s[len_p - i]; best_freq = freq;
       }
@@ -267,25 +283,43 @@ __device__ void op_borders(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *s
 }
 
 // ---- DP E: find_longest_affix (src/factorization-refinement.c:1134-1172) ----------------------------------
+// Wanted: among the cells (e, g) with equal end characters and weight 2*D/(e+g) <= 0.17, the minimal weight, LAST in
+// row-major order on ties.  A qualifying cell has D <= 0.085*(e+g) <= wd := floor(0.085*(el+gl)) + 1, and every cell
+// whose true distance is <= wd lies within wd diagonals of the main one and is computed exactly by a DP restricted
+// to that band (off-band cells can only be over-estimated, which never makes a cell qualify): the sweep is
+// O((el+gl)*wd) instead of el*gl, and the reduction runs inside it, so nothing but the wavefront state is stored.
 __device__ void op_affix(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *smem, int lane) {
   JobView J = view(B, w);
   const int el = J.la, gl = J.lb;
+  const int wd = (int)(0.085 * ((double)el + (double)gl)) + 1;
+  const int lo = max(-wd, -el), hi = min(wd, gl), W = hi - lo + 1;
   bool ok;
-  uint32_t *H = state_mem(B, wp, smem, (size_t)el + gl + 1, lane, ok);
+  uint32_t *H = state_mem(B, wp, smem, (size_t)W, lane, ok);
   if (!ok) PC_FAIL(PC_E_POOL);
-  const size_t cells = (size_t)(el + 1) * (gl + 1);
-  uint32_t *M = (uint32_t *)pc_pool_alloc(B, wp, cells * 4ull, lane);
-  if (!M) PC_FAIL(PC_E_POOL);
-  banded_dp<false, ST_MAT>(Str{J.a, 1}, el, Str{J.b, 1}, gl, -el, gl, H, nullptr, M, lane);
+  for (int x = lane; x < W; x += 32) H[x] = PC_INF;
   __syncwarp();
-  // minimal weight 2*D/(e+g) among valid cells, LAST in row-major order on ties
   double best = 2.0; long long best_idx = -1;
-  const long long total = (long long)el * gl;
-  for (long long c = lane; c < total; c += 32) {
-    const int e = (int)(c / gl) + 1, g = (int)(c % gl) + 1;
-    if (J.a[e - 1] != J.b[g - 1]) continue;
-    const double wgt = 2.0 * ((double)M[(size_t)e * (gl + 1) + g]) / (double)((size_t)e + (size_t)g);
-    if (wgt <= 0.17 && wgt <= best) { best = wgt; best_idx = c; }   // c increases per lane
+  for (int s = 0; s <= el + gl; ++s) {
+    const int i_lo = max(max(0, s - gl), ceil_half(s - hi)), i_hi = min(min(el, s), floor_half(s - lo));
+    for (int i = i_lo + lane; i <= i_hi; i += 32) {
+      const int j = s - i, x = j - i - lo;
+      uint32_t v;
+      if (i == 0) v = (uint32_t)j;
+      else if (j == 0) v = (uint32_t)i;
+      else {
+        const bool eq = J.a[i - 1] == J.b[j - 1];
+        v = H[x] + (eq ? 0u : 1u);
+        v = min(v, (x + 1 < W ? H[x + 1] : PC_INF) + 1u);
+        v = min(v, (x > 0 ? H[x - 1] : PC_INF) + 1u);
+        if (eq) {
+          const double wgt = 2.0 * ((double)v) / (double)((size_t)i + (size_t)j);
+          const long long idx = (long long)(i - 1) * gl + (j - 1);
+          if (wgt <= 0.17 && (wgt < best || (wgt == best && idx > best_idx) || best_idx < 0)) { best = wgt; best_idx = idx; }
+        }
+      }
+      H[x] = v;
+    }
+    __syncwarp();
   }
   for (int o = 16; o > 0; o >>= 1) {
     const double ob = __shfl_xor_sync(0xffffffffu, best, o);

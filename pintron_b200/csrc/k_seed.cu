@@ -37,8 +37,19 @@ __global__ void k_bucket_starts(const unsigned long long *keys, uint32_t n, int 
 
 __device__ __forceinline__ int lcp(const uint8_t *P, int n, int p, const uint8_t *T, uint32_t G, uint32_t t) {
   const int lim = min(n - p, (int)(G - t));
+  const uint8_t *a = P + p, *b = T + t;
   int l = 0;
-  while (l < lim && P[p + l] == T[t + l]) ++l;
+  // eight independent byte loads per round instead of a chain of dependent ones
+  while (l + 4 <= lim) {
+    const uint8_t a0 = a[l], a1 = a[l + 1], a2 = a[l + 2], a3 = a[l + 3];
+    const uint8_t b0 = b[l], b1 = b[l + 1], b2 = b[l + 2], b3 = b[l + 3];
+    if (a0 != b0) return l;
+    if (a1 != b1) return l + 1;
+    if (a2 != b2) return l + 2;
+    if (a3 != b3) return l + 3;
+    l += 4;
+  }
+  while (l < lim && a[l] == b[l]) ++l;
   return l;
 }
 
@@ -76,9 +87,10 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane) {
   const int np = n - word + 1;               // positions that can start a word
   if (np <= 0 || G < (uint32_t)word) { if (lane == 0) { res[0] = PC_OK; res[1] = 0; } return; }
   // per-position arrays: bucket start, bucket end, D / offsets, counts
-  int *arr = (int *)pc_pool_alloc(B, wp, 6ull * np * sizeof(int), lane);
+  int *arr = (int *)pc_pool_alloc(B, wp, 10ull * np * sizeof(int), lane);
   if (!arr) { if (lane == 0) res[0] = PC_E_POOL; return; }
   int *b_lo = arr, *b_hi = arr + np, *offs = arr + 2 * np, *cnt = arr + 3 * np, *thr_a = arr + 4 * np, *ncand = arr + 5 * np;
+  TL *first2 = (TL *)(arr + 6 * np);           // the first two candidates of every position: S2 rarely has to extend again
   // S1: bucket, D(p), number of candidates >= mfl
   for (int p = lane; p < np; p += 32) {
     const unsigned long long h = hash_word(P + p, word);
@@ -93,7 +105,7 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane) {
       const uint32_t t = B.ix_pos[k];
       if (p > 0 && t > 0 && T[t - 1] == prev) continue;
       const int l = lcp(P, n, p, T, G, t);
-      if (l >= mfl) { ++c; D = max(D, l); }
+      if (l >= mfl) { if (c < 2) { first2[2 * p + c].t = (int)t; first2[2 * p + c].l = l; } ++c; D = max(D, l); }
     }
     b_lo[p] = (int)k0; b_hi[p] = (int)k;
     int thr = (int)(size_t)((double)D * B.depth_rate);
@@ -116,6 +128,9 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane) {
     const uint8_t prev = p > 0 ? P[p - 1] : 0;
     int c = 0;
     if (ncand[p] == 0) { cnt[p] = 0; continue; }
+    if (ncand[p] <= 2) {
+      for (int k = 0; k < ncand[p]; ++k) if (first2[2 * p + k].l >= thr) v[c++] = first2[2 * p + k];
+    } else
     for (int k = b_lo[p]; k < b_hi[p]; ++k) {
       const uint32_t t = B.ix_pos[k];
       if (p > 0 && t > 0 && T[t - 1] == prev) continue;

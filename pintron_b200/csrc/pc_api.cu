@@ -11,6 +11,15 @@ unsigned long long g_pc_launches = 0;
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const bool g_prof = getenv("PC_PROFILE") != nullptr;
 static double g_t[8];      /* check, reserve, h2d, sort, launch, d2h, sync (racy sums: diagnostics only) */
+static double g_op_ms[PC_OP_COUNT]; static unsigned long long g_op_launches[PC_OP_COUNT], g_retry_rounds, g_retry_jobs, g_pool_grows;
+extern "C" void pc_debug_dump(void) {
+  if (!g_prof) return;
+  static const char *nm[PC_OP_COUNT] = {"ALIGN", "KBAND", "EDIT", "BORDERS", "GAP", "AFFIX", "SUFCUT", "PRECUT", "LCS", "SEED"};
+  fprintf(stderr, "[pc profile] host: check %.3f reserve %.3f h2d %.3f sort %.3f launch %.3f d2h %.3f sync %.3f s\n", g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5], g_t[6]);
+  fprintf(stderr, "[pc profile] device ms per op:");
+  for (int i = 0; i < PC_OP_COUNT; ++i) if (g_op_launches[i]) fprintf(stderr, " %s %.1f (%llu launches)", nm[i], g_op_ms[i], g_op_launches[i]);
+  fprintf(stderr, "\n[pc profile] pool retries: %llu rounds, %llu jobs, %llu pool growths\n", g_retry_rounds, g_retry_jobs, g_pool_grows);
+}
 struct ProfDump { ~ProfDump() { if (g_prof) fprintf(stderr, "[pc profile] check %.3f reserve %.3f h2d %.3f sort %.3f launch %.3f d2h %.3f sync %.3f s\n", g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5], g_t[6]); } } g_prof_dump;
 #define PROF(slot, t0) do { if (g_prof) { double t1_ = now_s(); g_t[slot] += t1_ - (t0); (t0) = t1_; } } while (0)
 static thread_local char g_err[512] = "";
@@ -187,7 +196,7 @@ extern "C" void pc_stream_enable_timers(pc_stream *st, int on) { if (st) st->tim
 static void drain_events(pc_stream *st) {
   for (auto &e : st->ev_pending) {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, e.second.first, e.second.second) == cudaSuccess) st->op_ms[e.first] += ms;
+    if (cudaEventElapsedTime(&ms, e.second.first, e.second.second) == cudaSuccess) { st->op_ms[e.first] += ms; if (g_prof) g_op_ms[e.first] += ms; }
     st->ev_free.push_back(e.second.first);
     st->ev_free.push_back(e.second.second);
   }
@@ -283,7 +292,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
     B.idx = (const uint32_t *)st->idx.p + i;
     B.n = (int)(j - i);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (st->timers) { e0 = get_event(st); e1 = get_event(st); cudaEventRecord(e0, st->s); }
+    if (st->timers || g_prof) { e0 = get_event(st); e1 = get_event(st); cudaEventRecord(e0, st->s); }
     const unsigned long long before = g_pc_launches;
     if (op == PC_OP_SEED) {
       if (!c->d_genome) return fail(PC_E_ARG, "%s", "PC_OP_SEED before pc_genome_upload");
@@ -309,7 +318,8 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
       pc_launch_dp((int)op, B, st->s, c->sm_count);
     }
     st->op_launches[op] += g_pc_launches - before;
-    if (st->timers) { cudaEventRecord(e1, st->s); st->ev_pending.push_back({(int)op, {e0, e1}}); }
+    if (g_prof) g_op_launches[op] += 1;
+    if (st->timers || g_prof) { cudaEventRecord(e1, st->s); st->ev_pending.push_back({(int)op, {e0, e1}}); }
     i = j;
   }
   CU(cudaMemcpyAsync(st->h_pool_need, st->d_pool_need, 8, cudaMemcpyDeviceToHost, st->s));
@@ -396,6 +406,7 @@ extern "C" int pc_stream_sync(pc_stream *st) {
   double tp = g_prof ? now_s() : 0;
   CU(cudaStreamSynchronize(st->s));
   PROF(6, tp);
+  if (g_prof) drain_events(st);
   Pending &P = st->pend;
   if (!P.active) return 0;
   // Jobs whose scratch did not fit their warp's pool slot are re-run with fewer warps (= larger slots); the pool
@@ -410,6 +421,7 @@ extern "C" int pc_stream_sync(pc_stream *st) {
     std::vector<uint32_t> redo;
     for (int i = 0; i < P.njobs; ++i) if (status[(size_t)i * PC_RES_INTS] == PC_E_POOL) redo.push_back((uint32_t)i);
     if (redo.empty()) break;
+    if (g_prof) { ++g_retry_rounds; g_retry_jobs += redo.size(); }
     const unsigned long long need = std::max<unsigned long long>(*st->h_pool_need, 4096) + 4096;
     if (need > st->pool.cap) {
       size_t free_b = 0, total_b = 0;
@@ -419,6 +431,7 @@ extern "C" int pc_stream_sync(pc_stream *st) {
         return fail(PC_E_NOMEM, "%s", "a single job needs more scratch than the device has free");
       }
       size_t want = std::min<size_t>(need * std::min<size_t>(redo.size(), 32), st->pool.cap + free_b / 2);
+      if (g_prof) ++g_pool_grows;
       int rc = st->pool.reserve(std::max<size_t>(want, need));
       if (rc) { P.active = false; st->max_warps = 0; return rc; }
     }

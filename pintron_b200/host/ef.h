@@ -46,7 +46,7 @@ int ef_config_parse(ef_config *c, int argc, char **argv);   /* also writes ./con
 
 /* ---- per-EST bump arena --------------------------------------------------------------------------- */
 typedef struct ef_chunk { struct ef_chunk *next; size_t cap, used; } ef_chunk;
-typedef struct ef_arena { ef_chunk *head; } ef_arena;
+typedef struct ef_arena { ef_chunk *head, *cur; } ef_arena;
 void *ar_alloc(ef_arena *a, size_t bytes);         /* zeroed, 16-aligned */
 void ar_reset(ef_arena *a);                        /* keeps the first chunk */
 void ar_free_all(ef_arena *a);

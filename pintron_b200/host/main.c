@@ -205,6 +205,7 @@ int main(int argc, char **argv) {
     fprintf(stderr, "* INFO  device batches: %llu, device jobs: %llu, kernel launches: %llu, summed wait on device: %.3f s, ESTs/s: %.1f\n",
             (unsigned long long)batches, (unsigned long long)jobs, (unsigned long long)pc_launch_count(), gpu_wait,
             t_alg > 0 ? (double)nest / t_alg : 0.0);
+  pc_debug_dump();
   fflush(NULL);
   _exit(0);        /* every output file is closed; skip the CUDA runtime's exit-time tear-down */
 }

@@ -17,6 +17,7 @@
 #include <sys/time.h>
 #include <ucontext.h>
 #include <unistd.h>
+#include <malloc.h>
 
 #define FIBER_STACK (512u << 10)
 
@@ -27,17 +28,24 @@ double ef_now(void) {
 }
 
 /* ---- arena / buffers ------------------------------------------------------------------------------- */
+/* Chunks are kept across ESTs (ar_reset only rewinds): giving big chunks back to the system means munmap, and
+ * every munmap interrupts all threads of the process to flush their TLBs — with a dozen workers handling long mRNAs
+ * that alone was most of the run time.  head = the chunk being filled; chunks after it on the list are spare. */
+#define AR_HDR (((sizeof(ef_chunk)) + 15u) & ~(size_t)15u)
 void *ar_alloc(ef_arena *a, size_t bytes) {
   bytes = (bytes + 15u) & ~(size_t)15u;
-  ef_chunk *c = a->head;
-  if (!c || c->used + bytes > c->cap) {
+  ef_chunk *c = a->cur;
+  while (!c || c->used + bytes > c->cap) {
+    ef_chunk *nx = c ? c->next : a->head;
+    if (nx && AR_HDR + bytes <= nx->cap) { nx->used = AR_HDR; a->cur = c = nx; continue; }
     size_t cap = 1u << 16;
     if (c && c->cap * 2 > cap) cap = MIN2(c->cap * 2, (size_t)8 << 20);
-    if (cap < bytes + sizeof(ef_chunk) + 16) cap = bytes + sizeof(ef_chunk) + 16;
+    if (cap < bytes + AR_HDR + 16) cap = bytes + AR_HDR + 16;
     ef_chunk *n = malloc(cap);
     if (!n) { fprintf(stderr, "* FATAL est-fact: out of memory\n"); exit(1); }
-    n->next = c; n->cap = cap; n->used = (sizeof(ef_chunk) + 15u) & ~(size_t)15u;
-    a->head = c = n;
+    n->cap = cap; n->used = AR_HDR;
+    if (c) { n->next = c->next; c->next = n; } else { n->next = a->head; a->head = n; }
+    a->cur = c = n;
   }
   void *p = (char *)c + c->used;
   c->used += bytes;
@@ -46,12 +54,21 @@ void *ar_alloc(ef_arena *a, size_t bytes) {
 }
 
 void ar_reset(ef_arena *a) {
-  while (a->head && a->head->next) { ef_chunk *n = a->head->next; free(a->head); a->head = n; }
-  if (a->head) a->head->used = (sizeof(ef_chunk) + 15u) & ~(size_t)15u;
+  /* rewind; keep at most 64 MB of chunks for the next EST */
+  size_t kept = 0;
+  ef_chunk **pp = &a->head;
+  while (*pp) {
+    ef_chunk *c = *pp;
+    if (kept + c->cap > ((size_t)64 << 20) && c != a->head) { *pp = c->next; free(c); continue; }
+    kept += c->cap; c->used = AR_HDR;
+    pp = &c->next;
+  }
+  a->cur = a->head;
 }
 
 void ar_free_all(ef_arena *a) {
   while (a->head) { ef_chunk *n = a->head->next; free(a->head); a->head = n; }
+  a->cur = NULL;
 }
 
 static void buf_reserve(ef_buf *b, size_t extra) {
@@ -488,6 +505,9 @@ static void *prepare_main(void *arg) {
 }
 
 void sched_prepare(const ef_config *cfg, const ef_seq *gen) {
+  /* no mmap / munmap / trim behind malloc: see ar_alloc */
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
+  mallopt(M_TRIM_THRESHOLD, 1 << 30);
   memset(&g_prep, 0, sizeof g_prep);
   g_prep.cfg = cfg; g_prep.gen = gen;
   if (pthread_create(&g_prep.th, NULL, prepare_main, NULL)) { perror("pthread_create"); exit(1); }

@@ -44,6 +44,7 @@ void *pc_host_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 1); }
 void pc_host_free(void *p) { free(p); }
 int pc_stream_sync(pc_stream *s) { (void)s; return 0; }
 uint64_t pc_launch_count(void) { return g_jobs; }
+void pc_debug_dump(void) {}
 
 int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes, const pc_job *jobs, int njobs, int32_t *res,
               uint8_t *var_out, size_t var_out_bytes) {
