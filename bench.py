@@ -33,6 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "est_fact_ESTs_per_sec"
+WORKLOADS = {"C3": "C3: synthetic 200 kbp genomic region x ESTs of 300-800 nt",
+             "C4": "C4: synthetic 2 Mbp multi-gene locus x ESTs (80 %) and mRNAs of 1-6 kbp (20 %), long introns, polyA tails"}
 OPS_PER_CELL = {"ALIGN": 5, "KBAND": 5, "GAP": 9}      # useful int ops per DP cell, SURVEY.md §8(d)
 
 
@@ -120,7 +122,7 @@ def run_reference(args, rank, world):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/est-fact not built (make -C oracle ref)"}))
         return
     per_core = args.ref_reads_per_core
-    synth = Synth("C3", reads=cores * per_core)
+    synth = Synth(args.workload, reads=cores * per_core)
     gtxt = synth.genome_fasta()
     tmp = tempfile.mkdtemp(prefix="pintron_ref_")
     dirs = []
@@ -145,25 +147,25 @@ def run_reference(args, rank, world):
     n = cores * per_core
     sec = sum(times) / len(times)
     v = n / sec
-    sample = f"{n} C3 ESTs per step = {cores} shards x {per_core}, one est-fact process per core, each rebuilding its suffix tree"
+    sample = f"{n} {args.workload} ESTs per step = {cores} shards x {per_core}, one est-fact process per core, each rebuilding its suffix tree"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "ESTs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "C3: synthetic 200 kbp genomic region x ESTs of 300-800 nt (bounded sample)", "reads_per_step": n},
+        "config": {"workload": WORKLOADS[args.workload] + " (bounded sample)", "reads_per_step": n},
         "cpu_baseline": {"value": v, "unit": "ESTs/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "ESTs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def cpu_baseline_sample(seconds_budget=20.0):
+def cpu_baseline_sample(workload="C3", seconds_budget=20.0):
     """Reference est-fact on a bounded sample with every host core (kind=reference), else the oracle port."""
     from pintron_b200.synth import Synth
     exe = os.path.join(ROOT, "oracle", "_ref", "est-fact")
     cores = os.cpu_count() or 1
     if not os.path.exists(exe):
         return None
-    per_core = 150
-    synth = Synth("C3", reads=cores * per_core)
+    per_core = 150 if workload == "C3" else 12
+    synth = Synth(workload, reads=cores * per_core)
     tmp = tempfile.mkdtemp(prefix="pintron_cpu_")
     gtxt = synth.genome_fasta()
     dirs = []
@@ -182,7 +184,7 @@ def cpu_baseline_sample(seconds_budget=20.0):
         return None
     n = cores * per_core
     return {"value": n / sec, "unit": "ESTs/s", "cores": cores, "kind": "reference",
-            "sample": f"{n} C3 ESTs, {cores} est-fact processes (one per core, {per_core} ESTs each), wall {sec:.2f} s"}
+            "sample": f"{n} {workload} ESTs, {cores} est-fact processes (one per core, {per_core} ESTs each), wall {sec:.2f} s"}
 
 
 def main():
@@ -194,6 +196,7 @@ def main():
     ap.add_argument("--reads", type=int, default=20000, help="ESTs per GPU per step, device leg")
     ap.add_argument("--e2e-reads", type=int, default=100000, help="ESTs per GPU per step, whole-program leg")
     ap.add_argument("--ref-reads-per-core", type=int, default=200)
+    ap.add_argument("--workload", default="C3", choices=["C3", "C4"], help="synthetic shape (pintron_b200/synth.py); C3 is the default bench line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the whole-program leg (profiling runs: ncu would follow the child)")
     args = ap.parse_args()
@@ -219,7 +222,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    synth = Synth("C3", reads=args.reads * world)
+    synth = Synth(args.workload, reads=args.reads * world)
     cu = pintron_b200.Cuda(local)
     L = cu.L
     cu.genome_upload(synth.genome, 15, 0.2)
@@ -275,7 +278,7 @@ def main():
         raise SystemExit("bench.py: pintron_b200/bin/est-fact is not built (python __graft_entry__.py)")
     work = tempfile.mkdtemp(prefix=f"pintron_e2e_r{rank}_")
     if not args.no_e2e:
-        e2e_synth = Synth("C3", reads=args.e2e_reads * world)
+        e2e_synth = Synth(args.workload, reads=args.e2e_reads * world)
         open(os.path.join(work, "genomic.txt"), "wb").write(e2e_synth.genome_fasta())
         open(os.path.join(work, "ests.txt"), "wb").write(e2e_synth.ests_fasta(rank * args.e2e_reads, args.e2e_reads))
     cores = os.cpu_count() or 1
@@ -378,12 +381,12 @@ def main():
                 "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
 
     if rank == 0:
-        cpu = None if args.no_cpu_baseline else cpu_baseline_sample()
+        cpu = None if args.no_cpu_baseline else cpu_baseline_sample(args.workload)
         line = {
             "metric": METRIC, "value": value, "unit": "ESTs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
-            "config": {"workload": "C3: synthetic 200 kbp genomic region x ESTs of 300-800 nt, device hot path "
+            "config": {"workload": WORKLOADS[args.workload] + ", device hot path "
                                    "(SEED + ALIGN/KBAND/GAP/LCS jobs from the simulated exon structure) for `value`; the whole est-fact program for `e2e`",
                        "reads_per_gpu_per_step": n_reads, "jobs_per_gpu_per_step": n, "l2": "flushed between steps (256 MB write)",
                        "sharding": f"ESTs dealt to {world} rank(s), genome index replicated, no collective"},

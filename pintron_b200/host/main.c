@@ -11,11 +11,14 @@
 #define _GNU_SOURCE
 #include "ef.h"
 #include <unistd.h>
+#include <pthread.h>
+#include <stdatomic.h>
 
 typedef struct est_item {
   ef_seq fwd, rc;
   bool has_rc;
   ef_buf raw, pest, megs, pmegs, edges, info;
+  _Atomic int done;               /* set by the worker when every buffer above is final */
 } est_item;
 
 typedef struct run_ctx {
@@ -105,9 +108,15 @@ static bool compute_est_fact(ef_task *T, const run_ctx *R, est_item *it, const e
   }
 }
 
+static void est_task_body(ef_task *T, run_ctx *R, est_item *it);
 static void est_task(ef_task *T, size_t index, void *user) {
   run_ctx *R = user;
   est_item *it = &R->items[index];
+  est_task_body(T, R, it);
+  atomic_store_explicit(&it->done, 1, memory_order_release);
+}
+
+static void est_task_body(ef_task *T, run_ctx *R, est_item *it) {
   /* EST preparation (main-est-fact.c:190-213) */
   ef_set_gb(&it->fwd);
   ef_set_strand_and_rc(&it->fwd);
@@ -119,6 +128,25 @@ static void est_task(ef_task *T, size_t index, void *user) {
     ar_reset(&T->ar);
     compute_est_fact(T, R, it, &it->rc);
   }
+}
+
+/* The writer: streams the per-EST records to the six files in INPUT order while the workers are still running. */
+typedef struct writer_ctx { est_item *items; size_t n; FILE *f[6]; double busy_s; } writer_ctx;
+
+static void *writer_main(void *arg) {
+  writer_ctx *W = arg;
+  for (size_t i = 0; i < W->n; ++i) {
+    est_item *it = &W->items[i];
+    while (!atomic_load_explicit(&it->done, memory_order_acquire)) usleep(200);
+    const double t0 = ef_now();
+    ef_buf *b[6] = {&it->raw, &it->pest, &it->megs, &it->pmegs, &it->edges, &it->info};
+    for (int k = 0; k < 6; ++k) {
+      if (b[k]->len) fwrite(b[k]->p, 1, b[k]->len, W->f[k]);
+      buf_free(b[k]);
+    }
+    W->busy_s += ef_now() - t0;
+  }
+  return NULL;
 }
 
 static FILE *open_out(const char *name) {
@@ -159,22 +187,17 @@ int main(int argc, char **argv) {
   }
 
   run_ctx R = {&cfg, gen, gen->orig, items};
+  writer_ctx W = {items, nest, {f_raw, f_pest, f_megs, f_pmegs, f_edges, f_info}, 0.0};
+  pthread_t wth;
+  if (pthread_create(&wth, NULL, writer_main, &W)) { perror("pthread_create"); return 1; }
   const double t_alg0 = ef_now();
   if (sched_run(&cfg, gen, nest, est_task, &R)) return 1;
   const double t_alg = ef_now() - t_alg0;
 
   const double t_io1 = ef_now();
-  for (size_t i = 0; i < nest; ++i) {
-    est_item *it = &items[i];
-    if (it->raw.len) fwrite(it->raw.p, 1, it->raw.len, f_raw);
-    if (it->pest.len) fwrite(it->pest.p, 1, it->pest.len, f_pest);
-    if (it->megs.len) fwrite(it->megs.p, 1, it->megs.len, f_megs);
-    if (it->pmegs.len) fwrite(it->pmegs.p, 1, it->pmegs.len, f_pmegs);
-    if (it->edges.len) fwrite(it->edges.p, 1, it->edges.len, f_edges);
-    if (it->info.len) fwrite(it->info.p, 1, it->info.len, f_info);
-  }
+  pthread_join(wth, NULL);
   fclose(f_raw); fclose(f_megs); fclose(f_pmegs); fclose(f_info); fclose(f_pest); fclose(f_edges);
-  t_io += ef_now() - t_io1;
+  t_io += ef_now() - t_io1 + W.busy_s;
   fprintf(finfo, "end\t%ld\n", (long)time(NULL));
   fclose(finfo);
 
