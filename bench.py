@@ -89,6 +89,26 @@ class ClockSampler(threading.Thread):
         self.gpu, self.samples, self.stop_flag = gpu, [], False
 
     def run(self):
+        """NVML in-process (cheap); nvidia-smi as the fallback.  Sample rows: [sm_mhz, sm_max_mhz, hw_slowdown, hw_thermal,
+        sw_thermal, sw_power_cap] with 'Active' / 'Not Active' strings for the reasons."""
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            bits = [(N.nvmlClocksThrottleReasonHwSlowdown, 2), (N.nvmlClocksThrottleReasonHwThermalSlowdown, 3),
+                    (N.nvmlClocksThrottleReasonSwThermalSlowdown, 4), (N.nvmlClocksThrottleReasonSwPowerCap, 5)]
+            while not self.stop_flag:
+                row = [str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx), "Not Active", "Not Active", "Not Active", "Not Active"]
+                r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for b, i in bits:
+                    if r & b:
+                        row[i] = "Active"
+                self.samples.append(row)
+                time.sleep(0.1)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
@@ -99,7 +119,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(1.0)
 
     def summary(self):
         if not self.samples:
