@@ -74,12 +74,18 @@ __device__ int warp_exscan(int *v, int n, int lane) {
 //  ascending t; filter A inside one p; filter B against the list of p-1; emit (p,t,l) by ascending p.
 struct TL { int t, l; };
 
-__device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane) {
+#define SEED_TILE 2048      /* EST bytes staged in shared memory per warp (longer ESTs are read through L1) */
+__device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane, uint8_t *tile) {
   const uint32_t ji = B.idx[w];
   const pc_job *job = B.jobs + ji;
   int32_t *res = B.res + (size_t)ji * PC_RES_INTS;
   const uint8_t *P = B.arena + job->a_off;
   const int n = (int)job->a_len, mfl = job->p0, word = B.ix_word;
+  if (n <= SEED_TILE) {                      // the EST is read ~ word + LCP times per position: keep it on chip
+    for (int i = lane; i < n; i += 32) tile[i] = P[i];
+    __syncwarp();
+    P = tile;
+  }
   const uint8_t *T = B.genome;
   const uint32_t G = B.genome_len;
   int32_t *out = (int32_t *)(B.var_out + job->out_off);
@@ -179,12 +185,13 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane) {
 }
 
 __global__ void __launch_bounds__(128) k_seed(PcDevBatch B) {
+  __shared__ uint8_t tiles[4][SEED_TILE];
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   WarpPool wp = pc_warp_pool(B, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < B.n; w += nwarps) {
     wp.used = 0;
-    seed_one(B, wp, w, lane);
+    seed_one(B, wp, w, lane, tiles[threadIdx.x >> 5]);
     __syncwarp();
   }
 }

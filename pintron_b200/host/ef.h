@@ -182,6 +182,7 @@ typedef struct ef_job_result {          /* per input EST, filled by the workers 
 
 typedef void (*ef_task_fn)(ef_task *T, size_t index, void *user);
 void sched_prepare(const ef_config *cfg, const ef_seq *gen);   /* optional: start device set-up early, in the background */
+void sched_set_order(const uint32_t *order);                       /* optional permutation of the items: dispatch order */
 int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_fn fn, void *user);
 void sched_stats(double *gpu_wait_s, uint64_t *batches, uint64_t *jobs);
 void sched_bytes(uint64_t *h2d, uint64_t *d2h);                    /* bytes staged to / from the devices */

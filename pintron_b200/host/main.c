@@ -186,6 +186,21 @@ int main(int argc, char **argv) {
     it->fwd = ests[i];       /* strand / reverse-complement / polyA masking happen in est_task, on the worker threads */
   }
 
+  /* EST batcher: inside windows of 32 768 input records the ESTs are dispatched longest first, so the ESTs in flight
+   * together (and the jobs of one device batch) have similar sizes; the writer still emits input order. */
+  uint32_t *order = malloc(sizeof(uint32_t) * (nest ? nest : 1));
+  {
+    const size_t WIN = 32768;
+    uint32_t cnt[65];
+    for (size_t w0 = 0; w0 < nest; w0 += WIN) {
+      const size_t w1 = MIN2(nest, w0 + WIN);
+      memset(cnt, 0, sizeof cnt);                       /* counting sort on min(len / 64, 63), descending */
+      for (size_t i = w0; i < w1; ++i) { size_t b = strlen(ests[i].seq) >> 6; if (b > 63) b = 63; ++cnt[63 - b + 1]; }
+      for (int b = 0; b < 64; ++b) cnt[b + 1] += cnt[b];
+      for (size_t i = w0; i < w1; ++i) { size_t b = strlen(ests[i].seq) >> 6; if (b > 63) b = 63; order[w0 + cnt[63 - b]++] = (uint32_t)i; }
+    }
+  }
+  sched_set_order(order);
   run_ctx R = {&cfg, gen, gen->orig, items};
   writer_ctx W = {items, nest, {f_raw, f_pest, f_megs, f_pmegs, f_edges, f_info}, 0.0};
   pthread_t wth;

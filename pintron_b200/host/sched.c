@@ -170,6 +170,7 @@ typedef struct worker {
 
 static _Atomic size_t g_next_item;
 static size_t g_n_items;
+static const uint32_t *g_order;       /* dispatch order (length-sorted windows), NULL = input order */
 static __thread fiber *tl_fiber;
 static __thread worker *tl_worker;
 static uint64_t g_batches, g_jobs, g_h2d, g_d2h;
@@ -393,7 +394,7 @@ static bool run_group(worker *w, group *g) {
       if (f->state == F_FREE || f->state == F_DONE) {
         size_t idx = atomic_fetch_add(&g_next_item, 1);
         if (idx >= g_n_items) { f->state = F_FREE; break; }
-        fiber_start(w, g, f, idx);
+        fiber_start(w, g, f, g_order ? g_order[idx] : idx);
       }
       if (f->state != F_RUNNABLE) break;
       tl_fiber = f;
@@ -460,6 +461,8 @@ static void *worker_main(void *arg) {
   pthread_mutex_unlock(&g_stat_mu);
   return NULL;
 }
+
+void sched_set_order(const uint32_t *order) { g_order = order; }
 
 void sched_bytes(uint64_t *h2d, uint64_t *d2h) { *h2d = g_h2d; *d2h = g_d2h; }
 
