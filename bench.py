@@ -315,6 +315,12 @@ def main():
             if "bytes host->device" in line:
                 w = line.replace(",", "").split()
                 e2e_info["h2d"], e2e_info["d2h"] = int(w[w.index("host->device:") + 1]), int(w[w.index("device->host:") + 1])
+            if "scheduler:" in line and "workers" in line:
+                w = line.replace(",", "").split()
+                e2e_info["context_index_s"] = float(w[w.index("index") + 1])
+                e2e_info["workers_s"] = float(w[w.index("workers") + 1])
+            if "@Timer Total" in line:
+                e2e_info["program_total_s"] = int(line.split()[-2]) / 1e6
             if "kernel launches:" in line:
                 w = line.replace(",", "").split()
                 e2e_info["launches"] = int(w[w.index("launches:") + 1])
@@ -419,7 +425,10 @@ def main():
                     "what": "one run of the shipped est-fact program per step (process start, CUDA context, index build, "
                             "host control flow, every H2D/D2H copy, six output files): wall clock of the process",
                     "ests_per_gpu_per_step": args.e2e_reads, "ests_aligned_rank0": n_out, "host_threads_per_gpu": threads,
-                    "device_jobs_per_step": e2e_info.get("jobs"), "gpu_launches_per_step": e2e_info.get("launches")},
+                    "device_jobs_per_step": e2e_info.get("jobs"), "gpu_launches_per_step": e2e_info.get("launches"),
+                    "last_step_breakdown_s": {"cuda_context_and_genome_index": e2e_info.get("context_index_s"),
+                                              "all_ests_through_workers": e2e_info.get("workers_s"),
+                                              "program_total": e2e_info.get("program_total_s")}},
             "host_buffers_device_path": {"value": total_reads / (ms_step_host * 1e-3), "unit": "ESTs/s", "ms_per_step": ms_step_host,
                                          "h2d_bytes_per_step": int(len(batch.arena) + jobs.nbytes),
                                          "d2h_bytes_per_step": int(n * PC_RES_INTS * 4 + batch.var_bytes),

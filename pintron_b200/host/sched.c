@@ -16,6 +16,22 @@
 #include <sys/mman.h>
 #include <sys/time.h>
 #include <ucontext.h>
+
+/* Fiber switch.  glibc's swapcontext saves and restores the signal mask with a system call on every switch; an EST
+ * yields about a hundred times, so on x86-64 the switch is done by hand: callee-saved registers + stack pointer. */
+#if defined(__x86_64__)
+#define EF_FAST_SWITCH 1
+__attribute__((naked, noinline)) static void ctx_switch(void **save_sp, void *load_sp) {
+  __asm__ volatile(
+      "pushq %rbp\n\tpushq %rbx\n\tpushq %r12\n\tpushq %r13\n\tpushq %r14\n\tpushq %r15\n\t"
+      "movq %rsp, (%rdi)\n\t"
+      "movq %rsi, %rsp\n\t"
+      "popq %r15\n\tpopq %r14\n\tpopq %r13\n\tpopq %r12\n\tpopq %rbx\n\tpopq %rbp\n\t"
+      "ret\n");
+}
+#else
+#define EF_FAST_SWITCH 0
+#endif
 #include <unistd.h>
 #include <malloc.h>
 
@@ -128,6 +144,7 @@ typedef struct ef_req { int op; ef_str a, b; int p0, p1, p2, out_cap; } ef_req;
 
 typedef struct fiber {
   ucontext_t ctx;
+  void *sp;                 /* saved stack pointer (fast switch) */
   void *stack;
   int state;
   size_t index;
@@ -160,6 +177,7 @@ typedef struct worker {
   pc_ctx *ctx;
   group g[2];
   ucontext_t main_ctx;
+  void *main_sp;
   const ef_config *cfg;
   const ef_seq *gen;
   ef_task_fn fn;
@@ -213,7 +231,12 @@ static void fiber_entry(void) {
   w->fn(&f->task, f->index, w->user);
   phase_account();
   f->state = F_DONE;
+#if EF_FAST_SWITCH
+  ctx_switch(&f->sp, w->main_sp);
+#else
   swapcontext(&f->ctx, &w->main_ctx);
+#endif
+  __builtin_unreachable();
 }
 
 static void fiber_start(worker *w, group *g, fiber *f, size_t index) {
@@ -222,11 +245,21 @@ static void fiber_start(worker *w, group *g, fiber *f, size_t index) {
     if (f->stack == MAP_FAILED) { perror("mmap fiber stack"); exit(1); }
     mprotect(f->stack, 4096, PROT_NONE);
   }
+#if EF_FAST_SWITCH
+  {
+    uintptr_t *sp = (uintptr_t *)(((uintptr_t)f->stack + FIBER_STACK) & ~(uintptr_t)15);
+    *--sp = 0;                          /* the return address fiber_entry never uses (keeps the ABI stack alignment) */
+    *--sp = (uintptr_t)fiber_entry;     /* where the first switch "returns" to */
+    for (int r = 0; r < 6; ++r) *--sp = 0;   /* rbp rbx r12 r13 r14 r15 */
+    f->sp = sp;
+  }
+#else
   getcontext(&f->ctx);
   f->ctx.uc_stack.ss_sp = f->stack;
   f->ctx.uc_stack.ss_size = FIBER_STACK;
   f->ctx.uc_link = NULL;
   makecontext(&f->ctx, fiber_entry, 0);
+#endif
   f->index = index;
   f->state = F_RUNNABLE;
   f->nreq = 0;
@@ -258,7 +291,11 @@ void dp_wait(void) {
   f->state = F_WAITING;
   phase_account();
   f->phase = tl_phase;
+#if EF_FAST_SWITCH
+  ctx_switch(&f->sp, tl_worker->main_sp);
+#else
   swapcontext(&f->ctx, &tl_worker->main_ctx);
+#endif
   /* resumed: results are in the group's batch buffers */
   tl_phase = f->phase; tl_mark = ef_now();
   for (int i = 0; i < f->nreq; ++i) {
@@ -398,7 +435,11 @@ static bool run_group(worker *w, group *g) {
       }
       if (f->state != F_RUNNABLE) break;
       tl_fiber = f;
+#if EF_FAST_SWITCH
+      ctx_switch(&w->main_sp, f->sp);
+#else
       swapcontext(&w->main_ctx, &f->ctx);
+#endif
       tl_fiber = NULL;
       if (f->state == F_WAITING) break;       /* F_DONE: loop to pick the next item */
     }
