@@ -157,6 +157,9 @@ static FILE *open_out(const char *name) {
 
 int main(int argc, char **argv) {
   const double t0 = ef_now();
+  /* load every kernel when the context is created (one thread) instead of lazily at first launch, when two dozen
+   * worker threads would queue up behind the module loader */
+  setenv("CUDA_MODULE_LOADING", "EAGER", 0);
   ef_config cfg;
   if (ef_config_parse(&cfg, argc, argv)) return 1;
   if (!cfg.quiet) fprintf(stderr, "* INFO  EST-FACTORIZATION v2 (B200 build)\n");
