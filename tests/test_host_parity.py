@@ -10,7 +10,7 @@ import pytest
 
 import estfact_util as U
 
-SMALL = ["test-AMBN", "test-788", "test-mattia1", "test-mattia3", "test-CPB2"]
+SMALL = ["test-AMBN", "test-788", "test-mattia1", "test-mattia3", "test-CPB2", "edge-cases"]
 
 
 @pytest.fixture(scope="module")
@@ -43,6 +43,15 @@ def test_cli_contract(cpu_bin, tmp_path):
     assert p.returncode != 0
     p = subprocess.run([cpu_bin, "--version"], cwd=str(tmp_path), capture_output=True)
     assert p.returncode == 0 and b"est-fact 0.1" in p.stdout
+
+
+def test_empty_inputs_are_not_fatal(cpu_bin, tmp_path):
+    """No ESTs, and an EST record with an empty sequence (the reference segfaults on the latter): exit 0, empty outputs."""
+    U.unpack("test-mattia3", str(tmp_path))
+    for content in (b"", b">empty /gb=E1\n\n"):
+        open(tmp_path / "ests.txt", "wb").write(content)
+        U.run(cpu_bin, str(tmp_path), "--quiet")
+        assert all(os.path.getsize(tmp_path / f) == 0 for f in U.FILES)
 
 
 def test_missing_inputs_fail_loudly(cpu_bin, tmp_path):
