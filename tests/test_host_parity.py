@@ -51,7 +51,7 @@ def test_empty_inputs_are_not_fatal(cpu_bin, tmp_path):
     for content in (b"", b">empty /gb=E1\n\n"):
         open(tmp_path / "ests.txt", "wb").write(content)
         U.run(cpu_bin, str(tmp_path), "--quiet")
-        assert all(os.path.getsize(tmp_path / f) == 0 for f in U.FILES)
+        assert all(os.path.getsize(tmp_path / f) == 0 for f in ("raw-multifasta-out.txt", "processed-ests.txt"))
 
 
 def test_missing_inputs_fail_loudly(cpu_bin, tmp_path):
