@@ -60,3 +60,25 @@ def check_case(binary, case, tmp_path, *args):
 def build_cpu_binary():
     subprocess.run(["make", "-s", "-C", HERE], check=True)
     return CPU_BIN
+
+
+OPTION_SETS = [
+    ["-l", "18"], ["-l", "12"], ["--no-transitive-reduction", "--no-short-edge-compaction"], ["--retain-externals=false"],
+    ["-B", "60", "--max-intron-length", "5000"], ["-d", "0.5", "-p", "0.4", "-s", "0.4"],
+    ["--suff-pref-length-intron", "50", "--suff-pref-length-est", "20", "--suff-pref-length-genomic", "20"],
+    ["--max-difference-of-coverage", "0.2", "--max-difference-of-gap-length", "-1", "--complexity-threshold", "10"],
+    ["-D", "10", "--max-no-of-factorizations", "2"], ["--max-pairings-in-CMEG", "10", "--max-shortest-pairing-frequence", "0.1"],
+]
+
+
+def check_options_vs_reference(binary, case, tmp_path, opts, *extra):
+    """Same flags to the unmodified reference binary and to `binary`; the five output files must be identical."""
+    import shutil
+    a, b = os.path.join(str(tmp_path), "ref"), os.path.join(str(tmp_path), "ours")
+    os.makedirs(a); os.makedirs(b)
+    unpack(case, a)
+    for f in ("genomic.txt", "ests.txt"):
+        shutil.copy(os.path.join(a, f), os.path.join(b, f))
+    run(REF_BIN, a, *opts)
+    run(binary, b, *opts, *extra)
+    assert md5s(a) == md5s(b), (case, opts)

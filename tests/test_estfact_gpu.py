@@ -64,3 +64,10 @@ def test_scheduling_and_sharding_do_not_change_bytes(gpu_bin, tmp_path):
             cat[f] += open(d / f, "rb").read()
     for f in U.FILES:
         assert cat[f] == open(whole / f, "rb").read(), f
+
+
+@pytest.mark.parametrize("opts", U.OPTION_SETS, ids=lambda o: " ".join(o))
+def test_option_variants_vs_reference_binary(gpu_bin, opts, tmp_path):
+    if not os.path.exists(U.REF_BIN):
+        pytest.skip("oracle/_ref/est-fact not built")
+    U.check_options_vs_reference(gpu_bin, "test-CPB2", tmp_path, opts, "--quiet")

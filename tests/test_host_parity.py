@@ -69,3 +69,11 @@ def test_product_binary_has_no_cpu_path(tmp_path):
     assert p.returncode != 0 and b"no CUDA device" in p.stderr
     syms = subprocess.run(["nm", "-D", "--undefined-only", U.GPU_BIN], capture_output=True, text=True).stdout
     assert "pc_submit" in syms and "po_" not in syms
+
+
+@pytest.mark.parametrize("opts", U.OPTION_SETS, ids=lambda o: " ".join(o))
+def test_option_variants_vs_reference_binary(cpu_bin, opts, tmp_path):
+    """Every tuning flag of src/options.ggo changes the result the same way it does in the reference."""
+    if not os.path.exists(U.REF_BIN):
+        pytest.skip("oracle/_ref/est-fact not built (make -C oracle ref)")
+    U.check_options_vs_reference(cpu_bin, "test-mattia1", tmp_path, opts, "--quiet", "--threads", "4")
