@@ -80,7 +80,8 @@ struct pc_stream {
   void *slab = nullptr;
   unsigned long long *d_pool_need = nullptr, *h_pool_need = nullptr;   /* device counter + pinned mirror */
   int max_warps = 0;
-  std::vector<uint32_t> h_idx, h_lcs;
+  std::vector<uint32_t> h_idx, h_lcs, h_bins, h_all;
+  std::vector<uint16_t> h_key;
   std::vector<int32_t> h_status;
   Pending pend;
   bool timers = false;
@@ -229,11 +230,12 @@ static int gap_class(const pc_job &j) {
   return j.a_len <= 64 ? 0 : (j.a_len <= 128 ? 1 : 2);
 }
 
-static double job_cost(const pc_job &j) {
-  switch (j.op) {
-    case PC_OP_LCS: case PC_OP_SEED: return (double)j.a_len + j.b_len;
-    default: return ((double)j.a_len + 1) * ((double)j.b_len + 1);
-  }
+// log2-ish cost class of a job, integers only (this runs once per job per batch on the submitting thread)
+static inline int job_cost_class(const pc_job &j) {
+  unsigned long long c;
+  if (j.op == PC_OP_LCS || j.op == PC_OP_SEED) c = (unsigned long long)j.a_len + j.b_len + 1ull;
+  else c = ((unsigned long long)j.a_len + 1ull) * ((unsigned long long)j.b_len + 1ull) + 1ull;
+  return 63 - __builtin_clzll(c);
 }
 
 // Launch the kernels for the jobs whose indices are in `sel` (all of one batch already resident on device).
@@ -247,8 +249,10 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
   order.resize(sel.size());
   {
     const int NB = PC_OP_COUNT * 4 * 64;
-    std::vector<uint32_t> bins(NB + 1, 0);
-    std::vector<uint16_t> key(sel.size());
+    std::vector<uint32_t> &bins = st->h_bins;
+    bins.assign(NB + 1, 0);
+    std::vector<uint16_t> &key = st->h_key;
+    key.resize(sel.size());
     for (size_t q = 0; q < sel.size(); ++q) {
       const pc_job &j = h_jobs[sel[q]];
       if (j.op >= PC_OP_COUNT) return fail(PC_E_ARG, "%s", "pc_submit: unknown op");
@@ -257,10 +261,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
       if (j.op == PC_OP_GAP && cls < 3) {        // paired jobs run max(m) steps: order by m, finely
         const uint32_t m = j.b_len;
         lg = m < 512 ? (int)(m >> 4) : 32 + (int)std::min<uint32_t>(31, (m - 512) >> 7);
-      } else {
-        unsigned long long c = (unsigned long long)job_cost(j) + 1;
-        while (c >>= 1) ++lg;
-      }
+      } else lg = job_cost_class(j);
       key[q] = (uint16_t)((j.op * 4 + cls) * 64 + (63 - lg));
       ++bins[key[q] + 1];
     }
@@ -366,8 +367,8 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
   CU(cudaMemsetAsync((uint8_t *)st->arena.p + arena_bytes, 0, 16, st->s));
   CU(cudaMemcpyAsync(st->jobs.p, jobs, sizeof(pc_job) * (size_t)njobs, cudaMemcpyHostToDevice, st->s));
   PROF(2, tp);
-  std::vector<uint32_t> all((size_t)njobs);
-  for (int i = 0; i < njobs; ++i) all[i] = (uint32_t)i;
+  std::vector<uint32_t> &all = st->h_all;
+  if ((int)all.size() != njobs) { all.resize((size_t)njobs); for (int i = 0; i < njobs; ++i) all[i] = (uint32_t)i; }
   rc = launch_selected(st, jobs, all, (const uint8_t *)st->arena.p, (const pc_job *)st->jobs.p, (int32_t *)st->res.p,
                        (uint8_t *)st->var.p);
   if (rc) return rc;
@@ -390,8 +391,8 @@ extern "C" int pc_submit_device(pc_stream *st, const uint8_t *d_arena, size_t ar
   CU(cudaSetDevice(st->ctx->device));
   int rc = check_jobs(st, h_jobs, njobs, arena_bytes, var_out_bytes);
   if (rc) return rc;
-  std::vector<uint32_t> all((size_t)njobs);
-  for (int i = 0; i < njobs; ++i) all[i] = (uint32_t)i;
+  std::vector<uint32_t> &all = st->h_all;
+  if ((int)all.size() != njobs) { all.resize((size_t)njobs); for (int i = 0; i < njobs; ++i) all[i] = (uint32_t)i; }
   rc = launch_selected(st, h_jobs, all, d_arena, d_jobs, d_res, d_var_out);
   if (rc) return rc;
   Pending &P = st->pend;
