@@ -11,6 +11,7 @@ unsigned long long g_pc_launches = 0;
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const bool g_prof = getenv("PC_PROFILE") != nullptr;
 static double g_t[8];      /* check, reserve, h2d, sort, launch, d2h, sync (racy sums: diagnostics only) */
+static unsigned long long g_dev_grows, g_host_allocs, g_host_alloc_bytes; static double g_host_alloc_s;
 static double g_op_ms[PC_OP_COUNT]; static unsigned long long g_op_launches[PC_OP_COUNT], g_retry_rounds, g_retry_jobs, g_pool_grows;
 extern "C" void pc_debug_dump(void) {
   if (!g_prof) return;
@@ -19,6 +20,8 @@ extern "C" void pc_debug_dump(void) {
   fprintf(stderr, "[pc profile] device ms per op:");
   for (int i = 0; i < PC_OP_COUNT; ++i) if (g_op_launches[i]) fprintf(stderr, " %s %.1f (%llu launches)", nm[i], g_op_ms[i], g_op_launches[i]);
   fprintf(stderr, "\n[pc profile] pool retries: %llu rounds, %llu jobs, %llu pool growths\n", g_retry_rounds, g_retry_jobs, g_pool_grows);
+  fprintf(stderr, "[pc profile] device buffer growths (cudaMalloc during the run): %llu; pinned host allocations: %llu, %.1f MB, %.3f s\n",
+          g_dev_grows, g_host_allocs, g_host_alloc_bytes / 1048576.0, g_host_alloc_s);
 }
 struct ProfDump { ~ProfDump() { if (g_prof) fprintf(stderr, "[pc profile] check %.3f reserve %.3f h2d %.3f sort %.3f launch %.3f d2h %.3f sync %.3f s\n", g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5], g_t[6]); } } g_prof_dump;
 #define PROF(slot, t0) do { if (g_prof) { double t1_ = now_s(); g_t[slot] += t1_ - (t0); (t0) = t1_; } } while (0)
@@ -52,12 +55,29 @@ struct DevBuf {
     if (p && !in_slab) cudaFree(p);
     p = nullptr; in_slab = false;
     size_t want = std::max(bytes, cap * 2);
+    __atomic_fetch_add(&g_dev_grows, 1ull, __ATOMIC_RELAXED);
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) { cap = 0; return fail(PC_E_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
     cap = want;
     return 0;
   }
   void release() { if (p && !in_slab) cudaFree(p); p = nullptr; cap = 0; in_slab = false; }
+};
+
+// Pinned host staging that only grows (job order and LCS block prefix travel to the device from here: a pageable
+// source would make cudaMemcpyAsync wait for the stream).
+struct PinBuf {
+  uint32_t *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    size_t want = std::max<size_t>(std::max(n, cap * 2), 1u << 16);
+    if (cudaHostAlloc((void **)&p, want * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) { cap = 0; return fail(PC_E_NOMEM, "%s", "cudaHostAlloc failed"); }
+    cap = want;
+    return 0;
+  }
 };
 
 struct Pending {          // what pc_stream_sync needs to re-run jobs that ran out of pool
@@ -80,7 +100,8 @@ struct pc_stream {
   void *slab = nullptr;
   unsigned long long *d_pool_need = nullptr, *h_pool_need = nullptr;   /* device counter + pinned mirror */
   int max_warps = 0;
-  std::vector<uint32_t> h_idx, h_lcs, h_bins, h_all;
+  std::vector<uint32_t> h_bins;
+  PinBuf pin_idx, pin_lcs;
   std::vector<uint16_t> h_key;
   std::vector<int32_t> h_status;
   Pending pend;
@@ -158,6 +179,7 @@ extern "C" pc_stream *pc_stream_create(pc_ctx *c) {
   uint8_t *cur = (uint8_t *)st->slab;
   DevBuf *bufs[7] = {&st->pool, &st->arena, &st->var, &st->jobs, &st->res, &st->idx, &st->lcs_best};
   for (int i = 0; i < 7; ++i) bufs[i]->carve(cur, sizes[i]);
+  if (st->pin_idx.reserve(1u << 16) || st->pin_lcs.reserve(1u << 14)) { delete st; return nullptr; }
   return st;
 }
 
@@ -168,6 +190,8 @@ extern "C" void pc_stream_destroy(pc_stream *st) {
   for (DevBuf *b : {&st->arena, &st->jobs, &st->idx, &st->res, &st->var, &st->pool, &st->lcs_best}) b->release();
   cudaFree(st->slab);
   cudaFree(st->d_pool_need); cudaFreeHost(st->h_pool_need);
+  if (st->pin_idx.p) cudaFreeHost(st->pin_idx.p);
+  if (st->pin_lcs.p) cudaFreeHost(st->pin_lcs.p);
   for (auto &e : st->ev_pending) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
   for (auto e : st->ev_free) cudaEventDestroy(e);
   cudaStreamDestroy(st->s);
@@ -176,7 +200,9 @@ extern "C" void pc_stream_destroy(pc_stream *st) {
 
 extern "C" void *pc_host_alloc(size_t bytes) {
   void *p = nullptr;
+  const double t0 = g_prof ? now_s() : 0;
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { fail(PC_E_NOMEM, "%s", "cudaHostAlloc failed"); return nullptr; }
+  if (g_prof) { __atomic_fetch_add(&g_host_allocs, 1ull, __ATOMIC_RELAXED); __atomic_fetch_add(&g_host_alloc_bytes, (unsigned long long)bytes, __ATOMIC_RELAXED); g_host_alloc_s += now_s() - t0; }
   return p;
 }
 double pc_int_peak_run(cudaStream_t s, int sm_count, float *ms_out);
@@ -238,39 +264,47 @@ static inline int job_cost_class(const pc_job &j) {
   return 63 - __builtin_clzll(c);
 }
 
-// Launch the kernels for the jobs whose indices are in `sel` (all of one batch already resident on device).
-static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vector<uint32_t> &sel, const uint8_t *d_arena,
+// Launch the kernels for the jobs whose indices are in `sel` (nullptr = all njobs of the batch, which is already
+// resident on the device).  One sequential pass over the host copy of the jobs gives every job its (op, class, cost)
+// key and every (op, class) segment its size and longest strings; a counting sort then lays the job indices out
+// segment by segment, heaviest first, for the persistent kernels.
+static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *sel, size_t nsel, const uint8_t *d_arena,
                            const pc_job *d_jobs, int32_t *d_res, uint8_t *d_var) {
   pc_ctx *c = st->ctx;
   double tp = g_prof ? now_s() : 0;
-  // partition by op, heaviest first inside each op
-  // counting sort on (op, log2 cost class descending): O(n), good enough for load balance
-  std::vector<uint32_t> &order = st->h_idx;
-  order.resize(sel.size());
+  constexpr int NSEG = PC_OP_COUNT * 4, NB = NSEG * 64;
+  struct Seg { uint32_t n, max_a, max_b; } seg[NSEG];
+  memset(seg, 0, sizeof seg);
+  PinBuf &order = st->pin_idx;
+  if (order.reserve(nsel + 1)) return PC_E_NOMEM;
   {
-    const int NB = PC_OP_COUNT * 4 * 64;
     std::vector<uint32_t> &bins = st->h_bins;
     bins.assign(NB + 1, 0);
     std::vector<uint16_t> &key = st->h_key;
-    key.resize(sel.size());
-    for (size_t q = 0; q < sel.size(); ++q) {
-      const pc_job &j = h_jobs[sel[q]];
+    key.resize(nsel);
+    for (size_t q = 0; q < nsel; ++q) {
+      const pc_job &j = h_jobs[sel ? sel[q] : q];
       if (j.op >= PC_OP_COUNT) return fail(PC_E_ARG, "%s", "pc_submit: unknown op");
       const int cls = gap_class(j);
-      int lg = 0;
+      int lg;
       if (j.op == PC_OP_GAP && cls < 3) {        // paired jobs run max(m) steps: order by m, finely
         const uint32_t m = j.b_len;
         lg = m < 512 ? (int)(m >> 4) : 32 + (int)std::min<uint32_t>(31, (m - 512) >> 7);
       } else lg = job_cost_class(j);
-      key[q] = (uint16_t)((j.op * 4 + cls) * 64 + (63 - lg));
+      const int sg = (int)j.op * 4 + cls;
+      Seg &S = seg[sg];
+      ++S.n; S.max_a = std::max(S.max_a, j.a_len); S.max_b = std::max(S.max_b, j.b_len);
+      key[q] = (uint16_t)(sg * 64 + (63 - lg));
       ++bins[key[q] + 1];
     }
     for (int b = 0; b < NB; ++b) bins[b + 1] += bins[b];
-    for (size_t q = 0; q < sel.size(); ++q) order[bins[key[q]]++] = sel[q];
+    uint32_t *out = order.p;
+    if (sel) for (size_t q = 0; q < nsel; ++q) out[bins[key[q]]++] = sel[q];
+    else for (size_t q = 0; q < nsel; ++q) out[bins[key[q]]++] = (uint32_t)q;
   }
   PROF(3, tp);
-  if (st->idx.reserve(order.size() * 4 + 4)) return PC_E_NOMEM;
-  CU(cudaMemcpyAsync(st->idx.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, st->s));
+  if (st->idx.reserve(nsel * 4 + 4)) return PC_E_NOMEM;
+  CU(cudaMemcpyAsync(st->idx.p, order.p, nsel * 4, cudaMemcpyHostToDevice, st->s));
   CU(cudaMemsetAsync(st->d_pool_need, 0, 8, st->s));
   PcDevBatch B;
   B.arena = d_arena; B.genome = c->d_genome; B.genome_len = c->genome_len;
@@ -279,17 +313,13 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
   B.slots = 1; B.max_warps = st->max_warps;
   B.ix_keys = c->ix_keys; B.ix_pos = c->ix_pos; B.ix_bstart = c->ix_bstart; B.ix_shift = c->ix_shift; B.ix_n = c->ix_n; B.ix_word = c->ix_word; B.depth_rate = c->depth_rate;
   size_t i = 0;
-  while (i < order.size()) {
-    const uint32_t op = h_jobs[order[i]].op;
-    const int cls = gap_class(h_jobs[order[i]]);
-    size_t j = i;
-    long long max_l1 = 0; int max_l2 = 0;
-    while (j < order.size() && h_jobs[order[j]].op == op && gap_class(h_jobs[order[j]]) == cls) {
-      max_l1 = std::max<long long>(max_l1, h_jobs[order[j]].b_len);
-      max_l2 = std::max<int>(max_l2, (int)h_jobs[order[j]].a_len);
-      ++j;
-    }
-    if (op >= PC_OP_COUNT) return fail(PC_E_ARG, "%s", "pc_submit: unknown op");
+  for (int sg = 0; sg < NSEG; ++sg) {
+    if (!seg[sg].n) continue;
+    const uint32_t op = (uint32_t)(sg / 4);
+    const int cls = sg & 3;
+    const size_t j = i + seg[sg].n;
+    const long long max_l1 = seg[sg].max_b;
+    const int max_l2 = (int)seg[sg].max_a;
     B.idx = (const uint32_t *)st->idx.p + i;
     B.n = (int)(j - i);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -302,16 +332,18 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const std::vecto
       // [best slots | block prefix] in one device buffer; the prefix comes from the host copy of the jobs
       const size_t best_b = (8ull * B.n + 255u) & ~(size_t)255u;
       if (st->lcs_best.reserve(best_b + 4ull * (B.n + 1))) return PC_E_NOMEM;
-      st->h_lcs.resize((size_t)B.n + 1);
+      PinBuf &pl = st->pin_lcs;
+      if (pl.reserve((size_t)B.n + 1)) return PC_E_NOMEM;
       uint64_t tot = 0;
       for (size_t q = i; q < j; ++q) {
-        st->h_lcs[q - i] = (uint32_t)tot;
-        tot += (uint64_t)pc_lcs_blocks(h_jobs[order[q]].b_len, (int)h_jobs[order[q]].a_len);
+        pl.p[q - i] = (uint32_t)tot;
+        const pc_job &jb = h_jobs[order.p[q]];
+        tot += (uint64_t)pc_lcs_blocks(jb.b_len, (int)jb.a_len);
       }
-      st->h_lcs[B.n] = (uint32_t)tot;
+      pl.p[B.n] = (uint32_t)tot;
       if (tot >= 0x7fffffffull) return fail(PC_E_RANGE, "%s", "LCS batch too large for one launch");
       uint32_t *d_prefix = (uint32_t *)((uint8_t *)st->lcs_best.p + best_b);
-      CU(cudaMemcpyAsync(d_prefix, st->h_lcs.data(), 4ull * (B.n + 1), cudaMemcpyHostToDevice, st->s));
+      CU(cudaMemcpyAsync(d_prefix, pl.p, 4ull * (B.n + 1), cudaMemcpyHostToDevice, st->s));
       pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, d_prefix, (uint32_t)tot, max_l2, st->s);
     } else if (op == PC_OP_GAP && cls < 3) {
       pc_launch_gap_pairs(cls, B, (int)max_l1, st->s, c->sm_count);
@@ -367,9 +399,7 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
   CU(cudaMemsetAsync((uint8_t *)st->arena.p + arena_bytes, 0, 16, st->s));
   CU(cudaMemcpyAsync(st->jobs.p, jobs, sizeof(pc_job) * (size_t)njobs, cudaMemcpyHostToDevice, st->s));
   PROF(2, tp);
-  std::vector<uint32_t> &all = st->h_all;
-  if ((int)all.size() != njobs) { all.resize((size_t)njobs); for (int i = 0; i < njobs; ++i) all[i] = (uint32_t)i; }
-  rc = launch_selected(st, jobs, all, (const uint8_t *)st->arena.p, (const pc_job *)st->jobs.p, (int32_t *)st->res.p,
+  rc = launch_selected(st, jobs, nullptr, (size_t)njobs, (const uint8_t *)st->arena.p, (const pc_job *)st->jobs.p, (int32_t *)st->res.p,
                        (uint8_t *)st->var.p);
   if (rc) return rc;
   Pending &P = st->pend;
@@ -391,9 +421,7 @@ extern "C" int pc_submit_device(pc_stream *st, const uint8_t *d_arena, size_t ar
   CU(cudaSetDevice(st->ctx->device));
   int rc = check_jobs(st, h_jobs, njobs, arena_bytes, var_out_bytes);
   if (rc) return rc;
-  std::vector<uint32_t> &all = st->h_all;
-  if ((int)all.size() != njobs) { all.resize((size_t)njobs); for (int i = 0; i < njobs; ++i) all[i] = (uint32_t)i; }
-  rc = launch_selected(st, h_jobs, all, d_arena, d_jobs, d_res, d_var_out);
+  rc = launch_selected(st, h_jobs, nullptr, (size_t)njobs, d_arena, d_jobs, d_res, d_var_out);
   if (rc) return rc;
   Pending &P = st->pend;
   P.active = true; P.device_mode = true; P.jobs = h_jobs; P.njobs = njobs; P.res = nullptr; P.var_out = nullptr;
@@ -437,7 +465,7 @@ extern "C" int pc_stream_sync(pc_stream *st) {
       if (rc) { P.active = false; st->max_warps = 0; return rc; }
     }
     st->max_warps = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(st->pool.cap / need, 1u << 20));
-    int rc = launch_selected(st, P.jobs, redo, P.d_arena, P.d_jobs, P.d_res, P.d_var);
+    int rc = launch_selected(st, P.jobs, redo.data(), redo.size(), P.d_arena, P.d_jobs, P.d_res, P.d_var);
     st->max_warps = 0;
     if (rc) { P.active = false; return rc; }
     if (!P.device_mode) {

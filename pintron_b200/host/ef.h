@@ -157,7 +157,9 @@ void refine_factorizations(ef_task *T, const ef_seq *est, ef_fzlist *L);        
 bool refine_intron(ef_task *T, const ef_seq *est, ef_factor *donor, ef_factor *acceptor, bool first_intron);
 int burset_freq(const char *donor, const char *acceptor);           /* getBursetFrequency */
 int burset_adaptor(const char *t, size_t cut1, size_t cut2);        /* getBursetFrequency_adaptor */
-char classify_intron(const char *gen, int glen, int start, int end);   /* 0 = U12, 1 = U2, 2 = not determined */
+char classify_intron(const char *gen, int glen, int start, int end);
+void ef_small_exon_scan(const char *g, int glen_all, const char *e, size_t estart, size_t elen, size_t allgstart, size_t allglen,
+                        size_t f1slen, size_t f2plen, size_t MINI, size_t out[7]);      /* refine_fact.c */   /* 0 = U12, 1 = U2, 2 = not determined */
 double dust_score(const char *s, int len);
 
 /* shared by est_factorizations and refine_factorizations */

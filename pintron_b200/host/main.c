@@ -248,5 +248,8 @@ int main(int argc, char **argv) {
             t_alg > 0 ? (double)nest / t_alg : 0.0);
   pc_debug_dump();
   fflush(NULL);
+#ifdef EF_GPROF
+  exit(0);         /* profiling build: let gmon.out be written */
+#endif
   _exit(0);        /* every output file is closed; skip the CUDA runtime's exit-time tear-down */
 }

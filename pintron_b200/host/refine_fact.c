@@ -1,3 +1,4 @@
+#define _GNU_SOURCE
 /* refine_fact.c — the post-factorization refinement of one EST (reference src/factorization-refinement.c).
  *
  * refine_EST_factorizations :1269-1305 = remove_invalid_factorizations :120, remove_duplicated_factorizations :174,
@@ -183,6 +184,60 @@ static void small_exon_at_prefix(ef_task *T, const ef_seq *est, ef_fz *z) {
 
 static size_t min3z(size_t a, size_t b, size_t c) { size_t t = a; if (t > b) t = b; if (t > c) t = c; return t; }
 
+/* The scan of search_small_exon (factorization-refinement.c:770-834): the longest trim (offstart, offend) of the EST
+ * middle e[estart, estart+elen) that occurs inside g[allgstart, allgstart+allglen) leaving two introns that both
+ * classify.  out = {max_sexon, ecut1, ecut2, gcut1_1, gcut1_2, gcut2_1, gcut2_2}.
+ * The reference runs strstr for every (offstart, offend) and keeps the first strictly longer hit.  Same result, fewer
+ * scans: an occurrence at q of the trim (offstart, offend), length sl = elen - offstart - offend, must satisfy
+ * offstart + MINI <= q <= allglen - MINI - elen + offstart (offend cancels out of the right limit), so for one
+ * offstart every longer trim occurs where the shortest one does: one memmem pass per offstart finds all of them,
+ * and trims that cannot beat the current best are skipped (classify_intron is pure). */
+void ef_small_exon_scan(const char *g, int glen_all, const char *e, size_t estart, size_t elen, size_t allgstart, size_t allglen,
+                        size_t f1slen, size_t f2plen, size_t MINI, size_t out[7]) {
+  const char *efact = e + estart, *allgfact = g + allgstart;
+  size_t max_sexon = 0, ecut1 = 0, ecut2 = 0, gcut1_1 = 0, gcut1_2 = 0, gcut2_1 = 0, gcut2_2 = 0;
+  const size_t max_offstart = min3z(f1slen + 1 - MIN_PERFECT_BORDER, elen + 1 - LB_SMALL_EXON, allglen + 1 - (2 * MINI) - LB_SMALL_EXON);
+  for (size_t offstart = 0; offstart < max_offstart; ++offstart) {
+    const size_t max_offend = min3z(f2plen + 1 - MIN_PERFECT_BORDER, elen + 1 - offstart - LB_SMALL_EXON,
+                                    allglen + 1 - (2 * MINI) - LB_SMALL_EXON - offstart);
+    const size_t sl_max = elen - offstart, sl_min = elen - offstart - (max_offend - 1);
+    if (sl_max <= max_sexon) continue;
+    if (allglen + offstart < MINI + elen) continue;                 /* no room for any occurrence */
+    const size_t qmin = offstart + MINI, qmax = allglen - MINI - elen + offstart;
+    if (qmax < qmin) continue;
+    const char *pat = efact + offstart;
+    /* occurrences of the shortest trim, ascending, with the length the full trim keeps matching there */
+    size_t best_here = 0;                                             /* the longest sl accepted for this offstart */
+    size_t b_q = 0, b_offend = 0;
+    const char *scan = allgfact + qmin, *scan_end = allgfact + qmax + sl_min;      /* last window ends here */
+    while (scan + sl_min <= scan_end) {
+      const char *occ = memmem(scan, (size_t)(scan_end - scan), pat, sl_min);
+      if (!occ) break;
+      const size_t q = (size_t)(occ - allgfact);
+      size_t ext = sl_min;
+      while (ext < sl_max && pat[ext] == allgfact[q + ext]) ++ext;
+      /* trims that occur at q: sl_min <= sl <= ext, longest (= smallest offend) first; only sl > best so far matter:
+       * for equal sl an earlier q wins, and earlier offstarts already hold max_sexon */
+      const size_t floor_sl = MAX2(max_sexon, best_here);
+      for (size_t sl = ext; sl >= sl_min && sl > floor_sl; --sl) {
+        const size_t offend = elen - offstart - sl;
+        const size_t i1start = allgstart + offstart, i1end = allgstart + q - 1;
+        const size_t i2start = i1end + 1 + sl, i2end = allgstart + allglen - offend - 1;
+        const char t1 = classify_intron(g, glen_all, (int)i1start, (int)i1end), t2 = classify_intron(g, glen_all, (int)i2start, (int)i2end);
+        if (t1 != 2 && t2 != 2) { best_here = sl; b_q = q; b_offend = offend; break; }
+      }
+      scan = occ + 1;
+    }
+    if (best_here > max_sexon) {
+      const size_t sl = best_here, i1start = allgstart + offstart, i1end = allgstart + b_q - 1;
+      const size_t i2start = i1end + 1 + sl, i2end = allgstart + allglen - b_offend - 1;
+      max_sexon = sl; ecut1 = estart + offstart; ecut2 = estart + offstart + sl;
+      gcut1_1 = i1start; gcut1_2 = i1end + 1; gcut2_1 = i2start; gcut2_2 = i2end + 1;
+    }
+  }
+  out[0] = max_sexon; out[1] = ecut1; out[2] = ecut2; out[3] = gcut1_1; out[4] = gcut1_2; out[5] = gcut2_1; out[6] = gcut2_2;
+}
+
 /* search_small_exon between exons i and i+1 of z; returns true when a new exon was inserted at i+1 */
 static bool small_exon_between(ef_task *T, const ef_seq *est, ef_fz *z, int i) {
   const ef_config *c = T->cfg;
@@ -226,37 +281,9 @@ static bool small_exon_between(ef_task *T, const ef_seq *est, ef_fz *z, int i) {
   const size_t allglen = g2pstart + g2pocc + f2plen - MIN_PERFECT_BORDER - allgstart;
   const size_t MINI = (size_t)MAX2(4, c->min_intron_length);
   if (f1slen < MIN_PERFECT_BORDER || f2plen < MIN_PERFECT_BORDER || allglen < 2 * MINI + LB_SMALL_EXON || elen < LB_SMALL_EXON) return false;
-  char *efact = ar_alloc(&T->ar, elen + 1), *allgfact = ar_alloc(&T->ar, allglen + 1);
-  memcpy(efact, e + estart, elen);
-  memcpy(allgfact, g + allgstart, allglen);
-  size_t max_sexon = 0, ecut1 = 0, ecut2 = 0, gcut1_1 = 0, gcut1_2 = 0, gcut2_1 = 0, gcut2_2 = 0;
-  const size_t max_offstart = min3z(f1slen + 1 - MIN_PERFECT_BORDER, elen + 1 - LB_SMALL_EXON, allglen + 1 - (2 * MINI) - LB_SMALL_EXON);
-  for (size_t offstart = 0; offstart < max_offstart; ++offstart) {
-    const size_t max_offend = min3z(f2plen + 1 - MIN_PERFECT_BORDER, elen + 1 - offstart - LB_SMALL_EXON,
-                                    allglen + 1 - (2 * MINI) - LB_SMALL_EXON - offstart);
-    for (size_t offend = 0; offend < max_offend; ++offend) {
-      const char endechar = efact[elen - offend];
-      efact[elen - offend] = 0;
-      const char endgchar = allgfact[allglen - offend - MINI];
-      allgfact[allglen - offend - MINI] = 0;
-      char *occ = allgfact + offstart + MINI;
-      while ((occ = strstr(occ, efact + offstart))) {
-        const size_t i1start = allgstart + offstart, i1end = allgstart + (size_t)(occ - allgfact) - 1;
-        const size_t i2start = i1end + 1 + elen - offstart - offend, i2end = allgstart + allglen - offend - 1;
-        const char t1 = classify_intron(g, glen_all, (int)i1start, (int)i1end), t2 = classify_intron(g, glen_all, (int)i2start, (int)i2end);
-        if (t1 != 2 && t2 != 2) {
-          const size_t sl = elen - offstart - offend;
-          if (sl > max_sexon) {
-            max_sexon = sl; ecut1 = estart + offstart; ecut2 = estart + offstart + sl;
-            gcut1_1 = i1start; gcut1_2 = i1end + 1; gcut2_1 = i2start; gcut2_2 = i2end + 1;
-          }
-        }
-        ++occ;
-      }
-      efact[elen - offend] = endechar;
-      allgfact[allglen - offend - MINI] = endgchar;
-    }
-  }
+  size_t cut[7];
+  ef_small_exon_scan(g, glen_all, e, estart, elen, allgstart, allglen, f1slen, f2plen, MINI, cut);
+  const size_t max_sexon = cut[0], ecut1 = cut[1], ecut2 = cut[2], gcut1_1 = cut[3], gcut1_2 = cut[4], gcut2_1 = cut[5], gcut2_2 = cut[6];
   if (max_sexon < LB_SMALL_EXON) return false;
   ef_factor nw = {(int)ecut1, (int)ecut2 - 1, (int)gcut1_2, (int)gcut2_1 - 1};
   p2->es = (int)ecut2; p2->gs = (int)gcut2_2;

@@ -154,6 +154,7 @@ typedef struct fiber {
   int base;                 /* index of this fiber's first job in the group's batch */
   int phase;
   bool has_results;
+  bool submitted;           /* its requests are part of the batch in flight (false: deferred to the next one) */
   struct group *grp;
 } fiber;
 
@@ -168,6 +169,7 @@ typedef struct group {
   int32_t *res; size_t res_cap;
   uint8_t *var; size_t var_cap, var_len;
   struct worker *w;
+  uint64_t deferred, grows;   /* fibers put off to a later batch; staging re-allocations */
   uint8_t *slab, *slab_end;   /* the initial pinned slab the four buffers above were carved from */
 } group;
 
@@ -191,7 +193,7 @@ static size_t g_n_items;
 static const uint32_t *g_order;       /* dispatch order (length-sorted windows), NULL = input order */
 static __thread fiber *tl_fiber;
 static __thread worker *tl_worker;
-static uint64_t g_batches, g_jobs, g_h2d, g_d2h;
+static uint64_t g_batches, g_jobs, g_h2d, g_d2h, g_deferred, g_grows;
 static double g_gpu_wait, g_t_fibers, g_t_gather, g_t_submit, g_t_init, g_t_fini;
 static pthread_mutex_t g_stat_mu = PTHREAD_MUTEX_INITIALIZER;
 
@@ -352,6 +354,25 @@ static void gather(group *g) {
   for (int k = 0; k < g->nfibers; ++k) {
     fiber *f = &g->fibers[k];
     if (f->state != F_WAITING) continue;
+    /* Back-pressure instead of growth: the pinned staging (and its device mirror) keeps the size it was given at
+     * start-up; a fiber whose requests do not fit any more waits for the next batch.  Re-pinning memory or cudaMalloc
+     * in the middle of a run stalls every thread of the process, which is what long mRNAs used to trigger all the
+     * time.  Only a single fiber that is larger than an EMPTY batch makes the buffers grow. */
+    {
+      size_t need_a = 0, need_v = 0;
+      for (int i = 0; i < f->nreq; ++i) {
+        const ef_req *r = &f->reqs[i];
+        need_a += (size_t)r->a.len + (size_t)(r->b.in_genome ? 0 : r->b.len) + 8;
+        if (r->op == PC_OP_ALIGN || r->op == PC_OP_GAP) need_v += (size_t)r->a.len + (size_t)r->b.len;
+        else if (r->op == PC_OP_SEED) need_v += 12u * (size_t)r->out_cap + 4;
+      }
+      if (g->njobs > 0 && (g->arena_len + need_a > g->arena_cap || g->var_len + need_v > g->var_cap || (size_t)g->njobs + (size_t)f->nreq > (size_t)g->jobs_cap)) {
+        f->submitted = false;
+        ++g->deferred;
+        continue;
+      }
+    }
+    f->submitted = true;
     f->base = g->njobs;
     for (int i = 0; i < f->nreq; ++i) {
       const ef_req *r = &f->reqs[i];
@@ -360,11 +381,13 @@ static void gather(group *g) {
         size_t nc = MAX2(g->arena_cap * 2, g->arena_len + need + (1u << 20));
         g->arena = pinned_grow(g->arena, g->arena_len, nc);
         g->arena_cap = nc;
+        ++g->grows;
       }
       if (g->njobs == g->jobs_cap) {
         int nc = g->jobs_cap ? g->jobs_cap * 2 : 4096;
         g->jobs = pinned_grow(g->jobs, sizeof(pc_job) * (size_t)g->njobs, sizeof(pc_job) * (size_t)nc);
         g->jobs_cap = nc;
+        ++g->grows;
       }
       pc_job *j = &g->jobs[g->njobs++];
       memset(j, 0, sizeof *j);
@@ -397,6 +420,7 @@ static void gather(group *g) {
     size_t nc = MAX2(g->res_cap * 2, (size_t)g->njobs * PC_RES_INTS + 4096);
     pinned_release(g->res);
     g->res = pc_host_alloc(nc * sizeof(int32_t));
+    ++g->grows;
     if (!g->res) die_pc("pc_host_alloc");
     g->res_cap = nc;
   }
@@ -404,6 +428,7 @@ static void gather(group *g) {
     size_t nc = MAX2(g->var_cap * 2, g->var_len + (1u << 20));
     pinned_release(g->var);
     g->var = pc_host_alloc(nc);
+    ++g->grows;
     if (!g->var) die_pc("pc_host_alloc");
     g->var_cap = nc;
   }
@@ -421,7 +446,7 @@ static bool run_group(worker *w, group *g) {
     w->gpu_wait += ef_now() - t0;
     g->pending = false;
     for (int k = 0; k < g->nfibers; ++k)
-      if (g->fibers[k].state == F_WAITING) { g->fibers[k].state = F_RUNNABLE; g->fibers[k].has_results = true; }
+      if (g->fibers[k].state == F_WAITING && g->fibers[k].submitted) { g->fibers[k].state = F_RUNNABLE; g->fibers[k].has_results = true; }
   }
   bool any = false;
   const double tf0 = ef_now();
@@ -496,6 +521,7 @@ static void *worker_main(void *arg) {
    * each call synchronising the device) only delays the threads that are still working. */
   pthread_mutex_lock(&g_stat_mu);
   g_batches += w->batches; g_jobs += w->jobs; g_gpu_wait += w->gpu_wait; g_h2d += w->h2d; g_d2h += w->d2h;
+  g_deferred += w->g[0].deferred + w->g[1].deferred; g_grows += w->g[0].grows + w->g[1].grows;
   g_t_fibers += w->t_fibers; g_t_gather += w->t_gather; g_t_submit += w->t_submit;
   g_t_init += tw1 - tw0; g_t_fini += ef_now() - tw2;
   for (int i = 0; i < EF_PH_COUNT; ++i) g_phase_s[i] += tl_phase_s[i];
@@ -575,7 +601,7 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
   if ((size_t)per_group * 2 * (size_t)nthreads > n_items) per_group = (int)(n_items / (2 * (size_t)nthreads)) + 1;
   atomic_store(&g_next_item, 0);
   g_n_items = n_items;
-  g_batches = g_jobs = g_h2d = g_d2h = 0; g_gpu_wait = 0; g_t_fibers = g_t_gather = g_t_submit = g_t_init = g_t_fini = 0;
+  g_batches = g_jobs = g_h2d = g_d2h = g_deferred = g_grows = 0; g_gpu_wait = 0; g_t_fibers = g_t_gather = g_t_submit = g_t_init = g_t_fini = 0;
   const double ts1 = ef_now();
   worker *ws = calloc((size_t)nthreads, sizeof(worker));
   for (int i = 0; i < nthreads; ++i) {
@@ -594,7 +620,9 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
   (void)ctxs;      /* contexts are left to process exit, see worker_main */
   if (!cfg->quiet)
     fprintf(stderr, "* INFO  scheduler: %d thread(s) x 2 x %d fibers on %d GPU(s); context + genome index %.3f s (%.3f s of it still to wait for), workers %.3f s "
-            "(stream set-up %.3f s, tear-down %.3f s per thread on average), context tear-down %.3f s\n",
-            nthreads, per_group, nuse, g_prep.secs, ts1 - ts0, ts2 - ts1, g_t_init / nthreads, g_t_fini / nthreads, ef_now() - ts2);
+            "(stream set-up %.3f s, tear-down %.3f s per thread on average), context tear-down %.3f s; "
+            "%llu fiber deferrals, %llu staging re-allocations\n",
+            nthreads, per_group, nuse, g_prep.secs, ts1 - ts0, ts2 - ts1, g_t_init / nthreads, g_t_fini / nthreads, ef_now() - ts2,
+            (unsigned long long)g_deferred, (unsigned long long)g_grows);
   return 0;
 }

@@ -77,3 +77,13 @@ def test_option_variants_vs_reference_binary(cpu_bin, opts, tmp_path):
     if not os.path.exists(U.REF_BIN):
         pytest.skip("oracle/_ref/est-fact not built (make -C oracle ref)")
     U.check_options_vs_reference(cpu_bin, "test-mattia1", tmp_path, opts, "--quiet", "--threads", "4")
+
+
+def test_small_exon_scan_matches_the_reference_loops(cpu_bin):
+    """search_small_exon's (offstart, offend) x strstr scan (factorization-refinement.c:770-834) is restructured in
+    refine_fact.c (one memmem pass per offstart, pruned trims); fuzz it against the literal loops."""
+    exe = os.path.join(os.path.dirname(cpu_bin), "small_exon_fuzz")
+    p = subprocess.run([exe, "6000"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.startswith("ok 6000 hits "), p.stdout
+    assert int(p.stdout.split()[-1]) > 100

@@ -22,6 +22,6 @@ for cfg in "$@"; do
   echo "== $W $READS reads: $cfg"
   s=$(date +%s.%N)
   /root/repo/pintron_b200/bin/est-fact $cfg 2> err.log
-  echo "rc=$? wall $(echo "$(date +%s.%N) - $s" | bc)"
+  e=$(date +%s.%N); echo "rc=$? wall $(python -c "print(round($e - $s, 3))") s"
   grep -E "Timer (Algorithm|Total)|device batches|thread-seconds|scheduler|by phase|pc profile|pc op" err.log
 done
