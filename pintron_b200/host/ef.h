@@ -48,6 +48,8 @@ int ef_config_parse(ef_config *c, int argc, char **argv);   /* also writes ./con
 typedef struct ef_chunk { struct ef_chunk *next; size_t cap, used; } ef_chunk;
 typedef struct ef_arena { ef_chunk *head, *cur; } ef_arena;
 void *ar_alloc(ef_arena *a, size_t bytes);         /* zeroed, 16-aligned */
+void *ar_alloc_raw(ef_arena *a, size_t bytes);     /* the same, not zeroed */
+void ar_undo(ef_arena *a, void *p);                /* rewind to p when it is in the current chunk (p = latest allocation) */
 void ar_reset(ef_arena *a);                        /* keeps the first chunk */
 void ar_free_all(ef_arena *a);
 
@@ -158,6 +160,7 @@ bool refine_intron(ef_task *T, const ef_seq *est, ef_factor *donor, ef_factor *a
 int burset_freq(const char *donor, const char *acceptor);           /* getBursetFrequency */
 int burset_adaptor(const char *t, size_t cut1, size_t cut2);        /* getBursetFrequency_adaptor */
 char classify_intron(const char *gen, int glen, int start, int end);
+void ef_small_exon_index_build(const char *g, size_t len);          /* 6-mer positions of the genome, once per run */
 void ef_small_exon_scan(const char *g, int glen_all, const char *e, size_t estart, size_t elen, size_t allgstart, size_t allglen,
                         size_t f1slen, size_t f2plen, size_t MINI, size_t out[7]);      /* refine_fact.c */   /* 0 = U12, 1 = U2, 2 = not determined */
 double dust_score(const char *s, int len);

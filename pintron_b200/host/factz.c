@@ -59,70 +59,62 @@ bool ef_timeout_expired(ef_task *T) {
 
 /* ---- embeddings ------------------------------------------------------------------------------------------------ */
 typedef struct ptl { int p, t, l; } ptl;
-/* An embedding is an immutable singly-linked list of pairings, leftmost first.  Putting a node in front of an embedding
- * rewrites only its first element, so the new embedding shares everything from the third element on with the old one:
- * O(1) per link instead of a copy, and two embeddings that reach the same list node are identical from there on
- * (maximality() stops at that point). */
-typedef struct enode { ptl v; const struct enode *next; } enode;
-typedef struct emb { const enode *head; int n; } emb;
+typedef struct emb { ptl *v; int n; } emb;                  /* v[0] is the head (leftmost pairing) */
 typedef struct emblist { emb **v; int n, cap; } emblist;
 
 static void el_push(ef_task *T, emblist *L, emb *e) {
   if (L->n == L->cap) {
     int nc = L->cap ? L->cap * 2 : 4;
-    emb **nv = ar_alloc(&T->ar, sizeof(emb *) * (size_t)nc);
+    emb **nv = ar_alloc_raw(&T->ar, sizeof(emb *) * (size_t)nc);
     if (L->n) memcpy(nv, L->v, sizeof(emb *) * (size_t)L->n);
     L->v = nv; L->cap = nc;
   }
   L->v[L->n++] = e;
 }
 
-static emb *emb_single(ef_task *T, ptl head) {
-  struct { emb e; enode a; } *m = ar_alloc(&T->ar, sizeof *m);
-  m->a.v = head; m->a.next = NULL;
-  m->e.head = &m->a; m->e.n = 1;
-  return &m->e;
-}
-
-/* [first, second, tail->head->next ...]: `second` replaces the old head of `tail` */
-static emb *emb_link(ef_task *T, const emb *tail, ptl first, ptl second) {
-  struct { emb e; enode a, b; } *m = ar_alloc(&T->ar, sizeof *m);
-  m->b.v = second; m->b.next = tail->head->next;
-  m->a.v = first; m->a.next = &m->b;
-  m->e.head = &m->a; m->e.n = tail->n + 1;
-  return &m->e;
+/* one allocation per embedding: header and pairings side by side (not zeroed: every field is written here) */
+static emb *emb_prepend(ef_task *T, const emb *tail, ptl head) {
+  const int n = (tail ? tail->n : 0) + 1;
+  emb *e = ar_alloc_raw(&T->ar, sizeof *e + sizeof(ptl) * (size_t)n);
+  e->n = n;
+  e->v = (ptl *)(e + 1);
+  e->v[0] = head;
+  if (tail) memcpy(e->v + 1, tail->v, sizeof(ptl) * (size_t)tail->n);
+  return e;
 }
 
 static bool covers(const ptl *in, const ptl *out) {   /* `in` lies inside `out` on P and on T */
   return !(in->p < out->p || in->p + in->l > out->p + out->l || in->t < out->t || in->t + in->l > out->t + out->l);
 }
 
-/* every one of the first m elements of `in` lies inside its counterpart of `out` */
-static bool covers_all(const enode *in, const enode *out, int m) {
-  for (int i = 0; i < m; ++i, in = in->next, out = out->next) {
-    if (in == out) return true;            /* shared tail: identical from here on */
-    if (!covers(&in->v, &out->v)) return false;
-  }
+/* Every one of the first m elements of `in` lies inside its counterpart of `out` (maximality_relation's loops,
+ * est-factorizations.c:1362).  A conjunction, so the order of evaluation is free: embeddings that leave the same node
+ * mostly share their first elements and part company further down, so after the two leading elements the scan runs
+ * from the far end backwards. */
+static bool covers_all(const ptl *in, const ptl *out, int m) {
+  if (m > 0 && !covers(&in[0], &out[0])) return false;
+  if (m > 1 && !covers(&in[1], &out[1])) return false;
+  for (int i = m - 1; i >= 2; --i) if (!covers(&in[i], &out[i])) return false;
   return true;
 }
 
 /* 2: add dominates cmp, 0: cmp dominates add, 1: neither (maximality_relation) */
 static int maximality(const emb *add, const emb *cmp) {
   const int m = MIN2(add->n, cmp->n);
-  if (add->n > cmp->n) return covers_all(cmp->head, add->head, m) ? 2 : 1;
-  if (add->n < cmp->n) return covers_all(add->head, cmp->head, m) ? 0 : 1;
-  if (covers_all(add->head, cmp->head, m)) return 0;
-  return covers_all(cmp->head, add->head, m) ? 2 : 1;
+  if (add->n > cmp->n) return covers_all(cmp->v, add->v, m) ? 2 : 1;
+  if (add->n < cmp->n) return covers_all(add->v, cmp->v, m) ? 0 : 1;
+  if (covers_all(add->v, cmp->v, m)) return 0;
+  return covers_all(cmp->v, add->v, m) ? 2 : 1;
 }
 
 /* update_embedding: try to put `node` in front of `e`; NULL = not compatible */
 static emb *link_embedding(ef_task *T, const emb *e, const ef_pairing *node) {
   const ef_config *c = T->cfg;
   const char *G = T->gen->seq;
-  const ptl head = e->head->v;
+  const ptl head = e->v[0];
   const ptl nd = {node->p, node->t, node->l};
-  if (head.p == SINK_START) return node->p >= 0 ? emb_single(T, nd) : NULL;
-  if (node->p < 0) { emb *cp = ar_alloc(&T->ar, sizeof *cp); *cp = *e; return cp; }     /* the source adds nothing: same list */
+  if (head.p == SINK_START) return node->p >= 0 ? emb_prepend(T, NULL, nd) : NULL;
+  if (node->p < 0) { emb *cp = ar_alloc_raw(&T->ar, sizeof *cp); *cp = *e; return cp; }     /* the source adds nothing: same pairings */
   const int small_delta = head.p + head.l - nd.p, big_delta = head.t + head.l - nd.t;
   const int min_fl = (int)c->min_factor_len, fl = 2 * min_fl;
   if (!(small_delta >= fl && big_delta >= fl)) return NULL;
@@ -153,7 +145,9 @@ static emb *link_embedding(ef_task *T, const emb *e, const ef_pairing *node) {
     nl = nd.l - (nd.p + nd.l - best_cut);
   }
   if (!(gap_t <= fl || intron_t)) return NULL;
-  return emb_link(T, e, (ptl){nd.p, nd.t, nl}, (ptl){hp, ht, hl});
+  emb *out = emb_prepend(T, e, (ptl){nd.p, nd.t, nl});
+  out->v[1] = (ptl){hp, ht, hl};
+  return out;
 }
 
 static emblist *subtree_embeddings(ef_task *T, ef_pairing *root, unsigned *tick) {
@@ -161,7 +155,7 @@ static emblist *subtree_embeddings(ef_task *T, ef_pairing *root, unsigned *tick)
   if (ef_timeout_expired(T)) return NULL;
   emblist *L = ar_alloc(&T->ar, sizeof *L);
   root->visited = true;
-  if (root->adjs.n == 0) el_push(T, L, emb_single(T, (ptl){root->p, root->t, root->l}));
+  if (root->adjs.n == 0) el_push(T, L, emb_prepend(T, NULL, (ptl){root->p, root->t, root->l}));
   for (int a = 0; a < root->adjs.n; ++a) {
     emblist *sub = subtree_embeddings(T, root->adjs.v[a], tick);
     if (!sub) return NULL;
@@ -177,6 +171,7 @@ static emblist *subtree_embeddings(ef_task *T, ef_pairing *root, unsigned *tick)
         else ++k;
       }
       if (rel >= 1) el_push(T, L, add);
+      else ar_undo(&T->ar, add);          /* dominated: its bytes are the latest allocation, reuse them */
     }
   }
   root->memo = L;
@@ -186,8 +181,8 @@ static emblist *subtree_embeddings(ef_task *T, ef_pairing *root, unsigned *tick)
 static ef_fz *factorization_of(ef_task *T, const emb *e) {
   const int fl = 2 * (int)T->cfg->min_factor_len;
   ef_fz *z = fz_new(T, e->n);
-  for (const enode *x = e->head; x; x = x->next) {
-    const ptl q = x->v;
+  for (int i = 0; i < e->n; ++i) {
+    const ptl q = e->v[i];
     if (z->n == 0 || q.t - z->f[z->n - 1].ge - 1 > fl) fz_push(T, z, (ef_factor){q.p, q.p + q.l - 1, q.t, q.t + q.l - 1});
     else { z->f[z->n - 1].ee = q.p + q.l - 1; z->f[z->n - 1].ge = q.t + q.l - 1; }
   }

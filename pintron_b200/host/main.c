@@ -176,6 +176,7 @@ int main(int argc, char **argv) {
   ef_parse_genomic_header(gen);
   ef_ntails_removal(gen);
   sched_prepare(&cfg, gen);
+  ef_small_exon_index_build(gen->seq, (size_t)gen->len);      /* host-side 6-mer index, while the CUDA context comes up */
   ef_seq *ests = NULL; size_t nest = 0;
   if (ef_read_fasta("ests.txt", &ests, &nest)) { fprintf(stderr, "* FATAL File ests.txt not found! Terminating\n"); return 1; }
   FILE *f_raw = open_out("raw-multifasta-out.txt"), *f_megs = open_out("megs.txt"), *f_pmegs = open_out("processed-megs.txt");
@@ -189,11 +190,11 @@ int main(int argc, char **argv) {
     it->fwd = ests[i];       /* strand / reverse-complement / polyA masking happen in est_task, on the worker threads */
   }
 
-  /* EST batcher: inside windows of 32 768 input records the ESTs are dispatched longest first, so the ESTs in flight
+  /* EST batcher: inside windows of 262 144 input records the ESTs are dispatched longest first, so the ESTs in flight
    * together (and the jobs of one device batch) have similar sizes; the writer still emits input order. */
   uint32_t *order = malloc(sizeof(uint32_t) * (nest ? nest : 1));
   {
-    const size_t WIN = 32768;
+    const size_t WIN = 262144;
     uint32_t cnt[65];
     for (size_t w0 = 0; w0 < nest; w0 += WIN) {
       const size_t w1 = MIN2(nest, w0 + WIN);

@@ -12,7 +12,7 @@
 void pl_push(ef_task *T, ef_plist *l, ef_pairing *x) {
   if (l->n == l->cap) {
     int nc = l->cap ? l->cap * 2 : 4;
-    ef_pairing **nv = ar_alloc(&T->ar, sizeof(ef_pairing *) * (size_t)nc);
+    ef_pairing **nv = ar_alloc_raw(&T->ar, sizeof(ef_pairing *) * (size_t)nc);
     if (l->n) memcpy(nv, l->v, sizeof(ef_pairing *) * (size_t)l->n);
     l->v = nv; l->cap = nc;
   }
@@ -63,16 +63,40 @@ static bool disjoint(const ef_pairing *a, const ef_pairing *b) {
 static void build_edges(ef_task *T, ef_meg *M, int l) {
   const ef_config *c = T->cfg;
   const int n = M->n, fl = 2 * l + 1, plen = n - 2;
-  for (int i = 1; i < n - 1; ++i)
-    for (int a = 0; a < M->V[i].n; ++a) {
-      ef_pairing *I = M->V[i].v[a];
-      const int ub = MIN2(I->p + I->l + fl + 1, n - l);
-      for (int j = 0; j < ub; ++j)
-        for (int b = 0; b < M->V[j].n; ++b) {
-          ef_pairing *J = M->V[j].v[b];
-          if (edge_ok(I, J, l, fl, c)) { pl_push(T, &I->adjs, J); pl_push(T, &J->incs, I); }
+  /* The reference scans V[0 .. ub) for every pairing I (max-emb-graph.c:540-550); most of those lists are empty, and
+   * edge_ok needs J.p > I.p, i.e. j > i.  Same pairs in the same order from a flat copy of the non-empty lists. */
+  int total = 0;
+  for (int j = 0; j < n; ++j) total += M->V[j].n;
+  ef_pairing **flat = ar_alloc_raw(&T->ar, sizeof(ef_pairing *) * (size_t)(total + 1));
+  int *first_at = ar_alloc_raw(&T->ar, sizeof(int) * (size_t)(n + 1));      /* flat index of the first pairing in V[j ..] */
+  {
+    int k = 0;
+    for (int j = 0; j < n; ++j) { first_at[j] = k; for (int b = 0; b < M->V[j].n; ++b) flat[k++] = M->V[j].v[b]; }
+    first_at[n] = k;
+  }
+  /* two sweeps: count, size every adjacency list once (room for the source / sink edge added below), fill */
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    for (int i = 1; i < n - 1; ++i)
+      for (int a = 0; a < M->V[i].n; ++a) {
+        ef_pairing *I = M->V[i].v[a];
+        const int ub = MIN2(I->p + I->l + fl + 1, n - l);
+        if (ub <= i + 1) continue;
+        const int k1 = first_at[ub];
+        for (int k = first_at[i + 1]; k < k1; ++k) {
+          ef_pairing *J = flat[k];
+          if (!edge_ok(I, J, l, fl, c)) continue;
+          if (sweep == 0) { ++I->adjs.cap; ++J->incs.cap; }
+          else { I->adjs.v[I->adjs.n++] = J; J->incs.v[J->incs.n++] = I; }
         }
-    }
+      }
+    if (sweep == 0)
+      for (int k = first_at[1]; k < first_at[n - 1]; ++k) {
+        ef_pairing *q = flat[k];
+        q->adjs.cap += 1; q->incs.cap += 1;
+        q->adjs.v = ar_alloc_raw(&T->ar, sizeof(ef_pairing *) * (size_t)q->adjs.cap);
+        q->incs.v = ar_alloc_raw(&T->ar, sizeof(ef_pairing *) * (size_t)q->incs.cap);
+      }
+  }
   ef_pairing *source = M->V[0].v[0], *sink = M->V[n - 1].v[0];
   const int max_p = (int)((double)plen * c->max_prefix_discarded_rate);
   for (int i = 1; i <= max_p; ++i)

@@ -184,19 +184,80 @@ static void small_exon_at_prefix(ef_task *T, const ef_seq *est, ef_fz *z) {
 
 static size_t min3z(size_t a, size_t b, size_t c) { size_t t = a; if (t > b) t = b; if (t > c) t = c; return t; }
 
+/* ---- 6-mer position index of the genome (host side) -------------------------------------------------------------
+ * Every trim searched by ef_small_exon_scan is at least LB_SMALL_EXON = 6 letters long, so its occurrences are among
+ * the positions of its first 6-mer.  Built once per genome (counting sort: positions ascending inside a bucket);
+ * windows with a byte outside upper-case ACGT are not indexed, and a trim that starts with such a byte is searched
+ * with memmem instead. */
+static struct { const char *g; size_t len; uint32_t *start, *pos; } g_kidx;
+static inline int nt_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+static inline int kmer6_code(const char *s) {
+  int code = 0;
+  for (int i = 0; i < 6; ++i) { const int c = nt_code(s[i]); if (c < 0) return -1; code = code * 4 + c; }
+  return code;
+}
+
+void ef_small_exon_index_build(const char *g, size_t len) {
+  free(g_kidx.start); free(g_kidx.pos);
+  g_kidx.start = g_kidx.pos = NULL;
+  g_kidx.g = g; g_kidx.len = len;
+  if (!g) return;                                             /* (NULL, 0) drops the index */
+  g_kidx.start = calloc(4097 + 1, sizeof(uint32_t));
+  g_kidx.pos = malloc(sizeof(uint32_t) * (len ? len : 1));
+  if (!g_kidx.start || !g_kidx.pos) { fprintf(stderr, "* FATAL est-fact: out of memory\n"); exit(1); }
+  if (len < 6) return;
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    int code = 0, valid = 0;                                /* rolling: valid = letters of the current run of ACGT */
+    for (size_t i = 0; i < len; ++i) {
+      const int c = nt_code(g[i]);
+      if (c < 0) { valid = 0; code = 0; continue; }
+      code = ((code << 2) | c) & 4095;
+      if (++valid >= 6) {
+        if (sweep == 0) ++g_kidx.start[code + 1];
+        else g_kidx.pos[g_kidx.start[code]++] = (uint32_t)(i - 5);
+      }
+    }
+    if (sweep == 0) for (int k = 0; k < 4096; ++k) g_kidx.start[k + 1] += g_kidx.start[k];
+    else { for (int k = 4096; k > 0; --k) g_kidx.start[k] = g_kidx.start[k - 1]; g_kidx.start[0] = 0; }   /* undo the cursor advance */
+  }
+}
+
 /* The scan of search_small_exon (factorization-refinement.c:770-834): the longest trim (offstart, offend) of the EST
  * middle e[estart, estart+elen) that occurs inside g[allgstart, allgstart+allglen) leaving two introns that both
  * classify.  out = {max_sexon, ecut1, ecut2, gcut1_1, gcut1_2, gcut2_1, gcut2_2}.
  * The reference runs strstr for every (offstart, offend) and keeps the first strictly longer hit.  Same result, fewer
  * scans: an occurrence at q of the trim (offstart, offend), length sl = elen - offstart - offend, must satisfy
  * offstart + MINI <= q <= allglen - MINI - elen + offstart (offend cancels out of the right limit), so for one
- * offstart every longer trim occurs where the shortest one does: one memmem pass per offstart finds all of them,
- * and trims that cannot beat the current best are skipped (classify_intron is pure). */
+ * offstart every longer trim occurs where the shortest one does: the occurrences of the shortest trim (from the 6-mer
+ * index, else one memmem pass) find all of them, and trims that cannot beat the current best are skipped
+ * (classify_intron is pure). */
+typedef struct se_state {
+  const char *g, *pat, *allgfact;
+  int glen_all;
+  size_t elen, offstart, allgstart, allglen, sl_min, sl_max, max_sexon, best_here, b_q, b_offend;
+} se_state;
+
+static inline void se_occurrence(se_state *S, size_t q) {
+  size_t ext = S->sl_min;
+  while (ext < S->sl_max && S->pat[ext] == S->allgfact[q + ext]) ++ext;
+  /* trims that occur at q: sl_min <= sl <= ext, longest (= smallest offend) first; only sl > best so far matter:
+   * for equal sl an earlier q wins, and earlier offstarts already hold max_sexon */
+  const size_t floor_sl = MAX2(S->max_sexon, S->best_here);
+  for (size_t sl = ext; sl >= S->sl_min && sl > floor_sl; --sl) {
+    const size_t offend = S->elen - S->offstart - sl;
+    const size_t i1start = S->allgstart + S->offstart, i1end = S->allgstart + q - 1;
+    const size_t i2start = i1end + 1 + sl, i2end = S->allgstart + S->allglen - offend - 1;
+    const char t1 = classify_intron(S->g, S->glen_all, (int)i1start, (int)i1end), t2 = classify_intron(S->g, S->glen_all, (int)i2start, (int)i2end);
+    if (t1 != 2 && t2 != 2) { S->best_here = sl; S->b_q = q; S->b_offend = offend; break; }
+  }
+}
+
 void ef_small_exon_scan(const char *g, int glen_all, const char *e, size_t estart, size_t elen, size_t allgstart, size_t allglen,
                         size_t f1slen, size_t f2plen, size_t MINI, size_t out[7]) {
   const char *efact = e + estart, *allgfact = g + allgstart;
   size_t max_sexon = 0, ecut1 = 0, ecut2 = 0, gcut1_1 = 0, gcut1_2 = 0, gcut2_1 = 0, gcut2_2 = 0;
   const size_t max_offstart = min3z(f1slen + 1 - MIN_PERFECT_BORDER, elen + 1 - LB_SMALL_EXON, allglen + 1 - (2 * MINI) - LB_SMALL_EXON);
+  const bool have_index = g_kidx.g == g && g_kidx.start != NULL;
   for (size_t offstart = 0; offstart < max_offstart; ++offstart) {
     const size_t max_offend = min3z(f2plen + 1 - MIN_PERFECT_BORDER, elen + 1 - offstart - LB_SMALL_EXON,
                                     allglen + 1 - (2 * MINI) - LB_SMALL_EXON - offstart);
@@ -205,32 +266,27 @@ void ef_small_exon_scan(const char *g, int glen_all, const char *e, size_t estar
     if (allglen + offstart < MINI + elen) continue;                 /* no room for any occurrence */
     const size_t qmin = offstart + MINI, qmax = allglen - MINI - elen + offstart;
     if (qmax < qmin) continue;
-    const char *pat = efact + offstart;
-    /* occurrences of the shortest trim, ascending, with the length the full trim keeps matching there */
-    size_t best_here = 0;                                             /* the longest sl accepted for this offstart */
-    size_t b_q = 0, b_offend = 0;
-    const char *scan = allgfact + qmin, *scan_end = allgfact + qmax + sl_min;      /* last window ends here */
-    while (scan + sl_min <= scan_end) {
-      const char *occ = memmem(scan, (size_t)(scan_end - scan), pat, sl_min);
-      if (!occ) break;
-      const size_t q = (size_t)(occ - allgfact);
-      size_t ext = sl_min;
-      while (ext < sl_max && pat[ext] == allgfact[q + ext]) ++ext;
-      /* trims that occur at q: sl_min <= sl <= ext, longest (= smallest offend) first; only sl > best so far matter:
-       * for equal sl an earlier q wins, and earlier offstarts already hold max_sexon */
-      const size_t floor_sl = MAX2(max_sexon, best_here);
-      for (size_t sl = ext; sl >= sl_min && sl > floor_sl; --sl) {
-        const size_t offend = elen - offstart - sl;
-        const size_t i1start = allgstart + offstart, i1end = allgstart + q - 1;
-        const size_t i2start = i1end + 1 + sl, i2end = allgstart + allglen - offend - 1;
-        const char t1 = classify_intron(g, glen_all, (int)i1start, (int)i1end), t2 = classify_intron(g, glen_all, (int)i2start, (int)i2end);
-        if (t1 != 2 && t2 != 2) { best_here = sl; b_q = q; b_offend = offend; break; }
+    se_state S = {g, efact + offstart, allgfact, glen_all, elen, offstart, allgstart, allglen, sl_min, sl_max, max_sexon, 0, 0, 0};
+    const int code = have_index ? kmer6_code(S.pat) : -1;
+    if (code >= 0) {
+      /* occurrences of the shortest trim, ascending: bucket positions inside [allgstart + qmin, allgstart + qmax] */
+      const uint32_t *lo = g_kidx.pos + g_kidx.start[code], *hi = g_kidx.pos + g_kidx.start[code + 1];
+      const size_t pmin = allgstart + qmin, pmax = allgstart + qmax;
+      while (lo < hi) { const uint32_t *mid = lo + (hi - lo) / 2; if (*mid < pmin) lo = mid + 1; else hi = mid; }
+      for (const uint32_t *it = lo, *end = g_kidx.pos + g_kidx.start[code + 1]; it < end && *it <= pmax; ++it)
+        if (sl_min == 6 || memcmp(g + *it + 6, S.pat + 6, sl_min - 6) == 0) se_occurrence(&S, (size_t)*it - allgstart);
+    } else {
+      const char *scan = allgfact + qmin, *scan_end = allgfact + qmax + sl_min;      /* last window ends here */
+      while (scan + sl_min <= scan_end) {
+        const char *occ = memmem(scan, (size_t)(scan_end - scan), S.pat, sl_min);
+        if (!occ) break;
+        se_occurrence(&S, (size_t)(occ - allgfact));
+        scan = occ + 1;
       }
-      scan = occ + 1;
     }
-    if (best_here > max_sexon) {
-      const size_t sl = best_here, i1start = allgstart + offstart, i1end = allgstart + b_q - 1;
-      const size_t i2start = i1end + 1 + sl, i2end = allgstart + allglen - b_offend - 1;
+    if (S.best_here > max_sexon) {
+      const size_t sl = S.best_here, i1start = allgstart + offstart, i1end = allgstart + S.b_q - 1;
+      const size_t i2start = i1end + 1 + sl, i2end = allgstart + allglen - S.b_offend - 1;
       max_sexon = sl; ecut1 = estart + offstart; ecut2 = estart + offstart + sl;
       gcut1_1 = i1start; gcut1_2 = i1end + 1; gcut2_1 = i2start; gcut2_2 = i2end + 1;
     }

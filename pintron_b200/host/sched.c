@@ -48,7 +48,7 @@ double ef_now(void) {
  * every munmap interrupts all threads of the process to flush their TLBs — with a dozen workers handling long mRNAs
  * that alone was most of the run time.  head = the chunk being filled; chunks after it on the list are spare. */
 #define AR_HDR (((sizeof(ef_chunk)) + 15u) & ~(size_t)15u)
-void *ar_alloc(ef_arena *a, size_t bytes) {
+void *ar_alloc_raw(ef_arena *a, size_t bytes) {
   bytes = (bytes + 15u) & ~(size_t)15u;
   ef_chunk *c = a->cur;
   while (!c || c->used + bytes > c->cap) {
@@ -65,8 +65,15 @@ void *ar_alloc(ef_arena *a, size_t bytes) {
   }
   void *p = (char *)c + c->used;
   c->used += bytes;
-  memset(p, 0, bytes);
   return p;
+}
+
+void *ar_alloc(ef_arena *a, size_t bytes) { return memset(ar_alloc_raw(a, bytes), 0, bytes); }
+
+/* give back the most recent allocation(s): everything from p on, if p lies in the chunk being filled */
+void ar_undo(ef_arena *a, void *p) {
+  ef_chunk *c = a->cur;
+  if (c && (char *)p >= (char *)c + AR_HDR && (char *)p < (char *)c + c->used) c->used = (size_t)((char *)p - (char *)c);
 }
 
 void ar_reset(ef_arena *a) {
@@ -154,6 +161,8 @@ typedef struct fiber {
   int base;                 /* index of this fiber's first job in the group's batch */
   int phase;
   bool has_results;
+  size_t need_a, need_v;    /* staging bytes of the pending requests (valid while need_valid) */
+  bool need_valid;
   bool submitted;           /* its requests are part of the batch in flight (false: deferred to the next one) */
   struct group *grp;
 } fiber;
@@ -194,7 +203,7 @@ static const uint32_t *g_order;       /* dispatch order (length-sorted windows),
 static __thread fiber *tl_fiber;
 static __thread worker *tl_worker;
 static uint64_t g_batches, g_jobs, g_h2d, g_d2h, g_deferred, g_grows;
-static double g_gpu_wait, g_t_fibers, g_t_gather, g_t_submit, g_t_init, g_t_fini;
+static double g_gpu_wait, g_t_fibers, g_t_gather, g_t_submit, g_t_init, g_t_fini, g_t_end_sum, g_t_end_min;
 static pthread_mutex_t g_stat_mu = PTHREAD_MUTEX_INITIALIZER;
 
 /* ---- where the host time goes: CPU seconds per phase of the per-EST code (fibers only run between yields) ------ */
@@ -291,6 +300,7 @@ void dp_wait(void) {
   fiber *f = tl_fiber;
   if (f->nreq == 0 || f->has_results) return;
   f->state = F_WAITING;
+  f->need_valid = false;
   phase_account();
   f->phase = tl_phase;
 #if EF_FAST_SWITCH
@@ -358,7 +368,7 @@ static void gather(group *g) {
      * start-up; a fiber whose requests do not fit any more waits for the next batch.  Re-pinning memory or cudaMalloc
      * in the middle of a run stalls every thread of the process, which is what long mRNAs used to trigger all the
      * time.  Only a single fiber that is larger than an EMPTY batch makes the buffers grow. */
-    {
+    if (!f->need_valid) {
       size_t need_a = 0, need_v = 0;
       for (int i = 0; i < f->nreq; ++i) {
         const ef_req *r = &f->reqs[i];
@@ -366,11 +376,12 @@ static void gather(group *g) {
         if (r->op == PC_OP_ALIGN || r->op == PC_OP_GAP) need_v += (size_t)r->a.len + (size_t)r->b.len;
         else if (r->op == PC_OP_SEED) need_v += 12u * (size_t)r->out_cap + 4;
       }
-      if (g->njobs > 0 && (g->arena_len + need_a > g->arena_cap || g->var_len + need_v > g->var_cap || (size_t)g->njobs + (size_t)f->nreq > (size_t)g->jobs_cap)) {
-        f->submitted = false;
-        ++g->deferred;
-        continue;
-      }
+      f->need_a = need_a; f->need_v = need_v; f->need_valid = true;
+    }
+    if (g->njobs > 0 && (g->arena_len + f->need_a > g->arena_cap || g->var_len + f->need_v > g->var_cap || (size_t)g->njobs + (size_t)f->nreq > (size_t)g->jobs_cap)) {
+      f->submitted = false;
+      ++g->deferred;
+      continue;
     }
     f->submitted = true;
     f->base = g->njobs;
@@ -500,7 +511,7 @@ static void *worker_main(void *arg) {
      * is done once per group; a buffer that outgrows its share later moves to its own allocation */
     const size_t per_fiber = 4096;
     g->arena_cap = MAX2((size_t)1 << 20, (size_t)g->nfibers * per_fiber);
-    g->jobs_cap = MAX2(4096, g->nfibers * 16);
+    g->jobs_cap = MAX2(4096, g->nfibers * 32);
     g->res_cap = (size_t)g->jobs_cap * PC_RES_INTS;
     g->var_cap = g->arena_cap;
     const size_t jobs_b = (sizeof(pc_job) * (size_t)g->jobs_cap + 255u) & ~(size_t)255u, res_b = g->res_cap * sizeof(int32_t);
@@ -524,6 +535,7 @@ static void *worker_main(void *arg) {
   g_deferred += w->g[0].deferred + w->g[1].deferred; g_grows += w->g[0].grows + w->g[1].grows;
   g_t_fibers += w->t_fibers; g_t_gather += w->t_gather; g_t_submit += w->t_submit;
   g_t_init += tw1 - tw0; g_t_fini += ef_now() - tw2;
+  g_t_end_sum += tw2; if (g_t_end_min == 0 || tw2 < g_t_end_min) g_t_end_min = tw2;
   for (int i = 0; i < EF_PH_COUNT; ++i) g_phase_s[i] += tl_phase_s[i];
   pthread_mutex_unlock(&g_stat_mu);
   return NULL;
@@ -601,7 +613,7 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
   if ((size_t)per_group * 2 * (size_t)nthreads > n_items) per_group = (int)(n_items / (2 * (size_t)nthreads)) + 1;
   atomic_store(&g_next_item, 0);
   g_n_items = n_items;
-  g_batches = g_jobs = g_h2d = g_d2h = g_deferred = g_grows = 0; g_gpu_wait = 0; g_t_fibers = g_t_gather = g_t_submit = g_t_init = g_t_fini = 0;
+  g_batches = g_jobs = g_h2d = g_d2h = g_deferred = g_grows = 0; g_gpu_wait = 0; g_t_fibers = g_t_gather = g_t_submit = g_t_init = g_t_fini = g_t_end_sum = g_t_end_min = 0;
   const double ts1 = ef_now();
   worker *ws = calloc((size_t)nthreads, sizeof(worker));
   for (int i = 0; i < nthreads; ++i) {
@@ -621,8 +633,8 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
   if (!cfg->quiet)
     fprintf(stderr, "* INFO  scheduler: %d thread(s) x 2 x %d fibers on %d GPU(s); context + genome index %.3f s (%.3f s of it still to wait for), workers %.3f s "
             "(stream set-up %.3f s, tear-down %.3f s per thread on average), context tear-down %.3f s; "
-            "%llu fiber deferrals, %llu staging re-allocations\n",
+            "%llu fiber deferrals, %llu staging re-allocations; threads idle at the end %.3f s on average (first done %.3f s before the last)\n",
             nthreads, per_group, nuse, g_prep.secs, ts1 - ts0, ts2 - ts1, g_t_init / nthreads, g_t_fini / nthreads, ef_now() - ts2,
-            (unsigned long long)g_deferred, (unsigned long long)g_grows);
+            (unsigned long long)g_deferred, (unsigned long long)g_grows, ts2 - g_t_end_sum / nthreads, ts2 - g_t_end_min);
   return 0;
 }

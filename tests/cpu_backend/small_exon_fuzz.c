@@ -1,7 +1,8 @@
 /* TEST INFRASTRUCTURE.  ef_small_exon_scan (pintron_b200/host/refine_fact.c: one memmem pass per offstart) against a
  * literal restatement of the reference's nested strstr loops (src/factorization-refinement.c:770-834: NUL-patched
  * copies of the EST middle and of the intron, strstr per (offstart, offend), "first strictly longer" update), on
- * random genomes with planted copies of the EST middle, real classify_intron included.  Prints "ok N hits H". */
+ * random genomes with planted copies of the EST middle (some with N / lower-case bytes), real classify_intron
+ * included; both search paths (6-mer index, memmem).  Prints "ok N hits H". */
 #include "ef.h"
 #include <stdio.h>
 #include <stdlib.h>
@@ -70,8 +71,10 @@ int main(int argc, char **argv) {
       memcpy(g + q, e + estart + os, sl);
       if (k & 1) { g[q - 2] = 'A'; g[q - 1] = 'G'; g[q + sl] = 'G'; g[q + sl + 1] = 'T'; }
     }
+    if (c % 7 == 3) for (int k = 0; k < 12; ++k) { g[rnd() % glen] = "Nacgt"[rnd() % 5]; e[rnd() % elenall] = "Nacgt"[rnd() % 5]; }
     if (c & 1) { memcpy(g + allgstart, "GT", 2); memcpy(g + allgstart + 1, "GT", 2); memcpy(g + allgstart + allglen - 2, "AG", 2); }
     size_t r1[7], r2[7];
+    ef_small_exon_index_build(c % 4 != 1 ? g : NULL, c % 4 != 1 ? glen : 0);        /* 3 of 4 cases through the 6-mer index, the rest through memmem */
     scan_literal(g, (int)glen, e, estart, elen, allgstart, allglen, f1slen, f2plen, MINI, r1);
     ef_small_exon_scan(g, (int)glen, e, estart, elen, allgstart, allglen, f1slen, f2plen, MINI, r2);
     if (memcmp(r1, r2, sizeof r1)) {
