@@ -12,6 +12,7 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 static const bool g_prof = getenv("PC_PROFILE") != nullptr;
 static double g_t[8];      /* check, reserve, h2d, sort, launch, d2h, sync (racy sums: diagnostics only) */
 static unsigned long long g_dev_grows, g_host_allocs, g_host_alloc_bytes; static double g_host_alloc_s;
+static unsigned long long g_op_jobs[PC_OP_COUNT], g_op_suma[PC_OP_COUNT], g_op_sumb[PC_OP_COUNT], g_op_maxa[PC_OP_COUNT], g_op_maxb[PC_OP_COUNT], g_op_cells[PC_OP_COUNT];
 static double g_op_ms[PC_OP_COUNT]; static unsigned long long g_op_launches[PC_OP_COUNT], g_retry_rounds, g_retry_jobs, g_pool_grows;
 extern "C" void pc_debug_dump(void) {
   if (!g_prof) return;
@@ -19,6 +20,8 @@ extern "C" void pc_debug_dump(void) {
   fprintf(stderr, "[pc profile] host: check %.3f reserve %.3f h2d %.3f sort %.3f launch %.3f d2h %.3f sync %.3f s\n", g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5], g_t[6]);
   fprintf(stderr, "[pc profile] device ms per op:");
   for (int i = 0; i < PC_OP_COUNT; ++i) if (g_op_launches[i]) fprintf(stderr, " %s %.1f (%llu launches)", nm[i], g_op_ms[i], g_op_launches[i]);
+  fprintf(stderr, "\n[pc profile] jobs per op (count, mean a_len, mean b_len, max a_len, max b_len, a*b cells):");
+  for (int i = 0; i < PC_OP_COUNT; ++i) if (g_op_jobs[i]) fprintf(stderr, " %s %llu %.1f %.1f %llu %llu %.3g;", nm[i], g_op_jobs[i], (double)g_op_suma[i] / g_op_jobs[i], (double)g_op_sumb[i] / g_op_jobs[i], g_op_maxa[i], g_op_maxb[i], (double)g_op_cells[i]);
   fprintf(stderr, "\n[pc profile] pool retries: %llu rounds, %llu jobs, %llu pool growths\n", g_retry_rounds, g_retry_jobs, g_pool_grows);
   fprintf(stderr, "[pc profile] device buffer growths (cudaMalloc during the run): %llu; pinned host allocations: %llu, %.1f MB, %.3f s\n",
           g_dev_grows, g_host_allocs, g_host_alloc_bytes / 1048576.0, g_host_alloc_s);
@@ -294,6 +297,8 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
       const int sg = (int)j.op * 4 + cls;
       Seg &S = seg[sg];
       ++S.n; S.max_a = std::max(S.max_a, j.a_len); S.max_b = std::max(S.max_b, j.b_len);
+      if (g_prof) { ++g_op_jobs[j.op]; g_op_suma[j.op] += j.a_len; g_op_sumb[j.op] += j.b_len; g_op_cells[j.op] += (unsigned long long)j.a_len * j.b_len;
+                    if (j.a_len > g_op_maxa[j.op]) g_op_maxa[j.op] = j.a_len; if (j.b_len > g_op_maxb[j.op]) g_op_maxb[j.op] = j.b_len; }
       key[q] = (uint16_t)(sg * 64 + (63 - lg));
       ++bins[key[q] + 1];
     }

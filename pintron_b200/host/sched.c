@@ -193,12 +193,14 @@ typedef struct worker {
   const ef_seq *gen;
   ef_task_fn fn;
   void *user;
+  int inflight;             /* ESTs started and not finished, both groups */
   uint64_t batches, jobs, h2d, d2h;
   double gpu_wait, t_fibers, t_gather, t_submit;
 } worker;
 
 static _Atomic size_t g_next_item;
 static size_t g_n_items;
+static int g_nthreads = 1;
 static const uint32_t *g_order;       /* dispatch order (length-sorted windows), NULL = input order */
 static __thread fiber *tl_fiber;
 static __thread worker *tl_worker;
@@ -460,14 +462,22 @@ static bool run_group(worker *w, group *g) {
       if (g->fibers[k].state == F_WAITING && g->fibers[k].submitted) { g->fibers[k].state = F_RUNNABLE; g->fibers[k].has_results = true; }
   }
   bool any = false;
+  int started_now = 0;
   const double tf0 = ef_now();
   for (int k = 0; k < g->nfibers; ++k) {
     fiber *f = &g->fibers[k];
     for (;;) {
       if (f->state == F_FREE || f->state == F_DONE) {
+        if (f->state == F_DONE) { --w->inflight; f->state = F_FREE; }
+        /* Ramp: a group takes at most 64 new ESTs per round.  ESTs are dealt longest first; a thread that filled all
+         * its fibers in one go would own the thousand longest ones (on mixed EST / mRNA inputs that is most of the
+         * work of the run, fixed at t = 0).  Taking them in small bites while the other threads do the same spreads
+         * the heavy ESTs evenly. */
+        if (started_now >= 64) break;
         size_t idx = atomic_fetch_add(&g_next_item, 1);
-        if (idx >= g_n_items) { f->state = F_FREE; break; }
+        if (idx >= g_n_items) break;
         fiber_start(w, g, f, g_order ? g_order[idx] : idx);
+        ++w->inflight; ++started_now;
       }
       if (f->state != F_RUNNABLE) break;
       tl_fiber = f;
@@ -526,6 +536,7 @@ static void *worker_main(void *arg) {
   while (alive[0] || alive[1]) {
     for (int i = 0; i < 2; ++i)
       if (alive[i] || w->g[i].pending) alive[i] = run_group(w, &w->g[i]);
+    if (!alive[0] && !alive[1] && atomic_load_explicit(&g_next_item, memory_order_relaxed) < g_n_items) alive[0] = true;   /* nothing in flight but ESTs left */
   }
   const double tw2 = ef_now();
   /* No tear-down: est-fact exits right after the last EST, and freeing pinned / device memory (two dozen streams,
@@ -613,6 +624,7 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
   if ((size_t)per_group * 2 * (size_t)nthreads > n_items) per_group = (int)(n_items / (2 * (size_t)nthreads)) + 1;
   atomic_store(&g_next_item, 0);
   g_n_items = n_items;
+  g_nthreads = nthreads;
   g_batches = g_jobs = g_h2d = g_d2h = g_deferred = g_grows = 0; g_gpu_wait = 0; g_t_fibers = g_t_gather = g_t_submit = g_t_init = g_t_fini = g_t_end_sum = g_t_end_min = 0;
   const double ts1 = ef_now();
   worker *ws = calloc((size_t)nthreads, sizeof(worker));
