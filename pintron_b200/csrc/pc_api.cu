@@ -10,11 +10,17 @@ unsigned long long g_pc_launches = 0;
 #include <chrono>
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const bool g_prof = getenv("PC_PROFILE") != nullptr;
+/* PC_CAPTURE=<file>: every batch handed to pc_submit is appended to <file> (bench.py replays the job stream of a real
+ * est-fact run as its device-resident workload).  Record = u32 njobs, u64 arena_bytes, jobs, arena. */
+#include <mutex>
+static FILE *g_capture = getenv("PC_CAPTURE") ? fopen(getenv("PC_CAPTURE"), "wb") : nullptr;
+static std::mutex g_capture_mu;
 static double g_t[8];      /* check, reserve, h2d, sort, launch, d2h, sync (racy sums: diagnostics only) */
 static unsigned long long g_dev_grows, g_host_allocs, g_host_alloc_bytes; static double g_host_alloc_s;
 static unsigned long long g_op_jobs[PC_OP_COUNT], g_op_suma[PC_OP_COUNT], g_op_sumb[PC_OP_COUNT], g_op_maxa[PC_OP_COUNT], g_op_maxb[PC_OP_COUNT], g_op_cells[PC_OP_COUNT];
 static double g_op_ms[PC_OP_COUNT]; static unsigned long long g_op_launches[PC_OP_COUNT], g_retry_rounds, g_retry_jobs, g_pool_grows;
 extern "C" void pc_debug_dump(void) {
+  if (g_capture) fflush(g_capture);
   if (!g_prof) return;
   static const char *nm[PC_OP_COUNT] = {"ALIGN", "KBAND", "EDIT", "BORDERS", "GAP", "AFFIX", "SUFCUT", "PRECUT", "LCS", "SEED"};
   fprintf(stderr, "[pc profile] host: check %.3f reserve %.3f h2d %.3f sort %.3f launch %.3f d2h %.3f sync %.3f s\n", g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5], g_t[6]);
@@ -394,6 +400,12 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
   CU(cudaSetDevice(st->ctx->device));
   int rc = check_jobs(st, jobs, njobs, arena_bytes, var_out_bytes);
   if (rc) return rc;
+  if (g_capture) {
+    std::lock_guard<std::mutex> lk(g_capture_mu);
+    const uint32_t n32 = (uint32_t)njobs; const uint64_t ab = arena_bytes;
+    fwrite(&n32, 4, 1, g_capture); fwrite(&ab, 8, 1, g_capture);
+    fwrite(jobs, sizeof(pc_job), (size_t)njobs, g_capture); fwrite(arena, 1, arena_bytes, g_capture);
+  }
   PROF(0, tp);
   // one spare readable byte after the arena: general_refine_borders reads t[len_t] (refine.c:362-374 adaptor)
   if (st->arena.reserve(arena_bytes + 16) || st->jobs.reserve(sizeof(pc_job) * (size_t)njobs) ||

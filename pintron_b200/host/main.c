@@ -162,6 +162,16 @@ int main(int argc, char **argv) {
   setenv("CUDA_MODULE_LOADING", "EAGER", 0);
   ef_config cfg;
   if (ef_config_parse(&cfg, argc, argv)) return 1;
+  /* --devices on a multi-GPU box: show the CUDA runtime only the GPUs this process will use (initialising the driver
+   * for eight GPUs to use one costs most of a second), and renumber them 0..n-1 */
+  if (cfg.n_devices > 0 && !getenv("CUDA_VISIBLE_DEVICES")) {
+    char list[16 * 12 + 1]; size_t at = 0;
+    for (int i = 0; i < cfg.n_devices; ++i) {
+      at += (size_t)snprintf(list + at, sizeof list - at, i ? ",%d" : "%d", cfg.devices[i]);
+      cfg.devices[i] = i;
+    }
+    setenv("CUDA_VISIBLE_DEVICES", list, 1);
+  }
   if (!cfg.quiet) fprintf(stderr, "* INFO  EST-FACTORIZATION v2 (B200 build)\n");
   char name[64];
   snprintf(name, sizeof name, "info-pid-%u.log", (unsigned)getpid());

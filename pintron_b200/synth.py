@@ -4,9 +4,13 @@ genomic.txt / ests.txt text in the reference's input format (one FASTA genome re
 multi-FASTA ESTs with `/gb=` and `/clone_end=` header fields, io-multifasta.c:279-504) plus the simulated exon
 structure of every EST (used only to derive DP job shapes for the device-path bench, never as a truth for parity).
 """
+import re
+
 import numpy as np
 
 COMP = bytes.maketrans(b"ACGTNacgtn", b"TGCANtgcan")
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_LINES = re.compile(rb".{1,70}", re.S)          # FASTA body lines of 70 columns
 
 CONFIGS = {
     # name: genome nt, genes, exons/gene, exon len range, intron len range, reads, read len range, mRNA fraction
@@ -93,21 +97,27 @@ class Synth:
         return b"\n".join(lines) + b"\n"
 
     def _mutate(self, s, err):
+        """Per-base errors at rate err: 60 % substitutions, 20 % insertions (a random base before the original one),
+        20 % deletions.  Vectorised: one numpy pass per read."""
         rng = self.rng
         n = len(s)
         r = rng.random(n)
-        if not (r < err).any():
+        hit = r < err
+        if not hit.any():
             return s
-        out = bytearray()
-        for i, c in enumerate(s):
-            x = r[i]
-            if x >= err:
-                out.append(c)
-            elif x < 0.6 * err:
-                out.append(b"ACGT"[int(rng.integers(0, 4))])
-            elif x < 0.8 * err:
-                out.append(b"ACGT"[int(rng.integers(0, 4))]); out.append(c)
-        return bytes(out)
+        src = np.frombuffer(s, dtype=np.uint8)
+        sub, ins, dele = hit & (r < 0.6 * err), hit & (r >= 0.6 * err) & (r < 0.8 * err), hit & (r >= 0.8 * err)
+        cnt = np.ones(n, dtype=np.int64)
+        cnt[ins] = 2
+        cnt[dele] = 0
+        off = np.concatenate(([0], np.cumsum(cnt)))
+        out = np.empty(int(off[-1]), dtype=np.uint8)
+        keep = ~dele
+        out[off[1:][keep] - 1] = src[keep]                      # the original base is the last byte of its slot
+        rnd = _ACGT[rng.integers(0, 4, size=n)]
+        out[off[:-1][sub]] = rnd[sub]
+        out[off[:-1][ins]] = rnd[ins]
+        return out.tobytes()
 
     def reads(self, start=0, count=None):
         """Yield (header, sequence, exon_pieces, forward_sequence); exon_pieces = [(genome_start, genome_end)] of the
@@ -123,10 +133,14 @@ class Synth:
             ln = min(int(rng.integers(lo, hi + 1)), len(t))
             s0 = int(rng.integers(0, len(t) - ln + 1))
             pieces = []
-            for k, (a, b) in enumerate(exons):
-                x0, x1 = max(s0, bounds[k]), min(s0 + ln, bounds[k + 1])
+            k0 = int(np.searchsorted(bounds, s0, side="right")) - 1
+            k1 = int(np.searchsorted(bounds, s0 + ln, side="left"))
+            for k in range(k0, k1):                      # the exons the read overlaps
+                a = exons[k][0]
+                bk = int(bounds[k])
+                x0, x1 = max(s0, bk), min(s0 + ln, int(bounds[k + 1]))
                 if x0 < x1:
-                    pieces.append((a + int(x0 - bounds[k]), a + int(x1 - bounds[k])))
+                    pieces.append((a + x0 - bk, a + x1 - bk))
             seq = self._mutate(t[s0:s0 + ln], cfg["err"])
             if rng.random() < 0.002 * 50:          # ~0.2 % N overall, concentrated in 10 % of the reads
                 sa = bytearray(seq)
@@ -145,5 +159,43 @@ class Synth:
         out = []
         for h, s, _, _ in self.reads(start, count):
             out.append(h)
-            out += [s[i:i + 70] for i in range(0, len(s), 70)]
+            out += _LINES.findall(s)
         return b"\n".join(out) + b"\n"
+
+
+def ests_fasta_parallel(name, total, start, count, chunk=4000, procs=None):
+    """ests.txt bytes for reads [start, start+count) of Synth(name, reads=total), generated by child processes
+    (`python -m pintron_b200.synth`, so it is safe next to an initialised CUDA context) in fixed chunks of `chunk` reads;
+    each chunk seeds its own generator from its first read index, so the bytes depend on `chunk` but not on the number
+    of processes."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    tasks = [(s, min(chunk, start + count - s)) for s in range(start, start + count, chunk)]
+    if len(tasks) <= 1:
+        return b"".join(Synth(name, reads=total).ests_fasta(s, c) for s, c in tasks)
+    procs = procs or max(1, min(len(tasks), (os.cpu_count() or 2) - 1))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = []
+    with tempfile.TemporaryDirectory(prefix="pintron_synth_") as tmp:
+        running, nxt, files = [], 0, [os.path.join(tmp, f"c{i}.fa") for i in range(len(tasks))]
+        while nxt < len(tasks) or running:
+            while nxt < len(tasks) and len(running) < procs:
+                s, c = tasks[nxt]
+                running.append(subprocess.Popen([sys.executable, "-m", "pintron_b200.synth", name, str(total), str(s), str(c), files[nxt]], cwd=root))
+                nxt += 1
+            p = running.pop(0)
+            if p.wait() != 0:
+                raise RuntimeError("synthetic EST generation failed")
+        for f in files:
+            with open(f, "rb") as fh:
+                out.append(fh.read())
+    return b"".join(out)
+
+
+if __name__ == "__main__":
+    import sys
+    _name, _total, _start, _count, _path = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
+    with open(_path, "wb") as _fh:
+        _fh.write(Synth(_name, reads=_total).ests_fasta(_start, _count))

@@ -21,7 +21,8 @@ shift
 for cfg in "$@"; do
   echo "== $W $READS reads: $cfg"
   s=$(date +%s.%N)
-  /root/repo/pintron_b200/bin/est-fact $cfg 2> err.log
+  { time /root/repo/pintron_b200/bin/est-fact $cfg 2> err.log ; } 2> time.log
   e=$(date +%s.%N); echo "rc=$? wall $(python -c "print(round($e - $s, 3))") s"
+  tr "\n" " " < time.log; echo
   grep -E "Timer (Algorithm|Total)|device batches|thread-seconds|scheduler|by phase|pc profile|pc op" err.log
 done
