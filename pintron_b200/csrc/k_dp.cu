@@ -451,7 +451,8 @@ __global__ void __launch_bounds__(PC_WARPS_PER_CTA * 32) k_warp_per_job(PcDevBat
   const int nwarps = gridDim.x * PC_WARPS_PER_CTA;
   // jobs are sorted heaviest first; deal them round-robin over the resident warps
   WarpPool wp = pc_warp_pool(B, blockIdx.x * PC_WARPS_PER_CTA + wib);
-  for (int w = blockIdx.x * PC_WARPS_PER_CTA + wib; w < B.n; w += nwarps) {
+  const int njobs = B.n_dev ? (int)*B.n_dev : B.n;
+  for (int w = blockIdx.x * PC_WARPS_PER_CTA + wib; w < njobs; w += nwarps) {
     wp.used = 0;
     if (OP == PC_OP_ALIGN) op_align(B, wp, w, smem[wib], lane);
     else if (OP == PC_OP_KBAND) op_kband(B, wp, w, smem[wib], lane);

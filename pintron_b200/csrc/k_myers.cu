@@ -1,0 +1,82 @@
+// k_myers.cu — edit_distance (reference src/refine.c:51, src/compute-alignments.c:235) and K_band_edit_distance
+// (src/compute-alignments.c:319-453) as ONE JOB PER THREAD, bit-parallel (myers_core.h), for sm_100a.
+//
+// est-fact issues these two by the million on short strings (splice-shift checks of 10-40 nt, one K-band test per exon
+// and candidate factorization): a warp-wide wavefront spends its time in __syncwarp and shared-memory round trips on
+// matrices of a few hundred cells.  Here 64 rows of a column are one 64-bit word, a column costs ~17 integer
+// instructions per block of 64 rows, and a warp works on 32 jobs at a time.  The match vectors (10 symbols x MAXW
+// words per thread) live in shared memory, interleaved by thread (conflict-free).
+//
+// Jobs this form cannot answer go to a device-side list that the generic wavefront kernel (k_dp.cu) then runs, so
+// every result stays bit-exact: strings with bytes outside ACGT/acgt/N/n, shorter strings above 64*MAXW letters, and
+// K-band jobs whose true distance is above k while the reference would report the value of its band-restricted
+// matrix (2k+1 < n): that value is not the edit distance and only the banded sweep reproduces it.
+#include "pc_device.cuh"
+#include "myers_core.h"
+
+namespace {
+
+constexpr int MY_TPB = 64;
+
+template <int OP, int MAXW>
+__global__ void __launch_bounds__(MY_TPB) k_myers(PcDevBatch B, uint32_t *slow_list, uint32_t *slow_count) {
+  __shared__ unsigned long long peq[MY_NSYM * MAXW * MY_TPB];
+  for (int w = blockIdx.x * MY_TPB + threadIdx.x; w < B.n; w += gridDim.x * MY_TPB) {
+    const uint32_t ji = B.idx[w];
+    const pc_job *job = B.jobs + ji;
+    int32_t *res = B.res + (size_t)ji * PC_RES_INTS;
+    const uint8_t *a = B.arena + job->a_off;
+    const uint8_t *b = ((job->flags & PC_B_IN_GENOME) ? B.genome : B.arena) + job->b_off;
+    const int la = (int)job->a_len, lb = (int)job->b_len;
+    const uint8_t *pat = a, *txt = b;
+    int m = la, n = lb;
+    if (m > n) { pat = b; txt = a; m = lb; n = la; }                 // the distance is symmetric; the shorter string goes along the bits
+    bool slow = m > 64 * MAXW;
+    if (OP == PC_OP_EDIT) {
+      if (!slow) {
+        const uint32_t d = my_edit_distance<MAXW>(pat, m, txt, n, peq + threadIdx.x, MY_TPB);
+        if (d == MY_UNSUPPORTED) slow = true;
+        else { res[0] = PC_OK; res[1] = (int32_t)d; }
+      }
+    } else {
+      // K_band_edit_distance(seq1, seq2, k, &edit): the order of the reference's tests
+      const uint32_t k = (uint32_t)job->p0;
+      if (la != lb && k == 0) { res[0] = PC_OK; res[1] = 0; res[2] = 1; }                                     // not equal, no error allowed
+      else if (la != lb && (uint32_t)(n - m) > k) { res[0] = PC_OK; res[1] = 0; res[2] = n - m; }               // length gap alone is too much
+      else if (!slow) {
+        const uint32_t d = my_edit_distance<MAXW>(pat, m, txt, n, peq + threadIdx.x, MY_TPB);
+        if (d == MY_UNSUPPORTED) slow = true;
+        else if (la == lb && d == 0) { res[0] = PC_OK; res[1] = 1; res[2] = 0; }                               // equal strings
+        else if (k == 0) { res[0] = PC_OK; res[1] = 0; res[2] = 1; }
+        else if (2ull * k + 1ull >= (unsigned long long)n || d <= k) { res[0] = PC_OK; res[1] = d <= k; res[2] = (int32_t)d; }   // full matrix, or inside the band: exact
+        else slow = true;                                                                                      // band-restricted value wanted
+      }
+    }
+    if (slow) slow_list[atomicAdd(slow_count, 1u)] = ji;
+  }
+}
+
+template <int OP, int MAXW>
+void launch_myers(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count) {
+  int per_sm = 8;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_myers<OP, MAXW>, MY_TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int needed = (B.n + MY_TPB - 1) / MY_TPB;
+  const int grid = needed < sm_count * per_sm ? needed : sm_count * per_sm;
+  k_myers<OP, MAXW><<<grid < 1 ? 1 : grid, MY_TPB, 0, s>>>(B, slow_list, slow_count);
+  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+}
+
+}  // namespace
+
+// op = PC_OP_EDIT or PC_OP_KBAND.  max_short = upper bound on min(a_len, b_len) over the jobs (picks the one-word
+// variant).  slow_list (B.n entries) / slow_count (zeroed here) receive the job indices left for the generic kernel.
+void pc_launch_myers(int op, const PcDevBatch &B, int max_short, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count) {
+  cudaMemsetAsync(slow_count, 0, sizeof(uint32_t), s);
+  if (op == PC_OP_EDIT) {
+    if (max_short <= 64) launch_myers<PC_OP_EDIT, 1>(B, slow_list, slow_count, s, sm_count);
+    else launch_myers<PC_OP_EDIT, MY_MAXW>(B, slow_list, slow_count, s, sm_count);
+  } else {
+    if (max_short <= 64) launch_myers<PC_OP_KBAND, 1>(B, slow_list, slow_count, s, sm_count);
+    else launch_myers<PC_OP_KBAND, MY_MAXW>(B, slow_list, slow_count, s, sm_count);
+  }
+}

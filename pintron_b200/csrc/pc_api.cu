@@ -314,14 +314,17 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
     else for (size_t q = 0; q < nsel; ++q) out[bins[key[q]]++] = (uint32_t)q;
   }
   PROF(3, tp);
-  if (st->idx.reserve(nsel * 4 + 4)) return PC_E_NOMEM;
+  /* [job order | list of the jobs the bit-parallel kernel leaves to the wavefront kernel | one counter per segment] */
+  const size_t idx_words = (nsel + 63) & ~(size_t)63;
+  if (st->idx.reserve((2 * idx_words + NSEG) * 4 + 256)) return PC_E_NOMEM;
+  uint32_t *d_slow = (uint32_t *)st->idx.p + idx_words, *d_slow_count = (uint32_t *)st->idx.p + 2 * idx_words;
   CU(cudaMemcpyAsync(st->idx.p, order.p, nsel * 4, cudaMemcpyHostToDevice, st->s));
   CU(cudaMemsetAsync(st->d_pool_need, 0, 8, st->s));
   PcDevBatch B;
   B.arena = d_arena; B.genome = c->d_genome; B.genome_len = c->genome_len;
   B.jobs = d_jobs; B.res = d_res; B.var_out = d_var;
   B.pool = (uint8_t *)st->pool.p; B.pool_cap = st->pool.cap; B.pool_need = st->d_pool_need;
-  B.slots = 1; B.max_warps = st->max_warps;
+  B.slots = 1; B.max_warps = st->max_warps; B.n_dev = nullptr;
   B.ix_keys = c->ix_keys; B.ix_pos = c->ix_pos; B.ix_bstart = c->ix_bstart; B.ix_shift = c->ix_shift; B.ix_n = c->ix_n; B.ix_word = c->ix_word; B.depth_rate = c->depth_rate;
   size_t i = 0;
   for (int sg = 0; sg < NSEG; ++sg) {
@@ -358,6 +361,12 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
       pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, d_prefix, (uint32_t)tot, max_l2, st->s);
     } else if (op == PC_OP_GAP && cls < 3) {
       pc_launch_gap_pairs(cls, B, (int)max_l1, st->s, c->sm_count);
+    } else if (op == PC_OP_EDIT || op == PC_OP_KBAND) {
+      // one job per thread, bit-parallel; what it cannot answer bit-exactly is listed for the wavefront kernel
+      pc_launch_myers((int)op, B, (int)std::min<long long>(max_l1, max_l2), d_slow + i, d_slow_count + sg, st->s, c->sm_count);
+      PcDevBatch S = B;
+      S.idx = d_slow + i; S.n_dev = d_slow_count + sg;
+      pc_launch_dp((int)op, S, st->s, c->sm_count);
     } else {
       pc_launch_dp((int)op, B, st->s, c->sm_count);
     }

@@ -15,6 +15,7 @@ struct PcDevBatch {
   const pc_job *jobs;
   const uint32_t *idx;        /* job indices of this op, heaviest first */
   int n;
+  const uint32_t *n_dev;      /* when set: the job count is read from device memory (list built by an earlier kernel) */
   int32_t *res;
   uint8_t *var_out;
   uint8_t *pool;              /* per-stream scratch pool: one equal slot per warp of the launch, reused job after job */
@@ -57,6 +58,7 @@ __device__ __forceinline__ uint8_t *pc_pool_alloc(const PcDevBatch &B, WarpPool 
 __device__ __forceinline__ bool pc_is_n(uint8_t c) { return c == 'n' || c == 'N'; }
 
 void pc_launch_dp(int op, const PcDevBatch &B, cudaStream_t s, int sm_count);
+void pc_launch_myers(int op, const PcDevBatch &B, int max_short, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count);
 void pc_launch_gap_pairs(int cls, const PcDevBatch &B, int max_m, cudaStream_t s, int sm_count);
 void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count);
 int pc_lcs_blocks(long long l1, int l2);

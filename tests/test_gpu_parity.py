@@ -266,3 +266,47 @@ def test_lcs_bit_parallel_vs_port(cu, port):
     for (s1, s2), rr in zip(cases, res):
         assert rr[0] == 0
         assert tuple(rr[1:4]) == port.lcs(s1, s2), (len(s1), len(s2), s1[:80], s2)
+
+
+def test_bit_parallel_edit_and_kband_vs_port(cu, port):
+    """k_myers (one job per thread) and its hand-over list to the wavefront kernel: short and multi-word strings,
+    strings above 320 letters, lower-case / N / masked bytes, k = 0, length gaps above k, distances above k inside
+    and outside the full-matrix case, equal strings, empty strings — every (ok, edit) and distance equals the port's."""
+    import random
+    rnd = random.Random(777)
+    alphabets = [b"ACGT", b"ACGT", b"ACGTacgtNn", b"ACGTN*#", b"AC"]
+
+    def mutate(s, rate, al):
+        out = bytearray()
+        for ch in s:
+            x = rnd.random()
+            if x < rate * 0.5:
+                out.append(rnd.choice(al))
+            elif x < rate * 0.75:
+                out.append(rnd.choice(al)); out.append(ch)
+            elif x < rate:
+                continue
+            else:
+                out.append(ch)
+        return bytes(out)
+
+    b, chk = Batch(), []
+    for it in range(6000):
+        al = alphabets[it % len(alphabets)]
+        ln = rnd.choice([0, 1, 5, 13, 19, 40, 63, 64, 65, 100, 128, 129, 200, 317, 320, 321, 400])
+        a = bytes(rnd.choice(al) for _ in range(ln))
+        c = a if it % 11 == 0 else mutate(a, rnd.choice([0.0, 0.02, 0.05, 0.3]), al)
+        if it % 13 == 0:
+            c = c + bytes(rnd.choice(al) for _ in range(rnd.randint(1, 30)))
+        if it % 2:
+            a, c = c, a
+        b.add(PC_OP.EDIT, a, c); chk.append(("edit", a, c))
+        k = rnd.choice([0, 1, 2, 3, 5, 9, 14, 40])
+        b.add(PC_OP.KBAND, a, c, p0=k); chk.append(("kband", a, c, k))
+    res, _ = cu.run(b)
+    for r, c in zip(res, chk):
+        assert r[0] == 0, (c, list(r))
+        if c[0] == "edit":
+            assert r[1] == port.edit(c[1], c[2]), c
+        else:
+            assert (bool(r[1]), int(r[2])) == port.kband(c[1], c[2], c[3]), c
