@@ -150,6 +150,16 @@ class Cuda:
         self._check(self.L.pc_stream_sync(self.st), "pc_stream_sync")
         return res, var
 
+    def run_arrays(self, arena, jobs, var_bytes):
+        """Same as run() for an arena / job array pair that was edited by hand (tests of the argument checks)."""
+        n = len(jobs)
+        res = np.zeros((n, PC_RES_INTS), dtype=np.int32)
+        var = np.zeros(max(var_bytes, 1), dtype=np.uint8)
+        self._check(self.L.pc_submit(self.st, arena.ctypes.data, len(arena), jobs.ctypes.data, n, res.ctypes.data,
+                                     var.ctypes.data, var_bytes), "pc_submit")
+        self._check(self.L.pc_stream_sync(self.st), "pc_stream_sync")
+        return res, var
+
     def launch_count(self):
         return int(self.L.pc_launch_count())
 

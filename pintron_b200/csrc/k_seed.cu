@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(128) k_seed(PcDevBatch B) {
 // diagonal i1-i2; one thread walks one diagonal, a block stages its slice of s1 in shared memory.  The
 // reference keeps the FIRST strictly longer run in (i1 outer, i2 inner) order = max len, then min i1, then
 // min i2: packed so that one 64-bit atomicMax per block picks it.
-#define LCS_TPB 256
-#define LCS_MAX_S2 4096
+#define LCS_TPB PC_LCS_TPB
+#define LCS_MAX_S2 PC_LCS_MAX_S2
 
 __device__ __forceinline__ unsigned long long lcs_key(int len, uint32_t i1, int i2) {
   return ((unsigned long long)len << 48) | ((unsigned long long)(0xffffffffu - i1) << 16) |

@@ -10,6 +10,7 @@ unsigned long long g_pc_launches = 0;
 #include <chrono>
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const bool g_prof = getenv("PC_PROFILE") != nullptr;
+#define PC_DEVICE_ORDER_MIN ((size_t)1 << 16)      /* batches from this size up are ordered on the device (k_order.cu) */
 /* PC_CAPTURE=<file>: every batch handed to pc_submit is appended to <file> (bench.py replays the job stream of a real
  * est-fact run as its device-resident workload).  Record = u32 njobs, u64 arena_bytes, jobs, arena. */
 #include <mutex>
@@ -110,7 +111,7 @@ struct pc_stream {
   unsigned long long *d_pool_need = nullptr, *h_pool_need = nullptr;   /* device counter + pinned mirror */
   int max_warps = 0;
   std::vector<uint32_t> h_bins;
-  PinBuf pin_idx, pin_lcs;
+  PinBuf pin_idx, pin_lcs, pin_seg;
   std::vector<uint16_t> h_key;
   std::vector<int32_t> h_status;
   Pending pend;
@@ -278,15 +279,39 @@ static inline int job_cost_class(const pc_job &j) {
 // key and every (op, class) segment its size and longest strings; a counting sort then lays the job indices out
 // segment by segment, heaviest first, for the persistent kernels.
 static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *sel, size_t nsel, const uint8_t *d_arena,
-                           const pc_job *d_jobs, int32_t *d_res, uint8_t *d_var) {
+                           const pc_job *d_jobs, int32_t *d_res, uint8_t *d_var, size_t arena_bytes, size_t var_bytes) {
   pc_ctx *c = st->ctx;
   double tp = g_prof ? now_s() : 0;
-  constexpr int NSEG = PC_OP_COUNT * 4, NB = NSEG * 64;
-  struct Seg { uint32_t n, max_a, max_b; } seg[NSEG];
+  constexpr int NSEG = PC_ORDER_SEGS, NB = PC_ORDER_BINS;
+  struct Seg { uint32_t n, max_a, max_b; unsigned long long lcs_blocks; } seg[NSEG];
   memset(seg, 0, sizeof seg);
+  /* device buffer: [job order | list of the jobs the bit-parallel kernel leaves to the wavefront kernel | one counter per
+   * segment | (device ordering only) keys, histogram work area, segment statistics] */
+  const size_t idx_words = (nsel + 63) & ~(size_t)63;
+  const bool on_device = sel == nullptr && nsel >= PC_DEVICE_ORDER_MIN;
+  const size_t extra_words = on_device ? idx_words / 2 + 3 * NB + 64 + NSEG * (sizeof(PcSegStat) / 4) : 0;
+  if (st->idx.reserve((2 * idx_words + 64 + extra_words) * 4 + 256)) return PC_E_NOMEM;
+  uint32_t *d_order = (uint32_t *)st->idx.p, *d_slow = d_order + idx_words, *d_slow_count = d_order + 2 * idx_words;
   PinBuf &order = st->pin_idx;
-  if (order.reserve(nsel + 1)) return PC_E_NOMEM;
-  {
+  if (on_device) {
+    // millions of jobs already in HBM: key, histogram, scan and scatter run there (k_order.cu); the host only reads
+    // the 40 segment records back.  The job check of pc_submit is part of the key kernel.
+    uint16_t *d_keys = (uint16_t *)(d_slow_count + 64);
+    uint32_t *d_work = (uint32_t *)(d_keys) + idx_words / 2;
+    PcSegStat *d_seg = (PcSegStat *)(((uintptr_t)(d_work + 3 * NB + 2) + 15u) & ~(uintptr_t)15u);
+    if (st->pin_seg.reserve(NSEG * (sizeof(PcSegStat) / 4) + 4)) return PC_E_NOMEM;
+    pc_order_jobs(d_jobs, (int)nsel, arena_bytes, c->genome_len, var_bytes, PC_LCS_TPB, PC_LCS_MAX_S2, d_keys, d_work, d_seg, d_order,
+                  st->s, c->sm_count);
+    PcSegStat *h_seg = (PcSegStat *)st->pin_seg.p;
+    uint32_t *h_invalid = st->pin_seg.p + NSEG * (sizeof(PcSegStat) / 4);
+    CU(cudaMemcpyAsync(h_seg, d_seg, sizeof(PcSegStat) * NSEG, cudaMemcpyDeviceToHost, st->s));
+    CU(cudaMemcpyAsync(h_invalid, d_work + 3 * NB + 1, 4, cudaMemcpyDeviceToHost, st->s));
+    CU(cudaStreamSynchronize(st->s));
+    if (*h_invalid) return fail(PC_E_ARG, "%s", "pc_submit: a job references bytes outside its buffers (or has an unknown op)");
+    for (int sg = 0; sg < NSEG; ++sg) { seg[sg].n = h_seg[sg].n; seg[sg].max_a = h_seg[sg].max_a; seg[sg].max_b = h_seg[sg].max_b; seg[sg].lcs_blocks = h_seg[sg].lcs_blocks; }
+    PROF(3, tp);
+  } else {
+    if (order.reserve(nsel + 1)) return PC_E_NOMEM;
     std::vector<uint32_t> &bins = st->h_bins;
     bins.assign(NB + 1, 0);
     std::vector<uint16_t> &key = st->h_key;
@@ -303,8 +328,6 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
       const int sg = (int)j.op * 4 + cls;
       Seg &S = seg[sg];
       ++S.n; S.max_a = std::max(S.max_a, j.a_len); S.max_b = std::max(S.max_b, j.b_len);
-      if (g_prof) { ++g_op_jobs[j.op]; g_op_suma[j.op] += j.a_len; g_op_sumb[j.op] += j.b_len; g_op_cells[j.op] += (unsigned long long)j.a_len * j.b_len;
-                    if (j.a_len > g_op_maxa[j.op]) g_op_maxa[j.op] = j.a_len; if (j.b_len > g_op_maxb[j.op]) g_op_maxb[j.op] = j.b_len; }
       key[q] = (uint16_t)(sg * 64 + (63 - lg));
       ++bins[key[q] + 1];
     }
@@ -312,13 +335,16 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
     uint32_t *out = order.p;
     if (sel) for (size_t q = 0; q < nsel; ++q) out[bins[key[q]]++] = sel[q];
     else for (size_t q = 0; q < nsel; ++q) out[bins[key[q]]++] = (uint32_t)q;
+    PROF(3, tp);
+    CU(cudaMemcpyAsync(d_order, order.p, nsel * 4, cudaMemcpyHostToDevice, st->s));
   }
-  PROF(3, tp);
-  /* [job order | list of the jobs the bit-parallel kernel leaves to the wavefront kernel | one counter per segment] */
-  const size_t idx_words = (nsel + 63) & ~(size_t)63;
-  if (st->idx.reserve((2 * idx_words + NSEG) * 4 + 256)) return PC_E_NOMEM;
-  uint32_t *d_slow = (uint32_t *)st->idx.p + idx_words, *d_slow_count = (uint32_t *)st->idx.p + 2 * idx_words;
-  CU(cudaMemcpyAsync(st->idx.p, order.p, nsel * 4, cudaMemcpyHostToDevice, st->s));
+  if (g_prof)
+    for (size_t q = 0; q < nsel && !on_device; ++q) {
+      const pc_job &j = h_jobs[sel ? sel[q] : q];
+      ++g_op_jobs[j.op]; g_op_suma[j.op] += j.a_len; g_op_sumb[j.op] += j.b_len; g_op_cells[j.op] += (unsigned long long)j.a_len * j.b_len;
+      if (j.a_len > g_op_maxa[j.op]) g_op_maxa[j.op] = j.a_len;
+      if (j.b_len > g_op_maxb[j.op]) g_op_maxb[j.op] = j.b_len;
+    }
   CU(cudaMemsetAsync(st->d_pool_need, 0, 8, st->s));
   PcDevBatch B;
   B.arena = d_arena; B.genome = c->d_genome; B.genome_len = c->genome_len;
@@ -334,7 +360,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
     const size_t j = i + seg[sg].n;
     const long long max_l1 = seg[sg].max_b;
     const int max_l2 = (int)seg[sg].max_a;
-    B.idx = (const uint32_t *)st->idx.p + i;
+    B.idx = d_order + i;
     B.n = (int)(j - i);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (st->timers || g_prof) { e0 = get_event(st); e1 = get_event(st); cudaEventRecord(e0, st->s); }
@@ -346,18 +372,23 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
       // [best slots | block prefix] in one device buffer; the prefix comes from the host copy of the jobs
       const size_t best_b = (8ull * B.n + 255u) & ~(size_t)255u;
       if (st->lcs_best.reserve(best_b + 4ull * (B.n + 1))) return PC_E_NOMEM;
-      PinBuf &pl = st->pin_lcs;
-      if (pl.reserve((size_t)B.n + 1)) return PC_E_NOMEM;
-      uint64_t tot = 0;
-      for (size_t q = i; q < j; ++q) {
-        pl.p[q - i] = (uint32_t)tot;
-        const pc_job &jb = h_jobs[order.p[q]];
-        tot += (uint64_t)pc_lcs_blocks(jb.b_len, (int)jb.a_len);
-      }
-      pl.p[B.n] = (uint32_t)tot;
-      if (tot >= 0x7fffffffull) return fail(PC_E_RANGE, "%s", "LCS batch too large for one launch");
       uint32_t *d_prefix = (uint32_t *)((uint8_t *)st->lcs_best.p + best_b);
-      CU(cudaMemcpyAsync(d_prefix, pl.p, 4ull * (B.n + 1), cudaMemcpyHostToDevice, st->s));
+      uint64_t tot = 0;
+      if (on_device) {
+        tot = seg[sg].lcs_blocks;
+        pc_lcs_prefix(d_jobs, d_order + i, B.n, PC_LCS_TPB, PC_LCS_MAX_S2, d_prefix, st->s);
+      } else {
+        PinBuf &pl = st->pin_lcs;
+        if (pl.reserve((size_t)B.n + 1)) return PC_E_NOMEM;
+        for (size_t q = i; q < j; ++q) {
+          pl.p[q - i] = (uint32_t)tot;
+          const pc_job &jb = h_jobs[order.p[q]];
+          tot += (uint64_t)pc_lcs_blocks(jb.b_len, (int)jb.a_len);
+        }
+        pl.p[B.n] = (uint32_t)tot;
+        CU(cudaMemcpyAsync(d_prefix, pl.p, 4ull * (B.n + 1), cudaMemcpyHostToDevice, st->s));
+      }
+      if (tot >= 0x7fffffffull) return fail(PC_E_RANGE, "%s", "LCS batch too large for one launch");
       pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, d_prefix, (uint32_t)tot, max_l2, st->s);
     } else if (op == PC_OP_GAP && cls < 3) {
       pc_launch_gap_pairs(cls, B, (int)max_l1, st->s, c->sm_count);
@@ -407,7 +438,7 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
   if (njobs == 0) return 0;
   double tp = g_prof ? now_s() : 0;
   CU(cudaSetDevice(st->ctx->device));
-  int rc = check_jobs(st, jobs, njobs, arena_bytes, var_out_bytes);
+  int rc = (size_t)njobs >= PC_DEVICE_ORDER_MIN ? 0 : check_jobs(st, jobs, njobs, arena_bytes, var_out_bytes);   /* large batches: checked by the key kernel */
   if (rc) return rc;
   if (g_capture) {
     std::lock_guard<std::mutex> lk(g_capture_mu);
@@ -426,7 +457,7 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
   CU(cudaMemcpyAsync(st->jobs.p, jobs, sizeof(pc_job) * (size_t)njobs, cudaMemcpyHostToDevice, st->s));
   PROF(2, tp);
   rc = launch_selected(st, jobs, nullptr, (size_t)njobs, (const uint8_t *)st->arena.p, (const pc_job *)st->jobs.p, (int32_t *)st->res.p,
-                       (uint8_t *)st->var.p);
+                       (uint8_t *)st->var.p, arena_bytes, var_out_bytes);
   if (rc) return rc;
   Pending &P = st->pend;
   P.active = true; P.device_mode = false; P.jobs = jobs; P.njobs = njobs; P.res = res; P.var_out = var_out;
@@ -445,9 +476,9 @@ extern "C" int pc_submit_device(pc_stream *st, const uint8_t *d_arena, size_t ar
   if (st->pend.active) return fail(PC_E_ARG, "%s", "pc_submit_device: previous batch not synced");
   if (njobs == 0) return 0;
   CU(cudaSetDevice(st->ctx->device));
-  int rc = check_jobs(st, h_jobs, njobs, arena_bytes, var_out_bytes);
+  int rc = (size_t)njobs >= PC_DEVICE_ORDER_MIN ? 0 : check_jobs(st, h_jobs, njobs, arena_bytes, var_out_bytes);
   if (rc) return rc;
-  rc = launch_selected(st, h_jobs, nullptr, (size_t)njobs, d_arena, d_jobs, d_res, d_var_out);
+  rc = launch_selected(st, h_jobs, nullptr, (size_t)njobs, d_arena, d_jobs, d_res, d_var_out, arena_bytes, var_out_bytes);
   if (rc) return rc;
   Pending &P = st->pend;
   P.active = true; P.device_mode = true; P.jobs = h_jobs; P.njobs = njobs; P.res = nullptr; P.var_out = nullptr;
@@ -491,7 +522,7 @@ extern "C" int pc_stream_sync(pc_stream *st) {
       if (rc) { P.active = false; st->max_warps = 0; return rc; }
     }
     st->max_warps = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(st->pool.cap / need, 1u << 20));
-    int rc = launch_selected(st, P.jobs, redo.data(), redo.size(), P.d_arena, P.d_jobs, P.d_res, P.d_var);
+    int rc = launch_selected(st, P.jobs, redo.data(), redo.size(), P.d_arena, P.d_jobs, P.d_res, P.d_var, 0, P.var_out_bytes);
     st->max_warps = 0;
     if (rc) { P.active = false; return rc; }
     if (!P.device_mode) {

@@ -33,6 +33,13 @@ struct PcDevBatch {
   double depth_rate;
 };
 
+/* device-side job ordering (k_order.cu) */
+#define PC_ORDER_SEGS (PC_OP_COUNT * 4)
+#define PC_ORDER_BINS (PC_ORDER_SEGS * 64)
+#define PC_LCS_TPB 256
+#define PC_LCS_MAX_S2 4096
+struct PcSegStat { uint32_t n, max_a, max_b, pad; unsigned long long lcs_blocks; };
+
 struct WarpPool { uint8_t *base; unsigned long long size, used; };
 
 __device__ __forceinline__ WarpPool pc_warp_pool(const PcDevBatch &B, int slot) {
@@ -59,6 +66,9 @@ __device__ __forceinline__ bool pc_is_n(uint8_t c) { return c == 'n' || c == 'N'
 
 void pc_launch_dp(int op, const PcDevBatch &B, cudaStream_t s, int sm_count);
 void pc_launch_myers(int op, const PcDevBatch &B, int max_short, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count);
+void pc_order_jobs(const pc_job *d_jobs, int n, size_t arena_bytes, size_t genome_len, size_t var_bytes, int lcs_tpb, int lcs_max_s2,
+                   uint16_t *d_keys, uint32_t *d_work, PcSegStat *d_seg, uint32_t *d_order, cudaStream_t s, int sm_count);
+void pc_lcs_prefix(const pc_job *d_jobs, const uint32_t *d_order, int n, int lcs_tpb, int lcs_max_s2, uint32_t *d_prefix, cudaStream_t s);
 void pc_launch_gap_pairs(int cls, const PcDevBatch &B, int max_m, cudaStream_t s, int sm_count);
 void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count);
 int pc_lcs_blocks(long long l1, int l2);

@@ -310,3 +310,66 @@ def test_bit_parallel_edit_and_kband_vs_port(cu, port):
             assert r[1] == port.edit(c[1], c[2]), c
         else:
             assert (bool(r[1]), int(r[2])) == port.kband(c[1], c[2], c[3]), c
+
+
+def test_large_batch_is_ordered_on_the_device(cu, port):
+    """>= 65 536 jobs: keys, histogram, scan, scatter and the LCS block prefix run on the GPU (k_order.cu) instead of the
+    submitting thread.  Every op, 300 distinct cases cycled to 70 000 jobs; each result equals the port's; a job that
+    points outside the arena makes pc_submit fail like the host-side check does."""
+    g = Gen(99)
+    genome = g.genome(5000)
+    cu.genome_upload(genome, 15, 0.2)
+    cases = []
+    for it in range(300):
+        a, c = g.pair(120, it)
+        kind = it % 7
+        if kind == 0:
+            cases.append((PC_OP.EDIT, a, c, {}, ("edit", port.edit(a, c))))
+        elif kind == 1:
+            k = g.rnd.randint(0, 9)
+            cases.append((PC_OP.KBAND, a, c, {"p0": k}, ("kband", port.kband(a, c, k))))
+        elif kind == 2:
+            est, gen = g.gap_case()
+            cases.append((PC_OP.GAP, est, gen, {}, ("gap", port.gap(est, gen))))
+        elif kind == 3:
+            p, t, me = g.borders_case()
+            cases.append((PC_OP.BORDERS, p, t, {"p0": me, "p1": 0, "p2": len(p)}, ("borders", port.borders(p, t, me, 0, len(p)))))
+        elif kind == 4:
+            cases.append((PC_OP.LCS, c, a, {}, ("lcs", port.lcs(a, c))))
+        elif kind == 5:
+            cases.append((PC_OP.ALIGN, a, c, {}, ("align", port.align(a, c))))
+        else:
+            cases.append((PC_OP.AFFIX, a, c, {}, ("affix", port.affix(a, c))))
+    b = Batch()
+    N = 70000
+    for q in range(N):
+        op, a, c, kw, _ = cases[q % len(cases)]
+        b.add(op, a, c, **kw)
+    res, var = cu.run(b)
+    _, jobs = b.arrays()
+    for q in range(N):
+        r, j = res[q], jobs[q]
+        kind, want = cases[q % len(cases)][4]
+        assert r[0] == 0, (q, kind, list(r))
+        if kind == "edit":
+            assert r[1] == want
+        elif kind == "kband":
+            assert (bool(r[1]), int(r[2])) == want
+        elif kind == "gap":
+            assert var[j["out_off"]:j["out_off"] + r[1]].tobytes() == want[0] and list(r[2:7]) == want[1]
+        elif kind == "borders":
+            assert bool(r[1]) == want[0] and list(r[2:6]) == want[1]
+        elif kind == "lcs":
+            assert tuple(r[1:4]) == want
+        elif kind == "align":
+            assert r[1] == want[0] and var[j["out_off"]:j["out_off"] + r[2]].tobytes() == want[1]
+        else:
+            assert bool(r[1]) == want[0] and (not want[0] or (r[2], r[3]) == (want[1], want[2]))
+    # an out-of-range job in a large batch is refused
+    bad = Batch()
+    for q in range(N):
+        bad.add(PC_OP.EDIT, b"ACGT", b"AGT")
+    arena, jb = bad.arrays()
+    jb["a_off"][N // 2] = len(arena) + 100
+    with pytest.raises(RuntimeError):
+        cu.run_arrays(arena, jb, bad.var_bytes)
