@@ -282,6 +282,127 @@ __device__ void op_borders(const PcDevBatch &B, WarpPool &wp, int w, uint32_t *s
   }
 }
 
+// ---- general_refine_borders, register-resident and 16x2-packed --------------------------------------------------
+// The two matrices of one job (p against the head of t, reversed p against the reversed tail of t) have the same
+// shape, so they travel as the low and the high 16-bit half of one register and share every instruction (the layout
+// of k_gap.cu: a group of LANES lanes owns a job, lane k holds rows 8k+1 .. 8k+8 in registers and sweeps the columns one
+// step behind lane k-1, boundary values by shuffle).  The per-row (minimum, first argmin) pair is followed in registers
+// with the DPX min whose predicates say which operand won.  The split is then chosen by the whole group: candidate i
+// goes to lane i mod LANES, and the reference's scan order (cost, then Burset frequency, then the smaller i;
+// refine.c:161-178) is the lexicographic minimum of (cost, -freq, i).
+template <int LANES>
+__global__ void __launch_bounds__(128) k_borders_packed(PcDevBatch B, int tcap) {
+  extern __shared__ uint32_t sh_b[];
+  constexpr int G = 32 / LANES, RMAX = 8 * LANES;
+  constexpr uint32_t ONE2 = 0x00010001u;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int k = lane % LANES, grp = lane / LANES;
+  const int per_group = (tcap + 1) + 2 * (RMAX + 1);
+  uint32_t *codes = sh_b + (size_t)(wib * G + grp) * per_group, *mnS = codes + tcap + 1, *posS = mnS + RMAX + 1;
+  const int warp_id = blockIdx.x * 4 + wib, ngroups = gridDim.x * 4 * G;
+  for (int q0 = warp_id * G; q0 < B.n; q0 += ngroups) {            // warp-uniform trip count
+    const int q = q0 + grp;
+    bool live = q < B.n;
+    JobView J;
+    int len_p = 0, len_t = 0, t_win = 0, min_cut = 0, max_cut = 0;
+    uint32_t max_errs = 0;
+    if (live) {
+      J = view(B, q);
+      len_p = J.la; len_t = J.lb;
+      max_errs = (uint32_t)J.job->p0; min_cut = J.job->p1; max_cut = J.job->p2;
+      t_win = (int)min((unsigned long long)len_p + max_errs, (unsigned long long)len_t);
+      if (min_cut < 0 || min_cut > max_cut || max_cut > len_p) { if (k == 0) J.res[0] = PC_E_ARG; live = false; }
+    }
+    if (live)
+      for (int j = k + 1; j <= t_win; j += LANES) codes[j] = (uint32_t)J.b[j - 1] | ((uint32_t)J.b[len_t - j] << 16);
+    uint32_t e[8], V[8], mn[8], pos[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = k * 8 + r + 1;
+      e[r] = (live && i <= len_p) ? ((uint32_t)J.a[i - 1] | ((uint32_t)J.a[len_p - i] << 16)) : 0u;
+      V[r] = (uint32_t)i * ONE2;                                 // column 0: D[i][0] = i, which is also the row minimum so far
+      mn[r] = V[r]; pos[r] = 0u;
+    }
+    int steps = live ? t_win + LANES - 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+    __syncwarp();
+    uint32_t inV = (uint32_t)(8 * k) * ONE2, gcur = 0;           // (row 8k, column 0)
+    for (int s = 1; s <= steps; ++s) {
+      const int j = s - k;
+      uint32_t dprev = inV;                                      // (row 8k, column j-1)
+      inV = __shfl_up_sync(0xffffffffu, V[7], 1, LANES);         // (row 8k, column j): lane k-1 finished it one step ago
+      gcur = __shfl_up_sync(0xffffffffu, gcur, 1, LANES);
+      if (k == 0) { dprev = (uint32_t)(j - 1) * ONE2; inV = (uint32_t)j * ONE2; gcur = codes[min(max(s, 1), max(t_win, 1))]; }   // row 0: D[0][j] = j
+      if (live && j >= 1 && j <= t_win) {
+        const uint32_t j2 = (uint32_t)j * ONE2;
+        uint32_t diag = dprev, up = inV;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const uint32_t c = __vminu2(e[r] ^ gcur, ONE2);        // 1 where the bytes differ, per half
+          uint32_t v = __vminu2(diag + c, up + ONE2);
+          v = __vminu2(v, V[r] + ONE2);
+          diag = V[r]; V[r] = v; up = v;
+          bool ph, pl;                                           // "the old minimum is still <= v": a later equal value never replaces it
+          const uint32_t m2 = __vibmin_u16x2(mn[r], v, &ph, &pl);
+          const uint32_t lo = pl ? pos[r] : j2, hi = ph ? pos[r] : j2;
+          pos[r] = __byte_perm(lo, hi, 0x7610);
+          mn[r] = m2;
+        }
+      }
+    }
+    __syncwarp();
+    if (live) {
+      if (k == 0) { mnS[0] = 0u; posS[0] = 0u; }                 // row 0: minimum 0 at column 0 on both sides
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int i = k * 8 + r + 1;
+        if (i <= len_p) { mnS[i] = mn[r]; posS[i] = pos[r]; }
+      }
+    }
+    __syncwarp();
+    unsigned long long best_key = ~0ull;
+    if (live) {
+      const int nul_at = (J.job->flags & PC_B_NUL_AFTER) ? len_t : -1;
+      uint32_t bc = 0xffffffffu;
+      for (int i = min_cut + k; i <= max_cut; i += LANES) {
+        const uint32_t c = (mnS[i] & 0xffffu) + (mnS[len_p - i] >> 16);
+        if (bc < c) continue;                                    // a worse split never wins: skip its Burset lookup
+        const int freq = burset_freq(J.b, (int)(posS[i] & 0xffffu), len_t - (int)(posS[len_p - i] >> 16), nul_at);
+        const unsigned long long key = ((unsigned long long)c << 32) | ((unsigned long long)(0xffff - freq) << 16) | (unsigned long long)i;
+        if (key < best_key) { best_key = key; bc = c; }
+      }
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best_key, o, LANES);
+      best_key = other < best_key ? other : best_key;
+    }
+    if (live && k == 0) {
+      const int i = (int)(best_key & 0xffffu);
+      const uint32_t best = (uint32_t)(best_key >> 32);
+      J.res[0] = PC_OK; J.res[1] = best <= max_errs; J.res[2] = i; J.res[3] = (int32_t)(posS[i] & 0xffffu);
+      J.res[4] = len_t - (int32_t)(posS[len_p - i] >> 16); J.res[5] = (int32_t)best;
+    }
+    __syncwarp();
+  }
+}
+
+template <int LANES>
+void launch_borders_packed(const PcDevBatch &B, int tcap, cudaStream_t s, int sm_count) {
+  constexpr int G = 32 / LANES;
+  const size_t sh = (size_t)4 * G * ((tcap + 1) + 2 * (8 * LANES + 1)) * sizeof(uint32_t);
+  static bool attr_done = false;
+  if (!attr_done) { cudaFuncSetAttribute(k_borders_packed<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_done = true; }
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_borders_packed<LANES>, 128, sh) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int needed = (B.n + 4 * G - 1) / (4 * G);
+  int grid = needed < sm_count * per_sm ? needed : sm_count * per_sm;
+  if (grid < 1) grid = 1;
+  k_borders_packed<LANES><<<grid, 128, sh, s>>>(B, tcap);
+  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+}
+
 // ---- DP E: find_longest_affix (src/factorization-refinement.c:1134-1172) ----------------------------------
 // Wanted: among the cells (e, g) with equal end characters and weight 2*D/(e+g) <= 0.17, the minimal weight, LAST in
 // row-major order on ties.  A qualifying cell has D <= 0.085*(e+g) <= wd := floor(0.085*(el+gl)) + 1, and every cell
@@ -480,6 +601,13 @@ void launch_wpj(const PcDevBatch &B, cudaStream_t s, int sm_count) {
 }
 
 }  // namespace
+
+// cls 0/1/2: len_p <= 64 / 128 / 256 with 1 <= t_win <= PC_BORDERS_FAST_MAX_T (the generic wavefront kernel takes the rest)
+void pc_launch_borders_packed(int cls, const PcDevBatch &B, int tcap, cudaStream_t s, int sm_count) {
+  if (cls == 0) launch_borders_packed<8>(B, tcap, s, sm_count);
+  else if (cls == 1) launch_borders_packed<16>(B, tcap, s, sm_count);
+  else launch_borders_packed<32>(B, tcap, s, sm_count);
+}
 
 void pc_launch_dp(int op, const PcDevBatch &B, cudaStream_t s, int sm_count) {
   switch (op) {

@@ -14,19 +14,6 @@
 
 namespace {
 
-__device__ __forceinline__ int gap_class_dev(const pc_job &j) {
-  if (j.op != PC_OP_GAP) return 0;
-  if (j.a_len < 1 || j.b_len < 1 || j.b_len > 4096 || j.a_len > 256) return 3;
-  return j.a_len <= 64 ? 0 : (j.a_len <= 128 ? 1 : 2);
-}
-
-__device__ __forceinline__ int cost_class_dev(const pc_job &j) {
-  unsigned long long c;
-  if (j.op == PC_OP_LCS || j.op == PC_OP_SEED) c = (unsigned long long)j.a_len + j.b_len + 1ull;
-  else c = ((unsigned long long)j.a_len + 1ull) * ((unsigned long long)j.b_len + 1ull) + 1ull;
-  return 63 - __clzll((long long)c);
-}
-
 __device__ __forceinline__ bool job_valid(const pc_job &j, size_t arena_bytes, size_t genome_len, size_t var_bytes) {
   if (j.op >= PC_OP_COUNT) return false;
   if ((size_t)j.a_off + j.a_len > arena_bytes) return false;
@@ -50,12 +37,8 @@ __global__ void __launch_bounds__(256) k_job_keys(const pc_job *jobs, int n, siz
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const pc_job j = jobs[i];
     if (!job_valid(j, arena_bytes, genome_len, var_bytes)) { keys[i] = 0xffffu; atomicAdd(invalid, 1u); continue; }
-    const int cls = gap_class_dev(j);
-    int lg;
-    if (j.op == PC_OP_GAP && cls < 3) {
-      const uint32_t m = j.b_len;
-      lg = m < 512 ? (int)(m >> 4) : 32 + (int)min(31u, (m - 512) >> 7);
-    } else lg = cost_class_dev(j);
+    const int cls = pc_job_class(j);
+    const int lg = pc_job_cost(j, cls);
     const int sg = (int)j.op * 4 + cls;
     const uint16_t key = (uint16_t)(sg * 64 + (63 - lg));
     keys[i] = key;

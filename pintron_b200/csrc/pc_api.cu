@@ -259,21 +259,6 @@ static cudaEvent_t get_event(pc_stream *st) {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 
-// GAP jobs that fit the packed register kernel (k_gap.cu): class by the number of EST rows; 3 = generic kernel.
-static int gap_class(const pc_job &j) {
-  if (j.op != PC_OP_GAP) return 0;
-  if (j.a_len < 1 || j.b_len < 1 || j.b_len > 4096 || j.a_len > 256) return 3;
-  return j.a_len <= 64 ? 0 : (j.a_len <= 128 ? 1 : 2);
-}
-
-// log2-ish cost class of a job, integers only (this runs once per job per batch on the submitting thread)
-static inline int job_cost_class(const pc_job &j) {
-  unsigned long long c;
-  if (j.op == PC_OP_LCS || j.op == PC_OP_SEED) c = (unsigned long long)j.a_len + j.b_len + 1ull;
-  else c = ((unsigned long long)j.a_len + 1ull) * ((unsigned long long)j.b_len + 1ull) + 1ull;
-  return 63 - __builtin_clzll(c);
-}
-
 // Launch the kernels for the jobs whose indices are in `sel` (nullptr = all njobs of the batch, which is already
 // resident on the device).  One sequential pass over the host copy of the jobs gives every job its (op, class, cost)
 // key and every (op, class) segment its size and longest strings; a counting sort then lays the job indices out
@@ -319,12 +304,8 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
     for (size_t q = 0; q < nsel; ++q) {
       const pc_job &j = h_jobs[sel ? sel[q] : q];
       if (j.op >= PC_OP_COUNT) return fail(PC_E_ARG, "%s", "pc_submit: unknown op");
-      const int cls = gap_class(j);
-      int lg;
-      if (j.op == PC_OP_GAP && cls < 3) {        // paired jobs run max(m) steps: order by m, finely
-        const uint32_t m = j.b_len;
-        lg = m < 512 ? (int)(m >> 4) : 32 + (int)std::min<uint32_t>(31, (m - 512) >> 7);
-      } else lg = job_cost_class(j);
+      const int cls = pc_job_class(j);
+      const int lg = pc_job_cost(j, cls);        // packed kernels run max(columns) steps per warp: ordered by that, finely
       const int sg = (int)j.op * 4 + cls;
       Seg &S = seg[sg];
       ++S.n; S.max_a = std::max(S.max_a, j.a_len); S.max_b = std::max(S.max_b, j.b_len);
@@ -392,6 +373,8 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
       pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, d_prefix, (uint32_t)tot, max_l2, st->s);
     } else if (op == PC_OP_GAP && cls < 3) {
       pc_launch_gap_pairs(cls, B, (int)max_l1, st->s, c->sm_count);
+    } else if (op == PC_OP_BORDERS && cls < 3) {
+      pc_launch_borders_packed(cls, B, (int)std::min<long long>(max_l1, PC_BORDERS_FAST_MAX_T), st->s, c->sm_count);
     } else if (op == PC_OP_EDIT || op == PC_OP_KBAND) {
       // one job per thread, bit-parallel; what it cannot answer bit-exactly is listed for the wavefront kernel
       pc_launch_myers((int)op, B, (int)std::min<long long>(max_l1, max_l2), d_slow + i, d_slow_count + sg, st->s, c->sm_count);
@@ -495,6 +478,9 @@ extern "C" int pc_stream_sync(pc_stream *st) {
   if (g_prof) drain_events(st);
   Pending &P = st->pend;
   if (!P.active) return 0;
+  // every job that ran out of scratch also raised the pool_need counter (pc_pool_alloc, k_gap): zero = nothing to re-run,
+  // and the statuses need not be read at all
+  if (*st->h_pool_need == 0) { P.active = false; return 0; }
   // Jobs whose scratch did not fit their warp's pool slot are re-run with fewer warps (= larger slots); the pool
   // itself grows only when a single job needs more than all of it.
   for (int round = 0; round < 64; ++round) {

@@ -40,6 +40,39 @@ struct PcDevBatch {
 #define PC_LCS_MAX_S2 4096
 struct PcSegStat { uint32_t n, max_a, max_b, pad; unsigned long long lcs_blocks; };
 
+#define PC_BORDERS_FAST_MAX_T 1024
+/* Kernel class of a job inside its op (shared by the host and the device ordering): GAP and BORDERS jobs that fit the
+ * packed register kernels are classed by their row count (0 / 1 / 2 = 8 / 16 / 32 lanes per job), 3 = generic kernel. */
+__host__ __device__ inline int pc_job_class(const pc_job &j) {
+  if (j.op == PC_OP_GAP) {
+    if (j.a_len < 1 || j.b_len < 1 || j.b_len > 4096 || j.a_len > 256) return 3;
+    return j.a_len <= 64 ? 0 : (j.a_len <= 128 ? 1 : 2);
+  }
+  if (j.op == PC_OP_BORDERS) {
+    const unsigned long long tw = (unsigned long long)j.a_len + (uint32_t)j.p0;
+    const unsigned long long t_win = tw < j.b_len ? tw : j.b_len;
+    if (j.a_len < 1 || j.a_len > 256 || t_win < 1 || t_win > PC_BORDERS_FAST_MAX_T) return 3;
+    return j.a_len <= 64 ? 0 : (j.a_len <= 128 ? 1 : 2);
+  }
+  return 0;
+}
+/* cost class inside a segment, 0..63, larger = heavier (packed kernels: by the number of column steps, finely) */
+__host__ __device__ inline int pc_job_cost(const pc_job &j, int cls) {
+  if ((j.op == PC_OP_GAP || j.op == PC_OP_BORDERS) && cls < 3) {
+    unsigned long long m = j.b_len;
+    if (j.op == PC_OP_BORDERS) { const unsigned long long tw = (unsigned long long)j.a_len + (uint32_t)j.p0; if (tw < m) m = tw; }
+    return m < 512 ? (int)(m >> 4) : 32 + (int)((m - 512) >> 7 < 31 ? (m - 512) >> 7 : 31);
+  }
+  unsigned long long c;
+  if (j.op == PC_OP_LCS || j.op == PC_OP_SEED) c = (unsigned long long)j.a_len + j.b_len + 1ull;
+  else c = ((unsigned long long)j.a_len + 1ull) * ((unsigned long long)j.b_len + 1ull) + 1ull;
+#ifdef __CUDA_ARCH__
+  return 63 - __clzll((long long)c);
+#else
+  return 63 - __builtin_clzll(c);
+#endif
+}
+
 struct WarpPool { uint8_t *base; unsigned long long size, used; };
 
 __device__ __forceinline__ WarpPool pc_warp_pool(const PcDevBatch &B, int slot) {
@@ -69,6 +102,7 @@ void pc_launch_myers(int op, const PcDevBatch &B, int max_short, uint32_t *slow_
 void pc_order_jobs(const pc_job *d_jobs, int n, size_t arena_bytes, size_t genome_len, size_t var_bytes, int lcs_tpb, int lcs_max_s2,
                    uint16_t *d_keys, uint32_t *d_work, PcSegStat *d_seg, uint32_t *d_order, cudaStream_t s, int sm_count);
 void pc_lcs_prefix(const pc_job *d_jobs, const uint32_t *d_order, int n, int lcs_tpb, int lcs_max_s2, uint32_t *d_prefix, cudaStream_t s);
+void pc_launch_borders_packed(int cls, const PcDevBatch &B, int tcap, cudaStream_t s, int sm_count);
 void pc_launch_gap_pairs(int cls, const PcDevBatch &B, int max_m, cudaStream_t s, int sm_count);
 void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count);
 int pc_lcs_blocks(long long l1, int l2);

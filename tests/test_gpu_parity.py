@@ -373,3 +373,47 @@ def test_large_batch_is_ordered_on_the_device(cu, port):
     jb["a_off"][N // 2] = len(arena) + 100
     with pytest.raises(RuntimeError):
         cu.run_arrays(arena, jb, bad.var_bytes)
+
+
+def test_packed_borders_vs_port(cu, port):
+    """k_borders_packed (two matrices per register, rows in registers) and its class boundaries: len_p at 1, 8, 9, 64,
+    65, 128, 129, 256 (packed) and 257 / 400 (generic kernel), windows shorter than p, max_errs 0, single-candidate
+    cut ranges, t taken from the device-resident genome, GT..AG planted so that the Burset tie-break decides."""
+    import random
+    rnd = random.Random(4711)
+    g = Gen(5)
+    genome = g.genome(8000)
+    cu.genome_upload(genome, 15, 0.2)
+    b, chk = Batch(), []
+    for it in range(2500):
+        lp = rnd.choice([1, 2, 7, 8, 9, 20, 40, 63, 64, 65, 100, 128, 129, 200, 256, 257, 400])
+        p = g.rs(lp)
+        cut = rnd.randint(0, lp)
+        mid = g.rs(rnd.choice([0, 0, 5, 60, 300, 1500]))
+        if it % 3 == 0 and len(mid) >= 4:
+            mid = b"GT" + mid[2:-2] + b"AG"
+        t = g.mutate(p[:cut], 0.04) + mid + g.mutate(p[cut:], 0.04)
+        if it % 17 == 0:
+            t = t[:max(1, lp // 2)]                       # window shorter than p
+        if len(t) < 2:
+            t += b"AC"
+        me = rnd.choice([0, 1, 3, 8, 12, 40])
+        lo = rnd.randint(0, lp); hi = rnd.randint(lo, lp)
+        if it % 5 == 0:
+            lo, hi = 0, lp
+        if it % 7 == 0 and len(t) < len(genome):          # the same t, addressed inside the genome copy on the device
+            off = rnd.randint(0, len(genome) - len(t))
+            lt = len(t)
+            t = genome[off:off + lt + 1]                  # the reference reads the byte after t: here the next genome byte
+            b.add(PC_OP.BORDERS, p, b_in_genome=(off, lt), p0=me, p1=lo, p2=hi)
+            chk.append((p, t, lt, me, lo, hi))
+        else:
+            b.add(PC_OP.BORDERS, p, t, p0=me, p1=lo, p2=hi)
+            chk.append((p, t, len(t), me, lo, hi))
+    res, _ = cu.run(b)
+    import ctypes
+    for r, (p, t, lt, me, lo, hi) in zip(res, chk):
+        assert r[0] == 0, (p, t, list(r))
+        out = (ctypes.c_int * 4)()
+        ok = bool(port.lib.po_borders(p, len(p), lo, hi, t, lt, ctypes.c_uint(me), out))
+        assert bool(r[1]) == ok and list(r[2:6]) == list(out), (p, t, lt, me, lo, hi, list(r), ok, list(out))
