@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(128) k_borders_packed(PcDevBatch B, int tcap) 
           v = __vminu2(v, V[r] + ONE2);
           diag = V[r]; V[r] = v; up = v;
           bool ph, pl;                                           // "the old minimum is still <= v": a later equal value never replaces it
-          const uint32_t m2 = __vibmin_u16x2(mn[r], v, &ph, &pl);
+          const uint32_t m2 = pc_vibmin_u16x2(mn[r], v, ph, pl);
           const uint32_t lo = pl ? pos[r] : j2, hi = ph ? pos[r] : j2;
           pos[r] = __byte_perm(lo, hi, 0x7610);
           mn[r] = m2;

@@ -157,22 +157,22 @@ __global__ void __launch_bounds__(128) k_gap_pairs(PcDevBatch B, int mcap) {
           const uint32_t c2m = TWO2 - __vimin3_u16x2(e[r] ^ gcur, e2[r], g2);
           uint32_t bits_a = 0, bits_b = 0;
           // L plane: diagonal, then up if strictly better, then left if strictly better
-          uint32_t v = __vibmax_u16x2(dL + c2m, upL, &ph, &pl);
+          uint32_t v = pc_vibmax_u16x2(dL + c2m, upL, ph, pl);
           if (!pl) bits_a |= 1u; if (!ph) bits_b |= 1u;
-          v = __vibmax_u16x2(v, YL[r], &ph, &pl);
+          v = pc_vibmax_u16x2(v, YL[r], ph, pl);
           if (!pl) bits_a |= 2u; if (!ph) bits_b |= 2u;
           const uint32_t llf = VL[r];
           dL = YL[r]; VL[r] = v; YL[r] = v - ONE2; upL = YL[r];
           // G plane: stay in the gap, or enter it from L
           const uint32_t glf = VG[r];
-          VG[r] = __vibmax_u16x2(glf, llf, &ph, &pl);
+          VG[r] = pc_vibmax_u16x2(glf, llf, ph, pl);
           if (!pl) bits_a |= 4u; if (!ph) bits_b |= 4u;
           // R plane: diagonal, left (free on the job's last row), jump from G, up
-          v = __vibmax_u16x2(dR + c2m, YR[r], &ph, &pl);
+          v = pc_vibmax_u16x2(dR + c2m, YR[r], ph, pl);
           if (!pl) bits_a |= 8u; if (!ph) bits_b |= 8u;
-          v = __vibmax_u16x2(v, glf, &ph, &pl);
+          v = pc_vibmax_u16x2(v, glf, ph, pl);
           if (!pl) bits_a |= 16u; if (!ph) bits_b |= 16u;
-          v = __vibmax_u16x2(v, upR, &ph, &pl);
+          v = pc_vibmax_u16x2(v, upR, ph, pl);
           if (!pl) bits_a |= 32u; if (!ph) bits_b |= 32u;
           dR = YR[r]; YR[r] = v - subv[r]; upR = v - ONE2;
           if (r < 4) { wa0 |= bits_a << (8 * r); wb0 |= bits_b << (8 * r); }

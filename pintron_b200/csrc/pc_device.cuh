@@ -95,6 +95,42 @@ __device__ __forceinline__ uint8_t *pc_pool_alloc(const PcDevBatch &B, WarpPool 
   return p;
 }
 
+// Per-halfword unsigned min / max that also say which operand won (pred = "a is the result": a <= b for min, a >= b
+// for max); ptxas turns each into one VIMNMX.U16x2 with two predicate outputs.  Same PTX as CUDA's __vibmin_u16x2 /
+// __vibmax_u16x2, but with early-clobber outputs: the header's version lets the result share a register with `a`
+// (seen with a loop-carried running minimum), after which its own compare reads the overwritten value and the
+// predicates come out constant.
+__device__ __forceinline__ uint32_t pc_vibmin_u16x2(uint32_t a, uint32_t b, bool &pred_hi, bool &pred_lo) {
+  uint32_t val, h, l;
+  asm("{.reg .pred pu, pv; \n\t"
+      ".reg .u16 rs0, rs1, rs2, rs3; \n\t"
+      "min.u16x2 %0, %3, %4; \n\t"
+      "mov.b32 {rs0, rs1}, %0; \n\t"
+      "mov.b32 {rs2, rs3}, %3; \n\t"
+      "setp.eq.u16 pv, rs0, rs2; \n\t"
+      "setp.eq.u16 pu, rs1, rs3; \n\t"
+      "selp.b32 %1, 1, 0, pu; \n\t"
+      "selp.b32 %2, 1, 0, pv;} \n\t"
+      : "=&r"(val), "=&r"(h), "=&r"(l) : "r"(a), "r"(b));
+  pred_hi = h != 0; pred_lo = l != 0;
+  return val;
+}
+__device__ __forceinline__ uint32_t pc_vibmax_u16x2(uint32_t a, uint32_t b, bool &pred_hi, bool &pred_lo) {
+  uint32_t val, h, l;
+  asm("{.reg .pred pu, pv; \n\t"
+      ".reg .u16 rs0, rs1, rs2, rs3; \n\t"
+      "max.u16x2 %0, %3, %4; \n\t"
+      "mov.b32 {rs0, rs1}, %0; \n\t"
+      "mov.b32 {rs2, rs3}, %3; \n\t"
+      "setp.eq.u16 pv, rs0, rs2; \n\t"
+      "setp.eq.u16 pu, rs1, rs3; \n\t"
+      "selp.b32 %1, 1, 0, pu; \n\t"
+      "selp.b32 %2, 1, 0, pv;} \n\t"
+      : "=&r"(val), "=&r"(h), "=&r"(l) : "r"(a), "r"(b));
+  pred_hi = h != 0; pred_lo = l != 0;
+  return val;
+}
+
 __device__ __forceinline__ bool pc_is_n(uint8_t c) { return c == 'n' || c == 'N'; }
 
 void pc_launch_dp(int op, const PcDevBatch &B, cudaStream_t s, int sm_count);
