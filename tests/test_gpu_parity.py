@@ -401,10 +401,10 @@ def test_packed_borders_vs_port(cu, port):
         lo = rnd.randint(0, lp); hi = rnd.randint(lo, lp)
         if it % 5 == 0:
             lo, hi = 0, lp
-        if it % 7 == 0 and len(t) < len(genome):          # the same t, addressed inside the genome copy on the device
-            off = rnd.randint(0, len(genome) - len(t))
+        if it % 7 == 0 and len(t) + 2 < len(genome):      # the same t, addressed inside the genome copy on the device
+            off = rnd.randint(0, len(genome) - len(t) - 2)
             lt = len(t)
-            t = genome[off:off + lt + 1]                  # the reference reads the byte after t: here the next genome byte
+            t = genome[off:off + lt + 2]                  # the reference may read the two bytes after t: here the next genome bytes
             b.add(PC_OP.BORDERS, p, b_in_genome=(off, lt), p0=me, p1=lo, p2=hi)
             chk.append((p, t, lt, me, lo, hi))
         else:

@@ -50,7 +50,7 @@ while at + 12 <= raw.size:
         elif o == PC_OP.KBAND:
             ok = r[0] == 0 and (bool(r[1]), int(r[2])) == port.kband(a, b, int(j["p0"]))
         elif o == PC_OP.BORDERS:
-            text = src[j["b_off"]:j["b_off"] + j["b_len"] + 1]
+            text = src[j["b_off"]:j["b_off"] + j["b_len"] + 2]
             if j["flags"] & 2:
                 text = b + b"\0"
             out = (ctypes.c_int * 4)()
