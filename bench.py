@@ -246,7 +246,9 @@ def main():
     h_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).pin_memory()
     h_res = torch.zeros(n * PC_RES_INTS, dtype=torch.int32).pin_memory()
     h_var = torch.zeros(max(var_bytes, 1), dtype=torch.uint8).pin_memory()
-    d_arena, d_jobs = h_arena.cuda(), h_jobs.cuda()
+    d_arena = torch.zeros(len(arena) + 16, dtype=torch.uint8, device="cuda")      # pc_submit_device: readable 16 bytes past the arena
+    d_arena[:len(arena)].copy_(h_arena)
+    d_jobs = h_jobs.cuda()
     d_res = torch.zeros(n * PC_RES_INTS, dtype=torch.int32, device="cuda")
     d_var = torch.zeros(max(var_bytes, 1) + 16, dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
@@ -440,6 +442,8 @@ def main():
             "int_alu_peak_tlaneops": int_peak / 1e12,
         }
         print(json.dumps(line))
+    if os.environ.get("PC_PROFILE"):
+        L.pc_debug_dump()
     if world > 1:
         dist.destroy_process_group()
     cu.close()

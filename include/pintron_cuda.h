@@ -100,7 +100,8 @@ int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes, const pc_
               int32_t *res, uint8_t *var_out, size_t var_out_bytes);
 
 /* Same, for inputs that are ALREADY in device memory (bench "value" leg, chained device pipelines):
- * d_arena / d_jobs / d_res / d_var_out are device pointers; nothing is copied. */
+ * d_arena / d_jobs / d_res / d_var_out are device pointers; nothing is copied.  d_arena must be readable (and zero)
+ * for 16 bytes past arena_bytes, d_var_out writable for 16 bytes past var_out_bytes (pc_submit pads its own copies). */
 int pc_submit_device(pc_stream *st, const uint8_t *d_arena, size_t arena_bytes, const pc_job *d_jobs,
                      const pc_job *h_jobs, int njobs, int32_t *d_res, uint8_t *d_var_out, size_t var_out_bytes);
 

@@ -12,6 +12,17 @@
 // K-band jobs whose true distance is above k while the reference would report the value of its band-restricted
 // matrix (2k+1 < n): that value is not the edit distance and only the banded sweep reproduces it.
 #include "pc_device.cuh"
+
+// symbol table in shared memory (filled per block) and word-wise string loads for myers_core.h
+#define MY_HD __device__ __forceinline__
+#define MY_SYM(c) ((int)my_symtab[(c)])
+#define MY_LOAD4(p) my_load4_dev(p)
+__device__ __forceinline__ uint32_t my_load4_dev(const uint8_t *p) {
+  const uintptr_t a = (uintptr_t)p;
+  const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);       // both buffers are readable 16 bytes past their end
+  return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8u);
+}
+__shared__ int8_t my_symtab[256];
 #include "myers_core.h"
 
 namespace {
@@ -21,6 +32,8 @@ constexpr int MY_TPB = 64;
 template <int OP, int MAXW>
 __global__ void __launch_bounds__(MY_TPB) k_myers(PcDevBatch B, uint32_t *slow_list, uint32_t *slow_count) {
   __shared__ unsigned long long peq[MY_NSYM * MAXW * MY_TPB];
+  for (int c = threadIdx.x; c < 256; c += MY_TPB) my_symtab[c] = (int8_t)my_sym_switch((uint8_t)c);
+  __syncthreads();
   for (int w = blockIdx.x * MY_TPB + threadIdx.x; w < B.n; w += gridDim.x * MY_TPB) {
     const uint32_t ji = B.idx[w];
     const pc_job *job = B.jobs + ji;
@@ -68,15 +81,18 @@ void launch_myers(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count
 
 }  // namespace
 
-// op = PC_OP_EDIT or PC_OP_KBAND.  max_short = upper bound on min(a_len, b_len) over the jobs (picks the one-word
-// variant).  slow_list (B.n entries) / slow_count (zeroed here) receive the job indices left for the generic kernel.
-void pc_launch_myers(int op, const PcDevBatch &B, int max_short, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count) {
+// op = PC_OP_EDIT or PC_OP_KBAND.  cls = length class of the segment (pc_job_class: shorter string <= 64 / 128 / 320
+// letters -> 1 / 2 / 5 words per column).  slow_list (B.n entries) / slow_count (zeroed here) receive the job indices
+// left for the generic kernel.
+void pc_launch_myers(int op, int cls, const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count) {
   cudaMemsetAsync(slow_count, 0, sizeof(uint32_t), s);
   if (op == PC_OP_EDIT) {
-    if (max_short <= 64) launch_myers<PC_OP_EDIT, 1>(B, slow_list, slow_count, s, sm_count);
+    if (cls == 0) launch_myers<PC_OP_EDIT, 1>(B, slow_list, slow_count, s, sm_count);
+    else if (cls == 1) launch_myers<PC_OP_EDIT, 2>(B, slow_list, slow_count, s, sm_count);
     else launch_myers<PC_OP_EDIT, MY_MAXW>(B, slow_list, slow_count, s, sm_count);
   } else {
-    if (max_short <= 64) launch_myers<PC_OP_KBAND, 1>(B, slow_list, slow_count, s, sm_count);
+    if (cls == 0) launch_myers<PC_OP_KBAND, 1>(B, slow_list, slow_count, s, sm_count);
+    else if (cls == 1) launch_myers<PC_OP_KBAND, 2>(B, slow_list, slow_count, s, sm_count);
     else launch_myers<PC_OP_KBAND, MY_MAXW>(B, slow_list, slow_count, s, sm_count);
   }
 }

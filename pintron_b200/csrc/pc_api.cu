@@ -19,6 +19,7 @@ static std::mutex g_capture_mu;
 static double g_t[8];      /* check, reserve, h2d, sort, launch, d2h, sync (racy sums: diagnostics only) */
 static unsigned long long g_dev_grows, g_host_allocs, g_host_alloc_bytes; static double g_host_alloc_s;
 static unsigned long long g_op_jobs[PC_OP_COUNT], g_op_suma[PC_OP_COUNT], g_op_sumb[PC_OP_COUNT], g_op_maxa[PC_OP_COUNT], g_op_maxb[PC_OP_COUNT], g_op_cells[PC_OP_COUNT];
+static unsigned long long g_op_slow[PC_OP_COUNT];
 static double g_op_ms[PC_OP_COUNT]; static unsigned long long g_op_launches[PC_OP_COUNT], g_retry_rounds, g_retry_jobs, g_pool_grows;
 extern "C" void pc_debug_dump(void) {
   if (g_capture) fflush(g_capture);
@@ -29,6 +30,7 @@ extern "C" void pc_debug_dump(void) {
   for (int i = 0; i < PC_OP_COUNT; ++i) if (g_op_launches[i]) fprintf(stderr, " %s %.1f (%llu launches)", nm[i], g_op_ms[i], g_op_launches[i]);
   fprintf(stderr, "\n[pc profile] jobs per op (count, mean a_len, mean b_len, max a_len, max b_len, a*b cells):");
   for (int i = 0; i < PC_OP_COUNT; ++i) if (g_op_jobs[i]) fprintf(stderr, " %s %llu %.1f %.1f %llu %llu %.3g;", nm[i], g_op_jobs[i], (double)g_op_suma[i] / g_op_jobs[i], (double)g_op_sumb[i] / g_op_jobs[i], g_op_maxa[i], g_op_maxb[i], (double)g_op_cells[i]);
+  fprintf(stderr, "\n[pc profile] jobs the bit-parallel kernel handed to the wavefront kernel: EDIT %llu, KBAND %llu", g_op_slow[PC_OP_EDIT], g_op_slow[PC_OP_KBAND]);
   fprintf(stderr, "\n[pc profile] pool retries: %llu rounds, %llu jobs, %llu pool growths\n", g_retry_rounds, g_retry_jobs, g_pool_grows);
   fprintf(stderr, "[pc profile] device buffer growths (cudaMalloc during the run): %llu; pinned host allocations: %llu, %.1f MB, %.3f s\n",
           g_dev_grows, g_host_allocs, g_host_alloc_bytes / 1048576.0, g_host_alloc_s);
@@ -112,6 +114,7 @@ struct pc_stream {
   int max_warps = 0;
   std::vector<uint32_t> h_bins;
   PinBuf pin_idx, pin_lcs, pin_seg;
+  uint32_t *last_slow_count = nullptr;      /* device: per-segment counts of jobs handed from k_myers to the wavefront kernel (profiling) */
   std::vector<uint16_t> h_key;
   std::vector<int32_t> h_status;
   Pending pend;
@@ -277,6 +280,8 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
   const size_t extra_words = on_device ? idx_words / 2 + 3 * NB + 64 + NSEG * (sizeof(PcSegStat) / 4) : 0;
   if (st->idx.reserve((2 * idx_words + 64 + extra_words) * 4 + 256)) return PC_E_NOMEM;
   uint32_t *d_order = (uint32_t *)st->idx.p, *d_slow = d_order + idx_words, *d_slow_count = d_order + 2 * idx_words;
+  st->last_slow_count = d_slow_count;
+  if (g_prof) CU(cudaMemsetAsync(d_slow_count, 0, 64 * sizeof(uint32_t), st->s));
   PinBuf &order = st->pin_idx;
   if (on_device) {
     // millions of jobs already in HBM: key, histogram, scan and scatter run there (k_order.cu); the host only reads
@@ -375,9 +380,9 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
       pc_launch_gap_pairs(cls, B, (int)max_l1, st->s, c->sm_count);
     } else if (op == PC_OP_BORDERS && cls < 3) {
       pc_launch_borders_packed(cls, B, (int)std::min<long long>(max_l1, PC_BORDERS_FAST_MAX_T), st->s, c->sm_count);
-    } else if (op == PC_OP_EDIT || op == PC_OP_KBAND) {
+    } else if ((op == PC_OP_EDIT || op == PC_OP_KBAND) && cls < 3) {
       // one job per thread, bit-parallel; what it cannot answer bit-exactly is listed for the wavefront kernel
-      pc_launch_myers((int)op, B, (int)std::min<long long>(max_l1, max_l2), d_slow + i, d_slow_count + sg, st->s, c->sm_count);
+      pc_launch_myers((int)op, cls, B, d_slow + i, d_slow_count + sg, st->s, c->sm_count);
       PcDevBatch S = B;
       S.idx = d_slow + i; S.n_dev = d_slow_count + sg;
       pc_launch_dp((int)op, S, st->s, c->sm_count);
@@ -476,6 +481,12 @@ extern "C" int pc_stream_sync(pc_stream *st) {
   CU(cudaStreamSynchronize(st->s));
   PROF(6, tp);
   if (g_prof) drain_events(st);
+  if (g_prof && st->last_slow_count) {
+    uint32_t h[64];
+    if (cudaMemcpy(h, st->last_slow_count, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
+      for (int sg = 0; sg < PC_ORDER_SEGS; ++sg) g_op_slow[sg / 4] += h[sg];
+    st->last_slow_count = nullptr;
+  }
   Pending &P = st->pend;
   if (!P.active) return 0;
   // every job that ran out of scratch also raised the pool_need counter (pc_pool_alloc, k_gap): zero = nothing to re-run,

@@ -42,7 +42,8 @@ struct PcSegStat { uint32_t n, max_a, max_b, pad; unsigned long long lcs_blocks;
 
 #define PC_BORDERS_FAST_MAX_T 1024
 /* Kernel class of a job inside its op (shared by the host and the device ordering): GAP and BORDERS jobs that fit the
- * packed register kernels are classed by their row count (0 / 1 / 2 = 8 / 16 / 32 lanes per job), 3 = generic kernel. */
+ * packed register kernels are classed by their row count (0 / 1 / 2 = 8 / 16 / 32 lanes per job), EDIT / KBAND jobs by
+ * the words per column of the bit-parallel kernel; 3 = generic wavefront kernel. */
 __host__ __device__ inline int pc_job_class(const pc_job &j) {
   if (j.op == PC_OP_GAP) {
     if (j.a_len < 1 || j.b_len < 1 || j.b_len > 4096 || j.a_len > 256) return 3;
@@ -53,6 +54,10 @@ __host__ __device__ inline int pc_job_class(const pc_job &j) {
     const unsigned long long t_win = tw < j.b_len ? tw : j.b_len;
     if (j.a_len < 1 || j.a_len > 256 || t_win < 1 || t_win > PC_BORDERS_FAST_MAX_T) return 3;
     return j.a_len <= 64 ? 0 : (j.a_len <= 128 ? 1 : 2);
+  }
+  if (j.op == PC_OP_EDIT || j.op == PC_OP_KBAND) {        /* bit-parallel kernel: words per column from the shorter string */
+    const uint32_t m = j.a_len < j.b_len ? j.a_len : j.b_len;
+    return m <= 64 ? 0 : (m <= 128 ? 1 : (m <= 320 ? 2 : 3));
   }
   return 0;
 }
@@ -134,7 +139,7 @@ __device__ __forceinline__ uint32_t pc_vibmax_u16x2(uint32_t a, uint32_t b, bool
 __device__ __forceinline__ bool pc_is_n(uint8_t c) { return c == 'n' || c == 'N'; }
 
 void pc_launch_dp(int op, const PcDevBatch &B, cudaStream_t s, int sm_count);
-void pc_launch_myers(int op, const PcDevBatch &B, int max_short, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count);
+void pc_launch_myers(int op, int cls, const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count);
 void pc_order_jobs(const pc_job *d_jobs, int n, size_t arena_bytes, size_t genome_len, size_t var_bytes, int lcs_tpb, int lcs_max_s2,
                    uint16_t *d_keys, uint32_t *d_work, PcSegStat *d_seg, uint32_t *d_order, cudaStream_t s, int sm_count);
 void pc_lcs_prefix(const pc_job *d_jobs, const uint32_t *d_order, int n, int lcs_tpb, int lcs_max_s2, uint32_t *d_prefix, cudaStream_t s);
