@@ -388,6 +388,106 @@ __global__ void __launch_bounds__(128) k_borders_packed(PcDevBatch B, int tcap) 
   }
 }
 
+// The same sweep for jobs of any height: one warp per job, rows in chunks of 256 (32 lanes x 8 rows).  The bottom row
+// of a chunk is the top boundary of the next one: lane 31 stores it column by column into a scratch row that lane 0
+// reads one column ahead (in place: lane 31 trails lane 0 by 31 columns).  Column letters come straight from t (two
+// bytes per step, fetched one step ahead), per-row minima go to scratch as each chunk ends.  Values must fit 16 bits
+// (len_p + t_win <= 65000); anything larger is listed for the wavefront kernel.
+__global__ void __launch_bounds__(128) k_borders_chunked(PcDevBatch B, uint32_t *slow_list, uint32_t *slow_count) {
+  constexpr uint32_t ONE2 = 0x00010001u;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp_id = blockIdx.x * 4 + wib, nwarps = gridDim.x * 4;
+  WarpPool wp = pc_warp_pool(B, warp_id);
+  for (int q = warp_id; q < B.n; q += nwarps) {
+    wp.used = 0;
+    JobView J = view(B, q);
+    const int len_p = J.la, len_t = J.lb;
+    const uint32_t max_errs = (uint32_t)J.job->p0;
+    const int min_cut = J.job->p1, max_cut = J.job->p2;
+    if (min_cut < 0 || min_cut > max_cut || max_cut > len_p) { if (lane == 0) J.res[0] = PC_E_ARG; continue; }
+    const unsigned long long tw64 = min((unsigned long long)len_p + max_errs, (unsigned long long)len_t);
+    if ((unsigned long long)len_p + tw64 > 65000ull) { if (lane == 0) slow_list[atomicAdd(slow_count, 1u)] = B.idx[q]; continue; }
+    const int t_win = (int)tw64;
+    uint32_t *rowbuf = (uint32_t *)pc_pool_alloc(B, wp, 4ull * ((unsigned long long)t_win + 2 + 2ull * (len_p + 1)), lane);
+    if (!rowbuf) { if (lane == 0) J.res[0] = PC_E_POOL; continue; }
+    uint32_t *mnS = rowbuf + t_win + 2, *posS = mnS + len_p + 1;
+    for (int j = lane; j <= t_win; j += 32) rowbuf[j] = (uint32_t)j * ONE2;             // row 0: D[0][j] = j
+    if (lane == 0) { mnS[0] = 0u; posS[0] = 0u; }
+    __syncwarp();
+    const int steps = t_win + 31;
+    for (int base = 0; base < len_p; base += 256) {
+      uint32_t e[8], V[8], mn[8], pos[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int i = base + lane * 8 + r + 1;
+        e[r] = i <= len_p ? ((uint32_t)J.a[i - 1] | ((uint32_t)J.a[len_p - i] << 16)) : 0u;
+        V[r] = (uint32_t)i * ONE2; mn[r] = V[r]; pos[r] = 0u;
+      }
+      uint32_t inV = (uint32_t)(base + 8 * lane) * ONE2, gcur = 0;
+      // lane 0 runs one column ahead on its two inputs: the boundary row and the letters of column j
+      uint32_t top_next = 0, code_next = 0;
+      if (lane == 0 && t_win >= 1) { top_next = rowbuf[1]; code_next = (uint32_t)J.b[0] | ((uint32_t)J.b[len_t - 1] << 16); }
+      for (int s = 1; s <= steps; ++s) {
+        const int j = s - lane;
+        uint32_t dprev = inV;
+        inV = __shfl_up_sync(0xffffffffu, V[7], 1);
+        gcur = __shfl_up_sync(0xffffffffu, gcur, 1);
+        if (lane == 0) {
+          inV = top_next; gcur = code_next;                        // (row base, column j), letters of column j; dprev = (row base, column j-1)
+          if (s + 1 <= t_win) { top_next = rowbuf[s + 1]; code_next = (uint32_t)J.b[s] | ((uint32_t)J.b[len_t - s - 1] << 16); }
+        }
+        if (j >= 1 && j <= t_win) {
+          const uint32_t j2 = (uint32_t)j * ONE2;
+          uint32_t diag = dprev, up = inV;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const uint32_t c = __vminu2(e[r] ^ gcur, ONE2);
+            uint32_t v = __vminu2(diag + c, up + ONE2);
+            v = __vminu2(v, V[r] + ONE2);
+            diag = V[r]; V[r] = v; up = v;
+            bool ph, pl;
+            const uint32_t m2 = pc_vibmin_u16x2(mn[r], v, ph, pl);
+            const uint32_t lo = pl ? pos[r] : j2, hi = ph ? pos[r] : j2;
+            pos[r] = __byte_perm(lo, hi, 0x7610);
+            mn[r] = m2;
+          }
+          if (lane == 31) rowbuf[j] = V[7];                        // bottom row of this chunk = top boundary of the next
+        }
+      }
+      if (lane == 31) rowbuf[0] = (uint32_t)(base + 256) * ONE2;   // column 0 of that boundary row
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int i = base + lane * 8 + r + 1;
+        if (i <= len_p) { mnS[i] = mn[r]; posS[i] = pos[r]; }
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+    const int nul_at = (J.job->flags & PC_B_NUL_AFTER) ? len_t : -1;
+    unsigned long long best_key = ~0ull;
+    uint32_t bc = 0xffffffffu;
+    for (int i = min_cut + lane; i <= max_cut; i += 32) {
+      const uint32_t c = (mnS[i] & 0xffffu) + (mnS[len_p - i] >> 16);
+      if (bc < c) continue;
+      const int freq = burset_freq(J.b, (int)(posS[i] & 0xffffu), len_t - (int)(posS[len_p - i] >> 16), nul_at);
+      const unsigned long long key = ((unsigned long long)c << 32) | ((unsigned long long)(0xffff - freq) << 16) | (unsigned long long)i;   // i <= len_p < 65536
+      if (key < best_key) { best_key = key; bc = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best_key, o);
+      best_key = other < best_key ? other : best_key;
+    }
+    if (lane == 0) {
+      const int i = (int)(best_key & 0xffffu);
+      const uint32_t best = (uint32_t)(best_key >> 32);
+      J.res[0] = PC_OK; J.res[1] = best <= max_errs; J.res[2] = i; J.res[3] = (int32_t)(posS[i] & 0xffffu);
+      J.res[4] = len_t - (int32_t)(posS[len_p - i] >> 16); J.res[5] = (int32_t)best;
+    }
+    __syncwarp();
+  }
+}
+
 template <int LANES>
 void launch_borders_packed(const PcDevBatch &B, int tcap, cudaStream_t s, int sm_count) {
   constexpr int G = 32 / LANES;
@@ -607,6 +707,21 @@ void pc_launch_borders_packed(int cls, const PcDevBatch &B, int tcap, cudaStream
   if (cls == 0) launch_borders_packed<8>(B, tcap, s, sm_count);
   else if (cls == 1) launch_borders_packed<16>(B, tcap, s, sm_count);
   else launch_borders_packed<32>(B, tcap, s, sm_count);
+}
+
+// BORDERS jobs outside the packed classes (taller than 256 rows, or a window above PC_BORDERS_FAST_MAX_T columns)
+void pc_launch_borders_chunked(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count) {
+  cudaMemsetAsync(slow_count, 0, sizeof(uint32_t), s);
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_borders_chunked, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int needed = (B.n + 3) / 4;
+  int grid = needed < sm_count * per_sm ? needed : sm_count * per_sm;
+  if (B.max_warps > 0 && grid > (B.max_warps + 3) / 4) grid = (B.max_warps + 3) / 4;
+  if (grid < 1) grid = 1;
+  PcDevBatch C = B;
+  C.slots = grid * 4;
+  k_borders_chunked<<<grid, 128, 0, s>>>(C, slow_list, slow_count);
+  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
 }
 
 void pc_launch_dp(int op, const PcDevBatch &B, cudaStream_t s, int sm_count) {

@@ -380,6 +380,12 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
       pc_launch_gap_pairs(cls, B, (int)max_l1, st->s, c->sm_count);
     } else if (op == PC_OP_BORDERS && cls < 3) {
       pc_launch_borders_packed(cls, B, (int)std::min<long long>(max_l1, PC_BORDERS_FAST_MAX_T), st->s, c->sm_count);
+    } else if (op == PC_OP_BORDERS) {
+      // taller than the packed classes: row-chunked packed sweep; what does not fit 16-bit scores goes to the wavefront kernel
+      pc_launch_borders_chunked(B, d_slow + i, d_slow_count + sg, st->s, c->sm_count);
+      PcDevBatch S = B;
+      S.idx = d_slow + i; S.n_dev = d_slow_count + sg;
+      pc_launch_dp((int)op, S, st->s, c->sm_count);
     } else if ((op == PC_OP_EDIT || op == PC_OP_KBAND) && cls < 3) {
       // one job per thread, bit-parallel; what it cannot answer bit-exactly is listed for the wavefront kernel
       pc_launch_myers((int)op, cls, B, d_slow + i, d_slow_count + sg, st->s, c->sm_count);

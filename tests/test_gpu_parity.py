@@ -377,7 +377,7 @@ def test_large_batch_is_ordered_on_the_device(cu, port):
 
 def test_packed_borders_vs_port(cu, port):
     """k_borders_packed (two matrices per register, rows in registers) and its class boundaries: len_p at 1, 8, 9, 64,
-    65, 128, 129, 256 (packed) and 257 / 400 (generic kernel), windows shorter than p, max_errs 0, single-candidate
+    65, 128, 129, 256 (packed), 257 .. 900 and windows above 1024 columns (row-chunked kernel), windows shorter than p, max_errs 0, single-candidate
     cut ranges, t taken from the device-resident genome, GT..AG planted so that the Burset tie-break decides."""
     import random
     rnd = random.Random(4711)
@@ -386,7 +386,7 @@ def test_packed_borders_vs_port(cu, port):
     cu.genome_upload(genome, 15, 0.2)
     b, chk = Batch(), []
     for it in range(2500):
-        lp = rnd.choice([1, 2, 7, 8, 9, 20, 40, 63, 64, 65, 100, 128, 129, 200, 256, 257, 400])
+        lp = rnd.choice([1, 2, 7, 8, 9, 20, 40, 63, 64, 65, 100, 128, 129, 200, 256, 257, 400, 511, 513, 900])
         p = g.rs(lp)
         cut = rnd.randint(0, lp)
         mid = g.rs(rnd.choice([0, 0, 5, 60, 300, 1500]))
@@ -397,7 +397,7 @@ def test_packed_borders_vs_port(cu, port):
             t = t[:max(1, lp // 2)]                       # window shorter than p
         if len(t) < 2:
             t += b"AC"
-        me = rnd.choice([0, 1, 3, 8, 12, 40])
+        me = rnd.choice([0, 1, 3, 8, 12, 40, 1500])       # 1500: a window above the packed kernels' 1024 columns when t is long
         lo = rnd.randint(0, lp); hi = rnd.randint(lo, lp)
         if it % 5 == 0:
             lo, hi = 0, lp
@@ -410,6 +410,9 @@ def test_packed_borders_vs_port(cu, port):
         else:
             b.add(PC_OP.BORDERS, p, t, p0=me, p1=lo, p2=hi)
             chk.append((p, t, len(t), me, lo, hi))
+    # scores that do not fit 16 bits: handed from the chunked kernel to the wavefront kernel
+    p = g.rs(100); t = g.rs(70000)
+    b.add(PC_OP.BORDERS, p, t, p0=70000, p1=0, p2=100); chk.append((p, t, len(t), 70000, 0, 100))
     res, _ = cu.run(b)
     import ctypes
     for r, (p, t, lt, me, lo, hi) in zip(res, chk):
