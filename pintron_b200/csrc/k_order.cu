@@ -129,7 +129,19 @@ __global__ void __launch_bounds__(1024) k_lcs_prefix(const pc_job *jobs, const u
   if (threadIdx.x == 0) prefix[n] = carry;
 }
 
+// jobs whose status is `code` (PC_E_POOL after a pass): their indices, for the re-run with larger scratch slots
+__global__ void __launch_bounds__(256) k_collect_status(const int32_t *res, int n, int code, uint32_t *list, uint32_t *count) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (res[(size_t)i * PC_RES_INTS] == code) list[atomicAdd(count, 1u)] = (uint32_t)i;
+}
+
 }  // namespace
+
+void pc_collect_status(const int32_t *d_res, int n, int code, uint32_t *d_list, uint32_t *d_count, cudaStream_t s, int sm_count) {
+  cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s);
+  k_collect_status<<<min((n + 255) / 256, sm_count * 8), 256, 0, s>>>(d_res, n, code, d_list, d_count);
+  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+}
 
 // Enqueue keys + histogram + scan + scatter on `s`.  work = [bins NB | start NB+1 | cursor NB | invalid 1] uint32 (zeroed here),
 // seg = PC_ORDER_SEGS PcSegStat (zeroed here).  The caller copies seg / invalid back and synchronises before it

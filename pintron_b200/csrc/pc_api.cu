@@ -501,14 +501,22 @@ extern "C" int pc_stream_sync(pc_stream *st) {
   // Jobs whose scratch did not fit their warp's pool slot are re-run with fewer warps (= larger slots); the pool
   // itself grows only when a single job needs more than all of it.
   for (int round = 0; round < 64; ++round) {
-    const int32_t *status = P.res;
-    if (P.device_mode) {
-      st->h_status.resize((size_t)P.njobs * PC_RES_INTS);
-      CU(cudaMemcpy(st->h_status.data(), P.d_res, sizeof(int32_t) * PC_RES_INTS * (size_t)P.njobs, cudaMemcpyDeviceToHost));
-      status = st->h_status.data();
-    }
     std::vector<uint32_t> redo;
-    for (int i = 0; i < P.njobs; ++i) if (status[(size_t)i * PC_RES_INTS] == PC_E_POOL) redo.push_back((uint32_t)i);
+    if (P.device_mode) {
+      // device-resident results: the failed jobs are listed by a kernel, only the list comes back
+      if (st->lcs_best.reserve(4ull * ((size_t)P.njobs + 4))) { P.active = false; return PC_E_NOMEM; }
+      uint32_t *d_list = (uint32_t *)st->lcs_best.p + 4, *d_count = (uint32_t *)st->lcs_best.p;
+      pc_collect_status(P.d_res, P.njobs, PC_E_POOL, d_list, d_count, st->s, st->ctx->sm_count);
+      uint32_t cnt = 0;
+      CU(cudaMemcpyAsync(&cnt, d_count, 4, cudaMemcpyDeviceToHost, st->s));
+      CU(cudaStreamSynchronize(st->s));
+      redo.resize(cnt);
+      if (cnt) CU(cudaMemcpy(redo.data(), d_list, 4ull * cnt, cudaMemcpyDeviceToHost));
+      std::sort(redo.begin(), redo.end());
+    } else {
+      const int32_t *status = P.res;
+      for (int i = 0; i < P.njobs; ++i) if (status[(size_t)i * PC_RES_INTS] == PC_E_POOL) redo.push_back((uint32_t)i);
+    }
     if (redo.empty()) break;
     if (g_prof) { ++g_retry_rounds; g_retry_jobs += redo.size(); }
     const unsigned long long need = std::max<unsigned long long>(*st->h_pool_need, 4096) + 4096;
