@@ -29,6 +29,17 @@ namespace {
 
 constexpr int MY_TPB = 64;
 
+// The wide variant serves 3, 4 and 5 words per column: the instance with exactly the job's word count runs, so a
+// 150-letter string does not pay for two predicated-off blocks per column (the Peq array is sized for 5).
+template <int MAXW>
+__device__ __forceinline__ uint32_t myers_dispatch(const uint8_t *pat, int m, const uint8_t *txt, int n, unsigned long long *peq, int stride) {
+  if (MAXW <= 2) return my_edit_distance<MAXW>(pat, m, txt, n, peq, stride);
+  const int W = (m + 63) >> 6;
+  if (W <= 3) return my_edit_distance<3>(pat, m, txt, n, peq, stride);
+  if (W == 4) return my_edit_distance<4>(pat, m, txt, n, peq, stride);
+  return my_edit_distance<5>(pat, m, txt, n, peq, stride);
+}
+
 template <int OP, int MAXW>
 __global__ void __launch_bounds__(MY_TPB) k_myers(PcDevBatch B, uint32_t *slow_list, uint32_t *slow_count) {
   __shared__ unsigned long long peq[MY_NSYM * MAXW * MY_TPB];
@@ -47,7 +58,7 @@ __global__ void __launch_bounds__(MY_TPB) k_myers(PcDevBatch B, uint32_t *slow_l
     bool slow = m > 64 * MAXW;
     if (OP == PC_OP_EDIT) {
       if (!slow) {
-        const uint32_t d = my_edit_distance<MAXW>(pat, m, txt, n, peq + threadIdx.x, MY_TPB);
+        const uint32_t d = myers_dispatch<MAXW>(pat, m, txt, n, peq + threadIdx.x, MY_TPB);
         if (d == MY_UNSUPPORTED) slow = true;
         else { res[0] = PC_OK; res[1] = (int32_t)d; }
       }
@@ -57,7 +68,7 @@ __global__ void __launch_bounds__(MY_TPB) k_myers(PcDevBatch B, uint32_t *slow_l
       if (la != lb && k == 0) { res[0] = PC_OK; res[1] = 0; res[2] = 1; }                                     // not equal, no error allowed
       else if (la != lb && (uint32_t)(n - m) > k) { res[0] = PC_OK; res[1] = 0; res[2] = n - m; }               // length gap alone is too much
       else if (!slow) {
-        const uint32_t d = my_edit_distance<MAXW>(pat, m, txt, n, peq + threadIdx.x, MY_TPB);
+        const uint32_t d = myers_dispatch<MAXW>(pat, m, txt, n, peq + threadIdx.x, MY_TPB);
         if (d == MY_UNSUPPORTED) slow = true;
         else if (la == lb && d == 0) { res[0] = PC_OK; res[1] = 1; res[2] = 0; }                               // equal strings
         else if (k == 0) { res[0] = PC_OK; res[1] = 0; res[2] = 1; }

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) k_job_keys(const pc_job *jobs, int n, siz
   __shared__ uint32_t sh_bins[PC_ORDER_BINS];
   __shared__ PcSegStat sh_seg[PC_ORDER_SEGS];
   for (int x = threadIdx.x; x < PC_ORDER_BINS; x += blockDim.x) sh_bins[x] = 0;
-  for (int x = threadIdx.x; x < PC_ORDER_SEGS; x += blockDim.x) { sh_seg[x].n = 0; sh_seg[x].max_a = 0; sh_seg[x].max_b = 0; sh_seg[x].lcs_blocks = 0; }
+  for (int x = threadIdx.x; x < PC_ORDER_SEGS; x += blockDim.x) { sh_seg[x].n = 0; sh_seg[x].max_a = 0; sh_seg[x].max_b = 0; sh_seg[x].max_t = 0; sh_seg[x].lcs_blocks = 0; }
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const pc_job j = jobs[i];
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) k_job_keys(const pc_job *jobs, int n, siz
     atomicAdd(&sh_seg[sg].n, 1u);
     atomicMax(&sh_seg[sg].max_a, j.a_len);
     atomicMax(&sh_seg[sg].max_b, j.b_len);
+    if (j.op == PC_OP_BORDERS) atomicMax(&sh_seg[sg].max_t, pc_borders_window(j));
     if (j.op == PC_OP_LCS) {
       const long long l1 = j.b_len; const int l2 = (int)j.a_len;
       const unsigned long long blocks = (l2 > lcs_max_s2 || l2 <= 0 || l1 <= 0) ? 0ull : (unsigned long long)((l1 + l2 - 1 + lcs_tpb - 1) / lcs_tpb);
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) k_job_keys(const pc_job *jobs, int n, siz
   for (int x = threadIdx.x; x < PC_ORDER_BINS; x += blockDim.x) if (sh_bins[x]) atomicAdd(&bins[x], sh_bins[x]);
   for (int x = threadIdx.x; x < PC_ORDER_SEGS; x += blockDim.x)
     if (sh_seg[x].n) {
-      atomicAdd(&seg[x].n, sh_seg[x].n); atomicMax(&seg[x].max_a, sh_seg[x].max_a); atomicMax(&seg[x].max_b, sh_seg[x].max_b);
+      atomicAdd(&seg[x].n, sh_seg[x].n); atomicMax(&seg[x].max_a, sh_seg[x].max_a); atomicMax(&seg[x].max_b, sh_seg[x].max_b); atomicMax(&seg[x].max_t, sh_seg[x].max_t);
       if (sh_seg[x].lcs_blocks) atomicAdd(&seg[x].lcs_blocks, sh_seg[x].lcs_blocks);
     }
 }

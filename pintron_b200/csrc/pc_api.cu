@@ -271,7 +271,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
   pc_ctx *c = st->ctx;
   double tp = g_prof ? now_s() : 0;
   constexpr int NSEG = PC_ORDER_SEGS, NB = PC_ORDER_BINS;
-  struct Seg { uint32_t n, max_a, max_b; unsigned long long lcs_blocks; } seg[NSEG];
+  struct Seg { uint32_t n, max_a, max_b, max_t; unsigned long long lcs_blocks; } seg[NSEG];
   memset(seg, 0, sizeof seg);
   /* device buffer: [job order | list of the jobs the bit-parallel kernel leaves to the wavefront kernel | one counter per
    * segment | (device ordering only) keys, histogram work area, segment statistics] */
@@ -298,7 +298,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
     CU(cudaMemcpyAsync(h_invalid, d_work + 3 * NB + 1, 4, cudaMemcpyDeviceToHost, st->s));
     CU(cudaStreamSynchronize(st->s));
     if (*h_invalid) return fail(PC_E_ARG, "%s", "pc_submit: a job references bytes outside its buffers (or has an unknown op)");
-    for (int sg = 0; sg < NSEG; ++sg) { seg[sg].n = h_seg[sg].n; seg[sg].max_a = h_seg[sg].max_a; seg[sg].max_b = h_seg[sg].max_b; seg[sg].lcs_blocks = h_seg[sg].lcs_blocks; }
+    for (int sg = 0; sg < NSEG; ++sg) { seg[sg].n = h_seg[sg].n; seg[sg].max_a = h_seg[sg].max_a; seg[sg].max_b = h_seg[sg].max_b; seg[sg].max_t = h_seg[sg].max_t; seg[sg].lcs_blocks = h_seg[sg].lcs_blocks; }
     PROF(3, tp);
   } else {
     if (order.reserve(nsel + 1)) return PC_E_NOMEM;
@@ -314,6 +314,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
       const int sg = (int)j.op * 4 + cls;
       Seg &S = seg[sg];
       ++S.n; S.max_a = std::max(S.max_a, j.a_len); S.max_b = std::max(S.max_b, j.b_len);
+      if (j.op == PC_OP_BORDERS) S.max_t = std::max(S.max_t, pc_borders_window(j));
       key[q] = (uint16_t)(sg * 64 + (63 - lg));
       ++bins[key[q] + 1];
     }
@@ -379,7 +380,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
     } else if (op == PC_OP_GAP && cls < 3) {
       pc_launch_gap_pairs(cls, B, (int)max_l1, st->s, c->sm_count);
     } else if (op == PC_OP_BORDERS && cls < 3) {
-      pc_launch_borders_packed(cls, B, (int)std::min<long long>(max_l1, PC_BORDERS_FAST_MAX_T), st->s, c->sm_count);
+      pc_launch_borders_packed(cls, B, (int)std::min<uint32_t>(seg[sg].max_t, PC_BORDERS_FAST_MAX_T), st->s, c->sm_count);
     } else if (op == PC_OP_BORDERS) {
       // taller than the packed classes: row-chunked packed sweep; what does not fit 16-bit scores goes to the wavefront kernel
       pc_launch_borders_chunked(B, d_slow + i, d_slow_count + sg, st->s, c->sm_count);

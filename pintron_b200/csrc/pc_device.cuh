@@ -38,7 +38,11 @@ struct PcDevBatch {
 #define PC_ORDER_BINS (PC_ORDER_SEGS * 64)
 #define PC_LCS_TPB 256
 #define PC_LCS_MAX_S2 4096
-struct PcSegStat { uint32_t n, max_a, max_b, pad; unsigned long long lcs_blocks; };
+struct PcSegStat { uint32_t n, max_a, max_b, max_t; unsigned long long lcs_blocks; };      /* max_t: widest BORDERS window */
+__host__ __device__ inline uint32_t pc_borders_window(const pc_job &j) {
+  const unsigned long long tw = (unsigned long long)j.a_len + (uint32_t)j.p0;
+  return (uint32_t)(tw < j.b_len ? tw : j.b_len);
+}
 
 #define PC_BORDERS_FAST_MAX_T 1024
 /* Kernel class of a job inside its op (shared by the host and the device ordering): GAP and BORDERS jobs that fit the
