@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""bench.py — est-fact hot path on synthetic data of BASELINE.json's shapes (default C4: 2 Mbp multi-gene locus x ESTs and
-mRNAs; --workload C3: 200 kbp x ESTs of 300-800 nt), one rank per GPU.
+"""bench.py — est-fact hot path on synthetic data of BASELINE.json's shapes (default C3: 200 kbp genomic region x ESTs of
+300-800 nt, 100 000 per GPU; --workload C4: 2 Mbp multi-gene locus x ESTs and mRNAs), one rank per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--workload C4|C3]     our arm (CUDA through the C ABI)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--workload C3|C4]     our arm (CUDA through the C ABI)
   python bench.py --impl reference ...                                                   the reference est-fact on the host cores
 
 Two legs per run, ESTs/s as the metric:
@@ -168,17 +168,22 @@ def cpu_baseline_sample(workload="C3", seconds_budget=20.0):
             "sample": f"{n} {workload} ESTs, {cores} est-fact processes (one per core, {per_core} ESTs each), wall {sec:.2f} s"}
 
 
+def _log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C4", choices=["C3", "C4"],
-                    help="synthetic shape (pintron_b200/synth.py).  C4 = BASELINE.json configs[3], the one quoted at 1/2/4/8 B200 "
-                         "(1 M ESTs over 8 GPUs = 125 000 per GPU); C3 = configs[2] (100 000 ESTs on one GPU)")
+    ap.add_argument("--workload", default="C3", choices=["C3", "C4"],
+                    help="synthetic shape (pintron_b200/synth.py).  C3 = BASELINE.json configs[2] (200 kbp x 100 000 ESTs per GPU), the default: "
+                         "it finishes in two minutes.  C4 = configs[3] (2 Mbp multi-gene locus, ESTs + mRNAs): a few reads per thousand "
+                         "send the embedding enumeration (ours and the reference's) into tens of seconds, so a run takes many minutes")
     ap.add_argument("--reads", type=int, default=None, help="ESTs per GPU per step, device leg (default 20000 for C3, 10000 for C4)")
-    ap.add_argument("--e2e-reads", type=int, default=None, help="ESTs per GPU per step, whole-program leg (default 100000 C3, 125000 C4)")
+    ap.add_argument("--e2e-reads", type=int, default=None, help="ESTs per GPU per step, whole-program leg (default 100000 C3, 30000 C4)")
     ap.add_argument("--e2e-max-steps", type=int, default=2)
     ap.add_argument("--e2e-max-warmup", type=int, default=1)
     ap.add_argument("--ref-reads-per-core", type=int, default=None, help="reference arm: ESTs per host core per step (default 200 C3, 150 C4)")
@@ -188,7 +193,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     c4 = args.workload == "C4"
     args.reads = args.reads or (10000 if c4 else 20000)
-    args.e2e_reads = args.e2e_reads or (125000 if c4 else 100000)
+    args.e2e_reads = args.e2e_reads or (30000 if c4 else 100000)
     args.ref_reads_per_core = args.ref_reads_per_core or (150 if c4 else 200)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -225,7 +230,11 @@ def main():
     open(os.path.join(cap_dir, "genomic.txt"), "wb").write(synth.genome_fasta())
     open(os.path.join(cap_dir, "ests.txt"), "wb").write(ests_fasta_parallel(args.workload, args.reads * world, rank * args.reads, args.reads,
                                                                              procs=max(1, cores // world - 1)))
+    _log("inputs written; capture run of est-fact")
     cap = replay.capture(exe, cap_dir, threads=threads, device=local)
+    _log("capture done; merging")
+    for l in getattr(replay.capture, "last_log", []):
+        _log("  est-fact: " + l.strip()[:400])
     arena, jobs, var_bytes, n_batches = replay.merge(cap)
     shutil.rmtree(cap_dir, ignore_errors=True)
     # the genome bytes the device holds are est-fact's: N tails stripped (io-multifasta.c:830); for synthetic ACGT genomes = as is
@@ -236,6 +245,7 @@ def main():
     seed_bytes = int(jobs["a_len"][seed_sel].sum())
     jobs_per_op = {nm: int((jobs["op"] == i).sum()) for i, nm in enumerate(replay.OP_NAMES) if (jobs["op"] == i).any()}
 
+    _log(f"merged {len(jobs)} jobs from {n_batches} batches, arena {len(arena) >> 20} MB")
     cu = pintron_b200.Cuda(local)
     L = cu.L
     cu.genome_upload(synth.genome, 15, 0.2)
@@ -281,7 +291,9 @@ def main():
             ms.append(e0.elapsed_time(e1))
         return ms
 
+    _log("device warm-up")
     timed(step_device, args.warmup)
+    _log("device warm-up done")
     st0 = d_res.view(n, PC_RES_INTS)[:, 0]
     PC_E_OUTCAP = -2      # a SEED job whose triples did not fit: est-fact re-issues it with the reported capacity (both are in the stream)
     assert int(((st0 != 0) & (st0 != PC_E_OUTCAP)).sum().item()) == 0, "a job failed on the device"
@@ -330,6 +342,7 @@ def main():
     L.pc_stream_reset_timers(cu.st)
     launches0 = cu.launch_count()
     ms_dev = timed(step_device, args.steps)
+    _log("device leg timed")
     launches = cu.launch_count() - launches0
     import ctypes as C
     op_names = ["ALIGN", "KBAND", "EDIT", "BORDERS", "GAP", "AFFIX", "SUFCUT", "PRECUT", "LCS", "SEED"]
@@ -349,8 +362,10 @@ def main():
     else:
         # one run takes seconds to tens of seconds: W and K are capped for this leg (stated in the JSON line)
         e2e_warmup, e2e_steps = min(args.warmup, args.e2e_max_warmup), min(args.steps, args.e2e_max_steps)
+        _log("whole-program leg")
         for _ in range(e2e_warmup):
             step_program()
+        _log("whole-program warm-up done")
         barrier()
         ms_e2e = [step_program() * 1e3 for _ in range(e2e_steps)]
         barrier()
@@ -410,6 +425,7 @@ def main():
                   for k in dp_ops if k in op_ms and op_ms[k] > 0}
 
     if rank == 0:
+        _log("cpu baseline sample")
         cpu = None if args.no_cpu_baseline else cpu_baseline_sample(args.workload)
         line = {
             "metric": METRIC, "value": value, "unit": "ESTs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -20,7 +20,7 @@ def capture(exe, workdir, threads=None, device=None):
     """Run est-fact in `workdir` with PC_CAPTURE set; returns the capture file path."""
     cap = os.path.join(workdir, "jobs.capture")
     env = dict(os.environ, PC_CAPTURE=cap)
-    cmd = [exe, "--quiet", "--no-aux-outputs"]
+    cmd = [exe, "--no-aux-outputs"]
     if threads:
         cmd += ["--threads", str(threads)]
     if device is not None:
@@ -28,6 +28,7 @@ def capture(exe, workdir, threads=None, device=None):
     p = subprocess.run(cmd, cwd=workdir, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     if p.returncode != 0:
         raise RuntimeError("est-fact (capture run) failed: " + p.stderr.decode("latin1")[-1000:])
+    capture.last_log = [l for l in p.stderr.decode("latin1").splitlines() if "scheduler:" in l or "@Timer Total" in l or "thread-seconds" in l]
     return cap
 
 

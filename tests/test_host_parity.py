@@ -87,3 +87,12 @@ def test_small_exon_scan_matches_the_reference_loops(cpu_bin):
     assert p.returncode == 0, p.stderr
     assert p.stdout.startswith("ok 6000 hits "), p.stdout
     assert int(p.stdout.split()[-1]) > 100
+
+
+def test_bit_parallel_core_matches_the_port(cpu_bin):
+    """pintron_b200/csrc/myers_core.h (what every thread of k_myers runs) compiled for the host: 30 000 random and
+    mutated pairs, 1 to 5 words per column, strided Peq layout, unsupported bytes reported — against po_edit."""
+    exe = os.path.join(os.path.dirname(cpu_bin), "myers_fuzz")
+    p = subprocess.run([exe, "30000"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.startswith("ok 30000"), p.stdout
