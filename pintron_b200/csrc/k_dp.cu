@@ -711,7 +711,6 @@ void pc_launch_borders_packed(int cls, const PcDevBatch &B, int tcap, cudaStream
 
 // BORDERS jobs outside the packed classes (taller than 256 rows, or a window above PC_BORDERS_FAST_MAX_T columns)
 void pc_launch_borders_chunked(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count) {
-  cudaMemsetAsync(slow_count, 0, sizeof(uint32_t), s);
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_borders_chunked, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int needed = (B.n + 3) / 4;

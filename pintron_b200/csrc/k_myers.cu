@@ -93,10 +93,9 @@ void launch_myers(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count
 }  // namespace
 
 // op = PC_OP_EDIT or PC_OP_KBAND.  cls = length class of the segment (pc_job_class: shorter string <= 64 / 128 / 320
-// letters -> 1 / 2 / 5 words per column).  slow_list (B.n entries) / slow_count (zeroed here) receive the job indices
+// letters -> 1 / 2 / 5 words per column).  slow_list (B.n entries) / slow_count (zeroed by the caller) receive the job indices
 // left for the generic kernel.
 void pc_launch_myers(int op, int cls, const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count) {
-  cudaMemsetAsync(slow_count, 0, sizeof(uint32_t), s);
   if (op == PC_OP_EDIT) {
     if (cls == 0) launch_myers<PC_OP_EDIT, 1>(B, slow_list, slow_count, s, sm_count);
     else if (cls == 1) launch_myers<PC_OP_EDIT, 2>(B, slow_list, slow_count, s, sm_count);

@@ -281,7 +281,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
   if (st->idx.reserve((2 * idx_words + 64 + extra_words) * 4 + 256)) return PC_E_NOMEM;
   uint32_t *d_order = (uint32_t *)st->idx.p, *d_slow = d_order + idx_words, *d_slow_count = d_order + 2 * idx_words;
   st->last_slow_count = d_slow_count;
-  if (g_prof) CU(cudaMemsetAsync(d_slow_count, 0, 64 * sizeof(uint32_t), st->s));
+  CU(cudaMemsetAsync(d_slow_count, 0, 64 * sizeof(uint32_t), st->s));      /* every segment's hand-over counter, once per batch */
   PinBuf &order = st->pin_idx;
   if (on_device) {
     // millions of jobs already in HBM: key, histogram, scan and scatter run there (k_order.cu); the host only reads
