@@ -220,7 +220,8 @@ def main():
     if not os.path.exists(exe):
         raise SystemExit("bench.py: pintron_b200/bin/est-fact is not built (python __graft_entry__.py)")
     cores = os.cpu_count() or 1
-    threads = max(1, (cores // world) * 3 // 4)
+    per_gpu = max(1, cores // world)
+    threads = per_gpu if per_gpu <= 4 else per_gpu * 3 // 4      # est-fact worker threads per GPU (few cores per GPU: use them all)
 
     # ---- the device workload: the job stream of a real est-fact run over this rank's R ESTs, merged into one batch ----
     from pintron_b200 import replay
@@ -454,7 +455,7 @@ def main():
                                          "h2d_bytes_per_step": int(len(arena) + jobs.nbytes),
                                          "d2h_bytes_per_step": int(n * PC_RES_INTS * 4 + var_bytes),
                                          "what": "the `value` batch submitted from pinned host buffers through pc_submit"},
-            "gpu_launches": int(launches) + args.steps * int(e2e_info.get("launches") or 0), "clocks": sampler.summary(),
+            "gpu_launches": int(launches) + (0 if args.no_e2e else min(args.steps, args.e2e_max_steps)) * int(e2e_info.get("launches") or 0), "clocks": sampler.summary(),
             "int_alu_peak_tlaneops": int_peak / 1e12,
         }
         print(json.dumps(line))
