@@ -152,6 +152,7 @@ static void *writer_main(void *arg) {
 static FILE *open_out(const char *name) {
   FILE *f = fopen(name, "w");
   if (!f) { fprintf(stderr, "* FATAL Cannot create file %s! Terminating\n", name); exit(1); }
+  setvbuf(f, NULL, _IOFBF, (size_t)4 << 20);       /* one write() per 4 MB: the writer thread emits hundreds of MB record by record */
   return f;
 }
 
@@ -200,11 +201,21 @@ int main(int argc, char **argv) {
     it->fwd = ests[i];       /* strand / reverse-complement / polyA masking happen in est_task, on the worker threads */
   }
 
-  /* EST batcher: inside windows of 262 144 input records the ESTs are dispatched longest first, so the ESTs in flight
-   * together (and the jobs of one device batch) have similar sizes; the writer still emits input order. */
+  /* EST batcher: inside windows of input records the ESTs are dispatched longest first, so the ESTs in flight together
+   * (and the jobs of one device batch) have similar sizes; the writer still emits input order, so it can only stream a
+   * window out once that window is done.  Reads of similar length (ESTs): windows of 32 768, the output streams while
+   * later windows run.  Mixed inputs (a few long mRNAs carry most of the work): 262 144, so that the long ones all
+   * start early and the threads run dry together. */
+  size_t WIN = 262144;
+  {
+    size_t maxl = 0; double sum = 0;
+    for (size_t i = 0; i < nest; ++i) { const size_t l = strlen(ests[i].seq); sum += (double)l; if (l > maxl) maxl = l; }
+    if (nest && (double)maxl <= 4.0 * sum / (double)nest) WIN = 32768;
+    const char *ov = getenv("EF_WINDOW");            /* experiments only */
+    if (ov && atol(ov) > 0) WIN = (size_t)atol(ov);
+  }
   uint32_t *order = malloc(sizeof(uint32_t) * (nest ? nest : 1));
   {
-    const size_t WIN = 262144;
     uint32_t cnt[65];
     for (size_t w0 = 0; w0 < nest; w0 += WIN) {
       const size_t w1 = MIN2(nest, w0 + WIN);
