@@ -180,8 +180,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=["C3", "C4"],
                     help="synthetic shape (pintron_b200/synth.py).  C3 = BASELINE.json configs[2] (200 kbp x 100 000 ESTs per GPU), the default: "
-                         "it finishes in two minutes.  C4 = configs[3] (2 Mbp multi-gene locus, ESTs + mRNAs): a few reads per thousand "
-                         "send the embedding enumeration (ours and the reference's) into tens of seconds, so a run takes many minutes")
+                         "it finishes in two minutes.  C4 = configs[3] (2 Mbp multi-gene locus, ESTs + mRNAs): about one read per thousand is an "
+                         "mRNA with a thousand candidate embeddings and end exons of several kbp (a minute each for the reference), so a run "
+                         "is longer and noisier")
     ap.add_argument("--reads", type=int, default=None, help="ESTs per GPU per step, device leg (default 20000 for C3, 10000 for C4)")
     ap.add_argument("--e2e-reads", type=int, default=None, help="ESTs per GPU per step, whole-program leg (default 100000 C3, 30000 C4)")
     ap.add_argument("--e2e-max-steps", type=int, default=2)
