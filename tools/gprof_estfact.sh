@@ -1,5 +1,5 @@
 #!/bin/bash
-# Sampling profile (tools/ef_prof.c) of the shipped host code, built as pintron_b200/bin/est-fact-pg, one worker thread.
+# Sampling profile (tools/ef_prof.c) of the shipped host code, one worker thread.  Build first: make -C pintron_b200/host prof
 #   WORKLOAD=C4 tools/gprof_estfact.sh READS [--lines]
 READS=${1:-5000}
 W=${WORKLOAD:-C4}
