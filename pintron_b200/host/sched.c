@@ -522,6 +522,10 @@ static void *worker_main(void *arg) {
     const size_t per_fiber = 4096;
     g->arena_cap = MAX2((size_t)1 << 20, (size_t)g->nfibers * per_fiber);
     g->jobs_cap = MAX2(4096, g->nfibers * 32);
+    {
+      const char *kb = getenv("EF_STAGING_KB");        /* tests: tiny staging, so that back-pressure and growth both happen */
+      if (kb && atol(kb) > 0) { g->arena_cap = (size_t)atol(kb) << 10; g->jobs_cap = (int)MAX2(64, atol(kb)); }
+    }
     g->res_cap = (size_t)g->jobs_cap * PC_RES_INTS;
     g->var_cap = g->arena_cap;
     const size_t jobs_b = (sizeof(pc_job) * (size_t)g->jobs_cap + 255u) & ~(size_t)255u, res_b = g->res_cap * sizeof(int32_t);

@@ -25,9 +25,11 @@ def unpack(case, dst):
     return json.load(open(os.path.join(GOLD, case, "expected.json")))
 
 
-def run(binary, cwd, *args, timeout=1200):
-    p = subprocess.run([binary, *args], cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+def run(binary, cwd, *args, timeout=1200, env=None):
+    p = subprocess.run([binary, *args], cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout, env=env)
     assert p.returncode == 0, p.stderr.decode("latin1")[-2000:]
+    with open(os.path.join(cwd, "stderr.txt"), "w") as f:
+        f.write(p.stderr.decode("latin1"))
     return p.stderr.decode("latin1")
 
 
@@ -39,9 +41,9 @@ def md5s(cwd):
     return out
 
 
-def check_case(binary, case, tmp_path, *args):
+def check_case(binary, case, tmp_path, *args, env=None):
     exp = unpack(case, str(tmp_path))
-    run(binary, str(tmp_path), *args)
+    run(binary, str(tmp_path), *args, env=env)
     got = md5s(str(tmp_path))
     for f in FILES:
         if got[f] != exp[f]:

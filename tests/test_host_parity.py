@@ -96,3 +96,19 @@ def test_bit_parallel_core_matches_the_port(cpu_bin):
     p = subprocess.run([exe, "30000"], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr
     assert p.stdout.startswith("ok 30000"), p.stdout
+
+
+def test_back_pressure_and_staging_growth_keep_the_bytes(cpu_bin, tmp_path):
+    """The batcher never grows its staging while a batch is being gathered: ESTs whose requests do not fit wait for the next
+    batch, and only a single EST larger than an empty batch makes the buffers grow.  With 1 KB of staging both happen
+    all the time; the output must not change."""
+    env = dict(os.environ, EF_STAGING_KB="1")
+    for case in ("test-AMBN", "test-CPB2"):
+        d = tmp_path / case
+        d.mkdir()
+        U.check_case(cpu_bin, case, str(d), "--threads", "3", "--fibers", "64", env=env)
+    log = (tmp_path / "test-CPB2" / "stderr.txt").read_text(errors="replace") if (tmp_path / "test-CPB2" / "stderr.txt").exists() else ""
+    if log:
+        import re
+        m = re.search(r"(\d+) fiber deferrals, (\d+) staging re-allocations", log)
+        assert m and int(m.group(1)) > 0 and int(m.group(2)) > 0, log[-400:]
