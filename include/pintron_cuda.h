@@ -120,6 +120,10 @@ int pc_longest_common_factor_batch(pc_stream *, const uint8_t *arena, size_t, co
 int pc_build_vertex_set_batch(pc_stream *, const uint8_t *arena, size_t, const pc_job *, int, int32_t *res, uint8_t *triples, size_t);
 
 /* ---- instrumentation ----------------------------------------------------------------------------- */
+/* Environment (read once when the library is loaded): PC_PROFILE=1 makes pc_debug_dump() print host-side phase times,
+ * device time / jobs per op, hand-over and re-run counts; PC_CAPTURE=<file> appends every batch given to pc_submit to
+ * <file> (u32 njobs, u64 arena_bytes, jobs, arena) — bench.py replays such a recording as its device workload and
+ * tools/check_capture.py checks every recorded job against the oracle. */
 uint64_t pc_launch_count(void);                  /* kernels launched by this library in this process */
 /* Device time (ms, CUDA events on the stream) and launches of the kernels of `op` since the last reset. */
 int pc_stream_op_time(pc_stream *st, int op, double *ms, uint64_t *launches);
