@@ -35,6 +35,44 @@ EXPORTS = ["pc_last_error", "pc_device_count", "pc_ctx_create", "pc_ctx_destroy"
            "pc_refine_borders_batch", "pc_gap_alignment_batch", "pc_longest_affix_batch", "pc_best_cut_batch",
            "pc_longest_common_factor_batch", "pc_build_vertex_set_batch", "pc_launch_count", "pc_stream_op_time",
            "pc_stream_reset_timers", "pc_stream_enable_timers", "pc_stream_cuda_stream", "pc_measure_int_peak"]
+ENGINE_EXPORTS = ["pc_engine_create", "pc_engine_destroy", "pc_engine_gpu_count", "pc_engine_backend", "pc_engine_open",
+                  "pc_engine_resize_lane", "pc_engine_close", "pc_engine_enable_timers", "pc_engine_segment_count",
+                  "pc_engine_segment_fd", "pc_engine_segment_base", "pc_submit_parts"]
+PCE_MAX_LANES, PCE_MAX_SESSION_LANES = 512, 256
+PCE_FREE, PCE_IDLE, PCE_POSTED, PCE_RUNNING, PCE_DONE = range(5)
+
+
+class pc_part(C.Structure):
+    _fields_ = [("arena", C.c_void_p), ("arena_bytes", C.c_size_t), ("jobs", C.c_void_p), ("njobs", C.c_int),
+                ("res", C.c_void_p), ("var_out", C.c_void_p), ("var_out_bytes", C.c_size_t)]
+
+
+class pc_session_req(C.Structure):
+    _fields_ = [("gpu", C.c_int), ("genome", C.c_char_p), ("genome_len", C.c_size_t), ("word_len", C.c_int),
+                ("depth_rate", C.c_double), ("nlanes", C.c_int), ("arena_cap", C.c_uint64), ("var_cap", C.c_uint64),
+                ("jobs_cap", C.c_uint32)]
+
+
+class pc_session_info(C.Structure):
+    _fields_ = [("session", C.c_uint32), ("gpu", C.c_int), ("nlanes", C.c_int), ("lane", C.c_uint32 * PCE_MAX_SESSION_LANES)]
+
+
+class pc_session_stats(C.Structure):
+    _fields_ = [("batches", C.c_uint64), ("lanes_merged", C.c_uint64), ("jobs", C.c_uint64), ("launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("retries", C.c_uint64), ("busy_s", C.c_double),
+                ("op_ms", C.c_double * 10)]
+
+
+class pce_lane(C.Structure):          # include/pintron_engine.h, 128 bytes
+    _fields_ = [("state", C.c_uint32), ("rc", C.c_int32), ("session", C.c_uint32), ("njobs", C.c_uint32),
+                ("arena_len", C.c_uint64), ("var_len", C.c_uint64), ("seg", C.c_uint32), ("jobs_cap", C.c_uint32),
+                ("arena_off", C.c_uint64), ("arena_cap", C.c_uint64), ("jobs_off", C.c_uint64), ("res_off", C.c_uint64),
+                ("var_off", C.c_uint64), ("var_cap", C.c_uint64), ("batches", C.c_uint64), ("jobs_total", C.c_uint64),
+                ("pad", C.c_uint8 * 24)]
+
+
+assert C.sizeof(pce_lane) == 128
+PCE_LANES_OFFSET = 128                # pce_hdr: magic, version, doorbell, sleepers, pad to 128, then the lanes
 
 
 def library_path():
@@ -73,6 +111,19 @@ def load_library():
     L.pc_stream_cuda_stream.argtypes = [C.c_void_p]
     L.pc_measure_int_peak.restype = C.c_double
     L.pc_measure_int_peak.argtypes = [C.c_void_p]
+    L.pc_submit_parts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(pc_part), C.c_int]
+    L.pc_engine_create.restype = C.c_void_p
+    L.pc_engine_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_size_t]
+    L.pc_engine_destroy.argtypes = [C.c_void_p]
+    L.pc_engine_backend.restype = C.c_char_p
+    L.pc_engine_open.argtypes = [C.c_void_p, C.POINTER(pc_session_req), C.POINTER(pc_session_info)]
+    L.pc_engine_resize_lane.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32]
+    L.pc_engine_close.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(pc_session_stats)]
+    L.pc_engine_enable_timers.argtypes = [C.c_void_p, C.c_int]
+    L.pc_engine_segment_count.argtypes = [C.c_void_p, C.c_int]
+    L.pc_engine_segment_fd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+    L.pc_engine_segment_base.restype = C.c_void_p
+    L.pc_engine_segment_base.argtypes = [C.c_void_p, C.c_int, C.c_int]
     return L
 
 
@@ -160,6 +211,19 @@ class Cuda:
         self._check(self.L.pc_stream_sync(self.st), "pc_stream_sync")
         return res, var
 
+    def run_parts(self, batches):
+        """Several Batches as ONE device batch (pc_submit_parts: what the engine does with the lanes it merges)."""
+        keep, parts = [], (pc_part * len(batches))()
+        for k, b in enumerate(batches):
+            arena, jobs = b.arrays()
+            res = np.zeros((len(jobs), PC_RES_INTS), dtype=np.int32)
+            var = np.zeros(max(b.var_bytes, 1), dtype=np.uint8)
+            keep.append((arena, jobs, res, var))
+            parts[k] = pc_part(arena.ctypes.data, len(b.arena), jobs.ctypes.data, len(jobs), res.ctypes.data, var.ctypes.data, b.var_bytes)
+        self._check(self.L.pc_submit_parts(self.st, None, parts, len(batches)), "pc_submit_parts")
+        self._check(self.L.pc_stream_sync(self.st), "pc_stream_sync")
+        return [(k[2], k[3]) for k in keep]
+
     def launch_count(self):
         return int(self.L.pc_launch_count())
 
@@ -224,3 +288,72 @@ class Cuda:
         assert res[0, 0] == 0, res[0]
         tri = var[:12 * res[0, 1]].view(np.int32).reshape(-1, 3)
         return [tuple(int(x) for x in r) for r in tri]
+
+
+class Engine:
+    """An in-process batch engine (include/pintron_engine.h) driven from Python: tests and bench.py post lanes the way
+    the est-fact host does (pce_post / pce_wait are re-stated with plain stores and polling: no futex from Python)."""
+
+    def __init__(self, devices=(0,), segment_bytes=0):
+        self.L = load_library()
+        arr = (C.c_int * len(devices))(*devices)
+        self.e = self.L.pc_engine_create(arr, len(devices), segment_bytes)
+        if not self.e:
+            raise RuntimeError("pc_engine_create failed: " + self.L.pc_last_error().decode())
+
+    def open(self, genome, nlanes, arena_cap, jobs_cap, var_cap, gpu=0, word_len=15, depth_rate=0.2):
+        req = pc_session_req(gpu, genome, len(genome), word_len, depth_rate, nlanes, arena_cap, var_cap, jobs_cap)
+        info = pc_session_info()
+        if self.L.pc_engine_open(self.e, C.byref(req), C.byref(info)):
+            raise RuntimeError("pc_engine_open failed: " + self.L.pc_last_error().decode())
+        return Session(self, info)
+
+    def close(self):
+        if self.e:
+            self.L.pc_engine_destroy(self.e)
+            self.e = None
+
+
+class Session:
+    def __init__(self, eng, info):
+        self.eng, self.id, self.gpu = eng, info.session, info.gpu
+        self.lanes = [int(info.lane[k]) for k in range(info.nlanes)]
+        self.hdr = eng.L.pc_engine_segment_base(eng.e, self.gpu, 0)
+
+    def lane(self, k):
+        return pce_lane.from_address(self.hdr + PCE_LANES_OFFSET + 128 * self.lanes[k])
+
+    def _view(self, seg, off, nbytes, dtype=np.uint8):
+        base = self.eng.L.pc_engine_segment_base(self.eng.e, self.gpu, seg)
+        return np.ctypeslib.as_array(C.cast(base + off, C.POINTER(C.c_uint8)), shape=(nbytes,)).view(dtype)
+
+    def post(self, k, batch):
+        """Copy a Batch into lane k and post it (the doorbell is bumped; the engine polls with a 20 ms timeout at worst)."""
+        l = self.lane(k)
+        arena, jobs = batch.arrays()
+        assert len(batch.arena) <= l.arena_cap and len(jobs) <= l.jobs_cap and batch.var_bytes <= l.var_cap, "lane too small"
+        self._view(l.seg, l.arena_off, max(len(batch.arena), 1))[:len(batch.arena)] = arena[:len(batch.arena)]
+        self._view(l.seg, l.jobs_off, jobs.nbytes or 44)[:jobs.nbytes] = jobs.view(np.uint8)
+        l.njobs, l.arena_len, l.var_len = len(jobs), len(batch.arena), batch.var_bytes
+        l.state = PCE_POSTED
+        bell = C.c_uint32.from_address(self.hdr + 8)
+        bell.value = bell.value + 1
+
+    def wait(self, k, njobs, var_bytes, timeout=120.0):
+        import time
+        l = self.lane(k)
+        t0 = time.time()
+        while l.state != PCE_DONE:
+            if time.time() - t0 > timeout:
+                raise TimeoutError("engine did not finish the lane")
+            time.sleep(0.0005)
+        if l.rc:
+            raise RuntimeError(f"engine batch failed ({l.rc})")
+        res = self._view(l.seg, l.res_off, njobs * PC_RES_INTS * 4, np.int32).reshape(njobs, PC_RES_INTS).copy()
+        var = self._view(l.seg, l.var_off, max(var_bytes, 1)).copy()
+        return res, var
+
+    def close(self):
+        st = pc_session_stats()
+        self.eng.L.pc_engine_close(self.eng.e, self.id, C.byref(st))
+        return st

@@ -396,7 +396,8 @@ __global__ void __launch_bounds__(128) k_borders_packed(PcDevBatch B, int tcap) 
 __global__ void __launch_bounds__(128) k_borders_chunked(PcDevBatch B, uint32_t *slow_list, uint32_t *slow_count) {
   constexpr uint32_t ONE2 = 0x00010001u;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int warp_id = blockIdx.x * 4 + wib, nwarps = gridDim.x * 4;
+  const int warp_id = blockIdx.x * 4 + wib, nwarps = pc_active_warps(B, gridDim.x * 4);
+  if (warp_id >= nwarps) return;
   WarpPool wp = pc_warp_pool(B, warp_id);
   for (int q = warp_id; q < B.n; q += nwarps) {
     wp.used = 0;
@@ -492,15 +493,13 @@ template <int LANES>
 void launch_borders_packed(const PcDevBatch &B, int tcap, cudaStream_t s, int sm_count) {
   constexpr int G = 32 / LANES;
   const size_t sh = (size_t)4 * G * ((tcap + 1) + 2 * (8 * LANES + 1)) * sizeof(uint32_t);
-  static bool attr_done = false;
-  if (!attr_done) { cudaFuncSetAttribute(k_borders_packed<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_done = true; }
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_borders_packed<LANES>, 128, sh) != cudaSuccess || per_sm < 1) per_sm = 1;
+  pc_smem_optin((const void *)k_borders_packed<LANES>, 100 * 1024);
+  const int per_sm = pc_cached_occupancy((const void *)k_borders_packed<LANES>, 128, sh);
   const int needed = (B.n + 4 * G - 1) / (4 * G);
   int grid = needed < sm_count * per_sm ? needed : sm_count * per_sm;
   if (grid < 1) grid = 1;
   k_borders_packed<LANES><<<grid, 128, sh, s>>>(B, tcap);
-  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(1);
 }
 
 // ---- DP E: find_longest_affix (src/factorization-refinement.c:1134-1172) ----------------------------------
@@ -669,7 +668,8 @@ template <int OP>
 __global__ void __launch_bounds__(PC_WARPS_PER_CTA * 32) k_warp_per_job(PcDevBatch B) {
   __shared__ uint32_t smem[PC_WARPS_PER_CTA][PC_SMEM_INTS_PER_WARP];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int nwarps = gridDim.x * PC_WARPS_PER_CTA;
+  const int nwarps = pc_active_warps(B, gridDim.x * PC_WARPS_PER_CTA);
+  if (blockIdx.x * PC_WARPS_PER_CTA + wib >= nwarps) return;      // no block-wide barrier in this kernel: a warp may leave
   // jobs are sorted heaviest first; deal them round-robin over the resident warps
   WarpPool wp = pc_warp_pool(B, blockIdx.x * PC_WARPS_PER_CTA + wib);
   const int njobs = B.n_dev ? (int)*B.n_dev : B.n;
@@ -694,10 +694,11 @@ void launch_wpj(const PcDevBatch &B, cudaStream_t s, int sm_count) {
   int grid = ctas_needed < resident ? ctas_needed : resident;
   if (B.max_warps > 0 && grid > (B.max_warps + PC_WARPS_PER_CTA - 1) / PC_WARPS_PER_CTA)
     grid = (B.max_warps + PC_WARPS_PER_CTA - 1) / PC_WARPS_PER_CTA;
+  if (grid < 1) grid = 1;
   PcDevBatch C = B;
-  C.slots = grid * PC_WARPS_PER_CTA;
+  C.slots = (B.max_warps > 0 && B.max_warps < grid * PC_WARPS_PER_CTA) ? B.max_warps : grid * PC_WARPS_PER_CTA;
   k_warp_per_job<OP><<<grid, PC_WARPS_PER_CTA * 32, 0, s>>>(C);
-  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(1);
 }
 
 }  // namespace
@@ -711,16 +712,15 @@ void pc_launch_borders_packed(int cls, const PcDevBatch &B, int tcap, cudaStream
 
 // BORDERS jobs outside the packed classes (taller than 256 rows, or a window above PC_BORDERS_FAST_MAX_T columns)
 void pc_launch_borders_chunked(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count) {
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_borders_chunked, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int per_sm = pc_cached_occupancy((const void *)k_borders_chunked, 128, 0);
   const int needed = (B.n + 3) / 4;
   int grid = needed < sm_count * per_sm ? needed : sm_count * per_sm;
   if (B.max_warps > 0 && grid > (B.max_warps + 3) / 4) grid = (B.max_warps + 3) / 4;
   if (grid < 1) grid = 1;
   PcDevBatch C = B;
-  C.slots = grid * 4;
+  C.slots = (B.max_warps > 0 && B.max_warps < grid * 4) ? B.max_warps : grid * 4;
   k_borders_chunked<<<grid, 128, 0, s>>>(C, slow_list, slow_count);
-  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(1);
 }
 
 void pc_launch_dp(int op, const PcDevBatch &B, cudaStream_t s, int sm_count) {
@@ -760,7 +760,7 @@ double pc_int_peak_run(cudaStream_t s, int sm_count, float *ms_out) {
   k_int_peak<<<grid, 256, 0, s>>>(iters, 3, 1 << 30, sink);
   cudaEventRecord(e1, s);
   cudaEventSynchronize(e1);
-  __atomic_fetch_add(&g_pc_launches, 2ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(2);
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
   if (ms_out) *ms_out = ms;

@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(128) k_gap_pairs(PcDevBatch B, int mcap) {
   const int k = lane % LANES, grp = lane / LANES;
   uint32_t *codes = sh_codes + (size_t)(wib * G + grp) * (mcap + 1);
   const int npairs = (B.n + 1) >> 1;
-  const int warp_id = blockIdx.x * 4 + wib, ngroups = gridDim.x * 4 * G;
+  const int warp_id = blockIdx.x * 4 + wib, nwarps = pc_active_warps(B, gridDim.x * 4), ngroups = nwarps * G;
+  if (warp_id >= nwarps) return;                          // retry rounds: fewer scratch slots than launched warps (no block-wide sync below)
   WarpPool wp = pc_warp_pool(B, warp_id);
   const unsigned long long gshare = (wp.size / G) & ~255ull;
   uint8_t *gbase = wp.base + gshare * grp;
@@ -224,18 +225,16 @@ void launch_pairs(const PcDevBatch &B, int mcap, cudaStream_t s, int sm_count) {
   const int npairs = (B.n + 1) / 2;
   const int ctas_needed = (npairs + 4 * G - 1) / (4 * G);
   const size_t sh = (size_t)4 * G * (mcap + 1) * sizeof(uint32_t);
-  static bool attr_done = false;
-  if (!attr_done) { cudaFuncSetAttribute(k_gap_pairs<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; }
+  pc_smem_optin((const void *)k_gap_pairs<LANES>, 200 * 1024);
   // persistent CTAs: exactly as many as are resident at once (registers limit this kernel), else the rest runs as a tail wave
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gap_pairs<LANES>, 128, sh) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int per_sm = pc_cached_occupancy((const void *)k_gap_pairs<LANES>, 128, sh);
   int grid = ctas_needed < sm_count * per_sm ? ctas_needed : sm_count * per_sm;
   if (B.max_warps > 0 && grid > (B.max_warps + 3) / 4) grid = (B.max_warps + 3) / 4;
   if (grid < 1) grid = 1;
   PcDevBatch C = B;
-  C.slots = grid * 4;
+  C.slots = (B.max_warps > 0 && B.max_warps < grid * 4) ? B.max_warps : grid * 4;
   k_gap_pairs<LANES><<<grid, 128, sh, s>>>(C, mcap);
-  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(1);
 }
 
 }  // namespace

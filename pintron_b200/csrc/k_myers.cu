@@ -82,12 +82,11 @@ __global__ void __launch_bounds__(MY_TPB) k_myers(PcDevBatch B, uint32_t *slow_l
 
 template <int OP, int MAXW>
 void launch_myers(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count) {
-  int per_sm = 8;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_myers<OP, MAXW>, MY_TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int per_sm = pc_cached_occupancy((const void *)k_myers<OP, MAXW>, MY_TPB, 0);
   const int needed = (B.n + MY_TPB - 1) / MY_TPB;
   const int grid = needed < sm_count * per_sm ? needed : sm_count * per_sm;
   k_myers<OP, MAXW><<<grid < 1 ? 1 : grid, MY_TPB, 0, s>>>(B, slow_list, slow_count);
-  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(1);
 }
 
 }  // namespace

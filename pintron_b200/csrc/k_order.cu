@@ -130,6 +130,22 @@ __global__ void __launch_bounds__(1024) k_lcs_prefix(const pc_job *jobs, const u
   if (threadIdx.x == 0) prefix[n] = carry;
 }
 
+// Multi-part batches (pc_submit_parts): the jobs of part q were written with offsets relative to that part's own arena /
+// var_out; parts[3q .. 3q+2] = (first job, arena base, var base) of part q inside the merged device buffers, parts[3*nparts]
+// = total jobs.  One thread per job finds its part by binary search and rebases the three offsets.
+__global__ void __launch_bounds__(256) k_rebase(pc_job *jobs, int n, const uint32_t *parts, int nparts) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = nparts - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (parts[3 * mid] <= (uint32_t)i) lo = mid; else hi = mid - 1; }
+    const uint32_t ab = parts[3 * lo + 1], vb = parts[3 * lo + 2];
+    pc_job j = jobs[i];
+    j.a_off += ab;
+    if (!(j.flags & PC_B_IN_GENOME)) j.b_off += ab;
+    j.out_off += vb;
+    jobs[i] = j;
+  }
+}
+
 // jobs whose status is `code` (PC_E_POOL after a pass): their indices, for the re-run with larger scratch slots
 __global__ void __launch_bounds__(256) k_collect_status(const int32_t *res, int n, int code, uint32_t *list, uint32_t *count) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -141,7 +157,7 @@ __global__ void __launch_bounds__(256) k_collect_status(const int32_t *res, int 
 void pc_collect_status(const int32_t *d_res, int n, int code, uint32_t *d_list, uint32_t *d_count, cudaStream_t s, int sm_count) {
   cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s);
   k_collect_status<<<min((n + 255) / 256, sm_count * 8), 256, 0, s>>>(d_res, n, code, d_list, d_count);
-  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(1);
 }
 
 // Enqueue keys + histogram + scan + scatter on `s`.  work = [bins NB | start NB+1 | cursor NB | invalid 1] uint32 (zeroed here),
@@ -156,10 +172,16 @@ void pc_order_jobs(const pc_job *d_jobs, int n, size_t arena_bytes, size_t genom
   k_job_keys<<<grid, 256, 0, s>>>(d_jobs, n, arena_bytes, genome_len, var_bytes, lcs_tpb, lcs_max_s2, d_keys, bins, d_seg, invalid);
   k_scan_bins<<<1, 1024, 0, s>>>(bins, start, cursor);
   k_scatter<<<min((n + 255) / 256, sm_count * 8), 256, 0, s>>>(d_keys, n, cursor, d_order);
-  __atomic_fetch_add(&g_pc_launches, 3ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(3);
+}
+
+void pc_rebase_jobs(pc_job *d_jobs, int n, const uint32_t *d_parts, int nparts, cudaStream_t s, int sm_count) {
+  if (n <= 0 || nparts <= 0) return;
+  k_rebase<<<min((n + 255) / 256, sm_count * 8), 256, 0, s>>>(d_jobs, n, d_parts, nparts);
+  PC_COUNT_LAUNCH(1);
 }
 
 void pc_lcs_prefix(const pc_job *d_jobs, const uint32_t *d_order, int n, int lcs_tpb, int lcs_max_s2, uint32_t *d_prefix, cudaStream_t s) {
   k_lcs_prefix<<<1, 1024, 0, s>>>(d_jobs, d_order, n, lcs_tpb, lcs_max_s2, d_prefix);
-  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(1);
 }

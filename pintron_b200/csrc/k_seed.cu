@@ -187,7 +187,8 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane, uin
 __global__ void __launch_bounds__(128) k_seed(PcDevBatch B) {
   __shared__ uint8_t tiles[4][SEED_TILE];
   const int lane = threadIdx.x & 31;
-  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int nwarps = pc_active_warps(B, gridDim.x * (blockDim.x >> 5));
+  if (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) >= nwarps) return;
   WarpPool wp = pc_warp_pool(B, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < B.n; w += nwarps) {
     wp.used = 0;
@@ -361,10 +362,11 @@ void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count) {
   const int ctas = (B.n + 3) / 4;
   int grid = ctas < sm_count * 8 ? ctas : sm_count * 8;
   if (B.max_warps > 0 && grid > (B.max_warps + 3) / 4) grid = (B.max_warps + 3) / 4;
+  if (grid < 1) grid = 1;
   PcDevBatch C = B;
-  C.slots = grid * 4;
+  C.slots = (B.max_warps > 0 && B.max_warps < grid * 4) ? B.max_warps : grid * 4;
   k_seed<<<grid, 128, 0, s>>>(C);
-  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(1);
 }
 
 // best: device array of B.n 64-bit slots (zeroed here); max_l1/max_l2 over the jobs of the batch
@@ -379,9 +381,9 @@ int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t 
   cudaMemsetAsync(best, 0, sizeof(unsigned long long) * B.n, s);
   size_t sh = LCS_TPB + 2 * (size_t)max_l2 + 8;
   if (sh < LCS_TPB + 64 + 8 + 4 * ((LCS_TPB + 64) / 32 + 2) + 72 + 16) sh = LCS_TPB + 64 + 8 + 4 * ((LCS_TPB + 64) / 32 + 2) + 72 + 16;
-  if (total_blocks > 0) { k_lcs<<<total_blocks, LCS_TPB, sh, s>>>(B, best, d_blk_prefix); __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED); }
+  if (total_blocks > 0) { k_lcs<<<total_blocks, LCS_TPB, sh, s>>>(B, best, d_blk_prefix); PC_COUNT_LAUNCH(1); }
   k_lcs_finish<<<(B.n + 127) / 128, 128, 0, s>>>(B, best);
-  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(1);
   return 0;
 }
 
@@ -397,7 +399,7 @@ int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned lon
   if (cudaMalloc(&k_in, 8ull * n) || cudaMalloc(&k_out, 8ull * n) || cudaMalloc(&p_in, 4ull * n) || cudaMalloc(&p_out, 4ull * n))
     return PC_E_NOMEM;
   k_hash_windows<<<(n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048, 256, 0, s>>>(d_genome, n, word, k_in, p_in);
-  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(1);
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, 64, s);
   void *tmp;
@@ -411,7 +413,7 @@ int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned lon
   uint32_t *bstart;
   if (cudaMalloc(&bstart, (nb + 2ull) * sizeof(uint32_t))) return PC_E_NOMEM;
   k_bucket_starts<<<(n + 256) / 256 < 2048 ? (n + 256) / 256 : 2048, 256, 0, s>>>(k_out, n, 64 - bits, nb, bstart);
-  __atomic_fetch_add(&g_pc_launches, 1ull, __ATOMIC_RELAXED);
+  PC_COUNT_LAUNCH(1);
   if (cudaStreamSynchronize(s) != cudaSuccess) return PC_E_CUDA;
   *keys_out = k_out; *pos_out = p_out; *n_out = n; *bstart_out = bstart; *shift_out = 64 - bits;
   return 0;

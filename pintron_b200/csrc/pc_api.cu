@@ -1,12 +1,17 @@
 // pc_api.cu — host side of the C ABI (include/pintron_cuda.h): contexts, streams, batch plumbing.
 #include "pc_device.cuh"
+#include "pintron_engine.h"
 #include <algorithm>
+#include <map>
+#include <set>
+#include <tuple>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
 unsigned long long g_pc_launches = 0;
+thread_local unsigned long long tl_pc_launches = 0;
 #include <chrono>
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const bool g_prof = getenv("PC_PROFILE") != nullptr;
@@ -43,7 +48,39 @@ static int fail(int code, const char *fmt, const char *detail = "") {
   snprintf(g_err, sizeof g_err, fmt, detail);
   return code;
 }
+int pc_set_error(int code, const char *msg) { return fail(code, "%s", msg); }      /* for the other translation units */
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(PC_E_CUDA, #call ": %s", cudaGetErrorString(e_)); } while (0)
+
+// ---- per-device launch facts, asked once ----------------------------------------------------------------------------
+static std::mutex g_occ_mu;
+static std::map<std::tuple<int, const void *, size_t>, int> g_occ;
+int pc_cached_occupancy(const void *func, int tpb, size_t smem) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t kb = (smem + 1023) >> 10;                     /* asked for the size rounded up to 1 KB: never optimistic */
+  const auto key = std::make_tuple(dev, func, kb * 4096 + (size_t)tpb);
+  {
+    std::lock_guard<std::mutex> lk(g_occ_mu);
+    auto it = g_occ.find(key);
+    if (it != g_occ.end()) return it->second;
+  }
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, tpb, kb << 10) != cudaSuccess || per_sm < 1) { per_sm = 1; cudaGetLastError(); }
+  std::lock_guard<std::mutex> lk(g_occ_mu);
+  g_occ[key] = per_sm;
+  return per_sm;
+}
+static std::set<std::pair<int, const void *>> g_optin;
+int pc_smem_optin(const void *func, int bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_occ_mu);
+  if (g_optin.count({dev, func})) return 0;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { fail(PC_E_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize): %s", cudaGetErrorString(e)); return PC_E_CUDA; }
+  g_optin.insert({dev, func});
+  return 0;
+}
 
 struct pc_ctx {
   int device = 0, sm_count = 148;
@@ -103,6 +140,11 @@ struct Pending {          // what pc_stream_sync needs to re-run jobs that ran o
   const pc_job *d_jobs = nullptr;
   int32_t *d_res = nullptr;
   uint8_t *d_var = nullptr;
+  /* multi-part batches (pc_submit_parts): where every part went inside the merged device buffers */
+  struct Part { pc_part p; size_t j_base, a_base, v_base; };
+  std::vector<Part> parts;
+  std::vector<pc_job> merged;     // host copy of all jobs, built only when a retry round needs it
+  pc_ctx *ctx = nullptr;          // genome the batch ran against
 };
 
 struct pc_stream {
@@ -113,7 +155,9 @@ struct pc_stream {
   unsigned long long *d_pool_need = nullptr, *h_pool_need = nullptr;   /* device counter + pinned mirror */
   int max_warps = 0;
   std::vector<uint32_t> h_bins;
-  PinBuf pin_idx, pin_lcs, pin_seg;
+  PinBuf pin_idx, pin_lcs, pin_seg, pin_parts;
+  DevBuf d_parts;
+  uint64_t n_retry_rounds = 0;
   uint32_t *last_slow_count = nullptr;      /* device: per-segment counts of jobs handed from k_myers to the wavefront kernel (profiling) */
   std::vector<uint16_t> h_key;
   std::vector<int32_t> h_status;
@@ -180,6 +224,8 @@ extern "C" pc_stream *pc_stream_create(pc_ctx *c) {
       cudaMalloc(&st->d_pool_need, 8) != cudaSuccess ||
       cudaHostAlloc((void **)&st->h_pool_need, 8, cudaHostAllocDefault) != cudaSuccess) {
     fail(PC_E_CUDA, "%s", "pc_stream_create: stream / counter allocation failed");
+    if (st->s) cudaStreamDestroy(st->s);
+    cudaFree(st->d_pool_need); cudaFreeHost(st->h_pool_need);
     delete st;
     return nullptr;
   }
@@ -188,11 +234,11 @@ extern "C" pc_stream *pc_stream_create(pc_ctx *c) {
   const size_t sizes[7] = {256ull << 20, 8u << 20, 8u << 20, sizeof(pc_job) << 16, (sizeof(int32_t) * PC_RES_INTS) << 16, 4u << 16, 8u << 14};
   size_t total = 0;
   for (size_t z : sizes) total += (z + 255u) & ~(size_t)255u;
-  if (cudaMalloc(&st->slab, total) != cudaSuccess) { fail(PC_E_NOMEM, "%s", "pc_stream_create: device allocation failed"); delete st; return nullptr; }
+  if (cudaMalloc(&st->slab, total) != cudaSuccess) { st->slab = nullptr; fail(PC_E_NOMEM, "%s", "pc_stream_create: device allocation failed"); pc_stream_destroy(st); return nullptr; }
   uint8_t *cur = (uint8_t *)st->slab;
   DevBuf *bufs[7] = {&st->pool, &st->arena, &st->var, &st->jobs, &st->res, &st->idx, &st->lcs_best};
   for (int i = 0; i < 7; ++i) bufs[i]->carve(cur, sizes[i]);
-  if (st->pin_idx.reserve(1u << 16) || st->pin_lcs.reserve(1u << 14)) { delete st; return nullptr; }
+  if (st->pin_idx.reserve(1u << 16) || st->pin_lcs.reserve(1u << 14)) { pc_stream_destroy(st); return nullptr; }
   return st;
 }
 
@@ -200,11 +246,13 @@ extern "C" void pc_stream_destroy(pc_stream *st) {
   if (!st) return;
   cudaSetDevice(st->ctx->device);
   cudaStreamSynchronize(st->s);
-  for (DevBuf *b : {&st->arena, &st->jobs, &st->idx, &st->res, &st->var, &st->pool, &st->lcs_best}) b->release();
+  for (DevBuf *b : {&st->arena, &st->jobs, &st->idx, &st->res, &st->var, &st->pool, &st->lcs_best, &st->d_parts}) b->release();
   cudaFree(st->slab);
   cudaFree(st->d_pool_need); cudaFreeHost(st->h_pool_need);
   if (st->pin_idx.p) cudaFreeHost(st->pin_idx.p);
   if (st->pin_lcs.p) cudaFreeHost(st->pin_lcs.p);
+  if (st->pin_seg.p) cudaFreeHost(st->pin_seg.p);
+  if (st->pin_parts.p) cudaFreeHost(st->pin_parts.p);
   for (auto &e : st->ev_pending) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
   for (auto e : st->ev_free) cudaEventDestroy(e);
   cudaStreamDestroy(st->s);
@@ -266,9 +314,9 @@ static cudaEvent_t get_event(pc_stream *st) {
 // resident on the device).  One sequential pass over the host copy of the jobs gives every job its (op, class, cost)
 // key and every (op, class) segment its size and longest strings; a counting sort then lays the job indices out
 // segment by segment, heaviest first, for the persistent kernels.
-static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *sel, size_t nsel, const uint8_t *d_arena,
-                           const pc_job *d_jobs, int32_t *d_res, uint8_t *d_var, size_t arena_bytes, size_t var_bytes) {
-  pc_ctx *c = st->ctx;
+static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const uint32_t *sel, size_t nsel, const uint8_t *d_arena,
+                           const pc_job *d_jobs, int32_t *d_res, uint8_t *d_var, size_t arena_bytes, size_t var_bytes,
+                           bool force_device_order = false) {
   double tp = g_prof ? now_s() : 0;
   constexpr int NSEG = PC_ORDER_SEGS, NB = PC_ORDER_BINS;
   struct Seg { uint32_t n, max_a, max_b, max_t; unsigned long long lcs_blocks; } seg[NSEG];
@@ -276,7 +324,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
   /* device buffer: [job order | list of the jobs the bit-parallel kernel leaves to the wavefront kernel | one counter per
    * segment | (device ordering only) keys, histogram work area, segment statistics] */
   const size_t idx_words = (nsel + 63) & ~(size_t)63;
-  const bool on_device = sel == nullptr && nsel >= PC_DEVICE_ORDER_MIN;
+  const bool on_device = sel == nullptr && (force_device_order || nsel >= PC_DEVICE_ORDER_MIN);
   const size_t extra_words = on_device ? idx_words / 2 + 3 * NB + 64 + NSEG * (sizeof(PcSegStat) / 4) : 0;
   if (st->idx.reserve((2 * idx_words + 64 + extra_words) * 4 + 256)) return PC_E_NOMEM;
   uint32_t *d_order = (uint32_t *)st->idx.p, *d_slow = d_order + idx_words, *d_slow_count = d_order + 2 * idx_words;
@@ -349,16 +397,16 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
     const int max_l2 = (int)seg[sg].max_a;
     B.idx = d_order + i;
     B.n = (int)(j - i);
+    if (op == PC_OP_SEED && !c->d_genome) return fail(PC_E_ARG, "%s", "PC_OP_SEED before pc_genome_upload");
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (st->timers || g_prof) { e0 = get_event(st); e1 = get_event(st); cudaEventRecord(e0, st->s); }
-    const unsigned long long before = g_pc_launches;
+    const unsigned long long before = tl_pc_launches;
     if (op == PC_OP_SEED) {
-      if (!c->d_genome) return fail(PC_E_ARG, "%s", "PC_OP_SEED before pc_genome_upload");
       pc_launch_seed(B, st->s, c->sm_count);
     } else if (op == PC_OP_LCS) {
       // [best slots | block prefix] in one device buffer; the prefix comes from the host copy of the jobs
       const size_t best_b = (8ull * B.n + 255u) & ~(size_t)255u;
-      if (st->lcs_best.reserve(best_b + 4ull * (B.n + 1))) return PC_E_NOMEM;
+      if (st->lcs_best.reserve(best_b + 4ull * (B.n + 1))) { if (e0) { st->ev_free.push_back(e0); st->ev_free.push_back(e1); } return PC_E_NOMEM; }
       uint32_t *d_prefix = (uint32_t *)((uint8_t *)st->lcs_best.p + best_b);
       uint64_t tot = 0;
       if (on_device) {
@@ -396,7 +444,7 @@ static int launch_selected(pc_stream *st, const pc_job *h_jobs, const uint32_t *
     } else {
       pc_launch_dp((int)op, B, st->s, c->sm_count);
     }
-    st->op_launches[op] += g_pc_launches - before;
+    st->op_launches[op] += tl_pc_launches - before;
     if (g_prof) g_op_launches[op] += 1;
     if (st->timers || g_prof) { cudaEventRecord(e1, st->s); st->ev_pending.push_back({(int)op, {e0, e1}}); }
     i = j;
@@ -451,13 +499,13 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
   CU(cudaMemsetAsync((uint8_t *)st->arena.p + arena_bytes, 0, 16, st->s));
   CU(cudaMemcpyAsync(st->jobs.p, jobs, sizeof(pc_job) * (size_t)njobs, cudaMemcpyHostToDevice, st->s));
   PROF(2, tp);
-  rc = launch_selected(st, jobs, nullptr, (size_t)njobs, (const uint8_t *)st->arena.p, (const pc_job *)st->jobs.p, (int32_t *)st->res.p,
+  rc = launch_selected(st, st->ctx, jobs, nullptr, (size_t)njobs, (const uint8_t *)st->arena.p, (const pc_job *)st->jobs.p, (int32_t *)st->res.p,
                        (uint8_t *)st->var.p, arena_bytes, var_out_bytes);
   if (rc) return rc;
   Pending &P = st->pend;
   P.active = true; P.device_mode = false; P.jobs = jobs; P.njobs = njobs; P.res = res; P.var_out = var_out;
   P.var_out_bytes = var_out_bytes; P.d_arena = (const uint8_t *)st->arena.p; P.d_jobs = (const pc_job *)st->jobs.p;
-  P.d_res = (int32_t *)st->res.p; P.d_var = (uint8_t *)st->var.p;
+  P.d_res = (int32_t *)st->res.p; P.d_var = (uint8_t *)st->var.p; P.parts.clear(); P.ctx = st->ctx;
   if (g_prof) tp = now_s();
   CU(cudaMemcpyAsync(res, st->res.p, sizeof(int32_t) * PC_RES_INTS * (size_t)njobs, cudaMemcpyDeviceToHost, st->s));
   if (var_out_bytes) CU(cudaMemcpyAsync(var_out, st->var.p, var_out_bytes, cudaMemcpyDeviceToHost, st->s));
@@ -473,12 +521,70 @@ extern "C" int pc_submit_device(pc_stream *st, const uint8_t *d_arena, size_t ar
   CU(cudaSetDevice(st->ctx->device));
   int rc = (size_t)njobs >= PC_DEVICE_ORDER_MIN ? 0 : check_jobs(st, h_jobs, njobs, arena_bytes, var_out_bytes);
   if (rc) return rc;
-  rc = launch_selected(st, h_jobs, nullptr, (size_t)njobs, d_arena, d_jobs, d_res, d_var_out, arena_bytes, var_out_bytes);
+  rc = launch_selected(st, st->ctx, h_jobs, nullptr, (size_t)njobs, d_arena, d_jobs, d_res, d_var_out, arena_bytes, var_out_bytes);
   if (rc) return rc;
   Pending &P = st->pend;
   P.active = true; P.device_mode = true; P.jobs = h_jobs; P.njobs = njobs; P.res = nullptr; P.var_out = nullptr;
-  P.var_out_bytes = var_out_bytes; P.d_arena = d_arena; P.d_jobs = d_jobs; P.d_res = d_res; P.d_var = d_var_out;
+  P.var_out_bytes = var_out_bytes; P.d_arena = d_arena; P.d_jobs = d_jobs; P.d_res = d_res; P.d_var = d_var_out; P.parts.clear(); P.ctx = st->ctx;
   return 0;
+}
+
+// D2H of every part's results out of the merged device buffers
+static int copy_parts_back(pc_stream *st) {
+  Pending &P = st->pend;
+  for (const Pending::Part &q : P.parts) {
+    CU(cudaMemcpyAsync(q.p.res, P.d_res + q.j_base * PC_RES_INTS, sizeof(int32_t) * PC_RES_INTS * (size_t)q.p.njobs, cudaMemcpyDeviceToHost, st->s));
+    if (q.p.var_out_bytes) CU(cudaMemcpyAsync(q.p.var_out, P.d_var + q.v_base, q.p.var_out_bytes, cudaMemcpyDeviceToHost, st->s));
+  }
+  return 0;
+}
+
+// Several (arena, jobs, res, var) quadruples as ONE device batch: the parts are laid one after the other in the stream's
+// device buffers (16-byte aligned), a kernel rebases the job offsets, and from there on the batch is an ordinary
+// device-resident one (validated, keyed and ordered on the device whatever its size).  What the engine runs for the
+// lanes it merged; results go back part by part.
+extern "C" int pc_submit_parts(pc_stream *st, pc_ctx *genome_ctx, const pc_part *parts, int nparts) {
+  if (!st || nparts < 0 || (nparts && !parts)) return fail(PC_E_ARG, "%s", "pc_submit_parts: bad argument");
+  if (st->pend.active) return fail(PC_E_ARG, "%s", "pc_submit_parts: previous batch not synced");
+  pc_ctx *c = genome_ctx ? genome_ctx : st->ctx;
+  if (c->device != st->ctx->device) return fail(PC_E_ARG, "%s", "pc_submit_parts: genome context and stream live on different devices");
+  Pending &P = st->pend;
+  P.parts.clear(); P.merged.clear();
+  size_t nj = 0, na = 0, nv = 0;
+  for (int q = 0; q < nparts; ++q) {
+    const pc_part &p = parts[q];
+    if (p.njobs < 0 || (p.njobs && (!p.jobs || !p.res)) || (p.arena_bytes && !p.arena) || (p.var_out_bytes && !p.var_out))
+      return fail(PC_E_ARG, "%s", "pc_submit_parts: bad part");
+    if (p.njobs == 0) continue;
+    P.parts.push_back({p, nj, na, nv});
+    nj += (size_t)p.njobs;
+    na = (na + p.arena_bytes + 16 + 15u) & ~(size_t)15u;       /* 16 spare bytes per part: BORDERS reads t[len_t], word loads run past the end */
+    nv = (nv + p.var_out_bytes + 15u) & ~(size_t)15u;
+  }
+  if (nj == 0) return 0;
+  if (nj >= 0x7fffffffull || na >= 0xfff00000ull || nv >= 0xfff00000ull) return fail(PC_E_RANGE, "%s", "pc_submit_parts: merged batch exceeds 32-bit offsets");
+  CU(cudaSetDevice(c->device));
+  const size_t np = P.parts.size();
+  if (st->arena.reserve(na + 16) || st->jobs.reserve(sizeof(pc_job) * nj) || st->res.reserve(sizeof(int32_t) * PC_RES_INTS * nj) ||
+      st->var.reserve(nv + 16) || st->d_parts.reserve(4 * (3 * np + 4)) || st->pin_parts.reserve(3 * np + 4))
+    return PC_E_NOMEM;
+  uint32_t *tab = st->pin_parts.p;
+  for (size_t q = 0; q < np; ++q) {
+    const Pending::Part &pp = P.parts[q];
+    tab[3 * q] = (uint32_t)pp.j_base; tab[3 * q + 1] = (uint32_t)pp.a_base; tab[3 * q + 2] = (uint32_t)pp.v_base;
+    if (pp.p.arena_bytes) CU(cudaMemcpyAsync((uint8_t *)st->arena.p + pp.a_base, pp.p.arena, pp.p.arena_bytes, cudaMemcpyHostToDevice, st->s));
+    CU(cudaMemcpyAsync((pc_job *)st->jobs.p + pp.j_base, pp.p.jobs, sizeof(pc_job) * (size_t)pp.p.njobs, cudaMemcpyHostToDevice, st->s));
+  }
+  tab[3 * np] = (uint32_t)nj;
+  CU(cudaMemcpyAsync(st->d_parts.p, tab, 4 * (3 * np + 1), cudaMemcpyHostToDevice, st->s));
+  pc_rebase_jobs((pc_job *)st->jobs.p, (int)nj, (const uint32_t *)st->d_parts.p, (int)np, st->s, c->sm_count);
+  int rc = launch_selected(st, c, nullptr, nullptr, nj, (const uint8_t *)st->arena.p, (const pc_job *)st->jobs.p, (int32_t *)st->res.p,
+                           (uint8_t *)st->var.p, na, nv, true);
+  if (rc) { P.parts.clear(); return rc; }
+  P.active = true; P.device_mode = true; P.jobs = nullptr; P.njobs = (int)nj; P.res = nullptr; P.var_out = nullptr;
+  P.var_out_bytes = nv; P.d_arena = (const uint8_t *)st->arena.p; P.d_jobs = (const pc_job *)st->jobs.p;
+  P.d_res = (int32_t *)st->res.p; P.d_var = (uint8_t *)st->var.p; P.ctx = c;
+  return copy_parts_back(st);
 }
 
 extern "C" int pc_stream_sync(pc_stream *st) {
@@ -499,8 +605,15 @@ extern "C" int pc_stream_sync(pc_stream *st) {
   // every job that ran out of scratch also raised the pool_need counter (pc_pool_alloc, k_gap): zero = nothing to re-run,
   // and the statuses need not be read at all
   if (*st->h_pool_need == 0) { P.active = false; return 0; }
-  // Jobs whose scratch did not fit their warp's pool slot are re-run with fewer warps (= larger slots); the pool
-  // itself grows only when a single job needs more than all of it.
+  // Jobs whose scratch did not fit their warp's pool slot are re-run with fewer warps (= larger slots: the launchers
+  // give exactly max_warps warps a slot); the pool itself grows only when a single job needs more than all of it.
+  const pc_job *h_jobs = P.jobs;
+  if (!P.parts.empty()) {           // merged batch: the host copy of the jobs is only put together now that it is needed
+    P.merged.resize((size_t)P.njobs);     // (lengths, op and parameters only: the offsets stay un-rebased and are not read)
+    for (const Pending::Part &q : P.parts) memcpy(P.merged.data() + q.j_base, q.p.jobs, sizeof(pc_job) * (size_t)q.p.njobs);
+    h_jobs = P.merged.data();
+  }
+  size_t left = 0;
   for (int round = 0; round < 64; ++round) {
     std::vector<uint32_t> redo;
     if (P.device_mode) {
@@ -518,7 +631,9 @@ extern "C" int pc_stream_sync(pc_stream *st) {
       const int32_t *status = P.res;
       for (int i = 0; i < P.njobs; ++i) if (status[(size_t)i * PC_RES_INTS] == PC_E_POOL) redo.push_back((uint32_t)i);
     }
+    left = redo.size();
     if (redo.empty()) break;
+    ++st->n_retry_rounds;
     if (g_prof) { ++g_retry_rounds; g_retry_jobs += redo.size(); }
     const unsigned long long need = std::max<unsigned long long>(*st->h_pool_need, 4096) + 4096;
     if (need > st->pool.cap) {
@@ -534,16 +649,19 @@ extern "C" int pc_stream_sync(pc_stream *st) {
       if (rc) { P.active = false; st->max_warps = 0; return rc; }
     }
     st->max_warps = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(st->pool.cap / need, 1u << 20));
-    int rc = launch_selected(st, P.jobs, redo.data(), redo.size(), P.d_arena, P.d_jobs, P.d_res, P.d_var, 0, P.var_out_bytes);
+    int rc = launch_selected(st, P.ctx, h_jobs, redo.data(), redo.size(), P.d_arena, P.d_jobs, P.d_res, P.d_var, 0, P.var_out_bytes);
     st->max_warps = 0;
     if (rc) { P.active = false; return rc; }
-    if (!P.device_mode) {
+    if (!P.parts.empty()) { rc = copy_parts_back(st); if (rc) { P.active = false; return rc; } }
+    else if (!P.device_mode) {
       CU(cudaMemcpyAsync(P.res, P.d_res, sizeof(int32_t) * PC_RES_INTS * (size_t)P.njobs, cudaMemcpyDeviceToHost, st->s));
       if (P.var_out_bytes) CU(cudaMemcpyAsync(P.var_out, P.d_var, P.var_out_bytes, cudaMemcpyDeviceToHost, st->s));
     }
     CU(cudaStreamSynchronize(st->s));
+    if (*st->h_pool_need == 0) { left = 0; break; }
   }
   P.active = false;
+  if (left) return fail(PC_E_NOMEM, "%s", "jobs still short of scratch after 64 retry rounds");
   return 0;
 }
 

@@ -45,12 +45,13 @@ __host__ __device__ inline uint32_t pc_borders_window(const pc_job &j) {
 }
 
 #define PC_BORDERS_FAST_MAX_T 1024
+#define PC_GAP_FAST_MAX_M 3000      /* packed GAP kernel: 64 * (m + 1) B of column codes per CTA must fit the 200 KB opt-in */
 /* Kernel class of a job inside its op (shared by the host and the device ordering): GAP and BORDERS jobs that fit the
  * packed register kernels are classed by their row count (0 / 1 / 2 = 8 / 16 / 32 lanes per job), EDIT / KBAND jobs by
  * the words per column of the bit-parallel kernel; 3 = generic wavefront kernel. */
 __host__ __device__ inline int pc_job_class(const pc_job &j) {
   if (j.op == PC_OP_GAP) {
-    if (j.a_len < 1 || j.b_len < 1 || j.b_len > 4096 || j.a_len > 256) return 3;
+    if (j.a_len < 1 || j.b_len < 1 || j.b_len > PC_GAP_FAST_MAX_M || j.a_len > 256) return 3;
     return j.a_len <= 64 ? 0 : (j.a_len <= 128 ? 1 : 2);
   }
   if (j.op == PC_OP_BORDERS) {
@@ -158,3 +159,12 @@ int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t 
 int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned long long **keys, uint32_t **pos,
                    uint32_t *n_out, uint32_t **bstart, int *shift, cudaStream_t s);
 extern unsigned long long g_pc_launches;
+extern thread_local unsigned long long tl_pc_launches;      /* launches issued by the calling thread (per-stream accounting) */
+#define PC_COUNT_LAUNCH(n) do { __atomic_fetch_add(&g_pc_launches, (unsigned long long)(n), __ATOMIC_RELAXED); tl_pc_launches += (n); } while (0)
+/* cudaOccupancyMaxActiveBlocksPerMultiprocessor, asked once per (device, kernel, shared-memory KB) instead of per launch */
+int pc_cached_occupancy(const void *func, int tpb, size_t smem);
+/* cudaFuncSetAttribute(MaxDynamicSharedMemorySize), once per (device, kernel): the attribute is per device */
+int pc_smem_optin(const void *func, int bytes);
+void pc_rebase_jobs(pc_job *d_jobs, int n, const uint32_t *d_parts, int nparts, cudaStream_t s, int sm_count);
+/* warps of a launch that own a scratch slot: retry rounds may allow fewer warps than one CTA holds */
+__device__ __forceinline__ int pc_active_warps(const PcDevBatch &B, int launched) { return B.slots < launched ? B.slots : launched; }

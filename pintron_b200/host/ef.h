@@ -40,6 +40,7 @@ typedef struct ef_config {
   /* ours (not in the reference): execution knobs, none changes results */
   int threads, fibers, n_devices, devices[16];
   bool quiet, aux_outputs;
+  char engine[16];               /* auto | daemon | inproc: where the batch engine runs (engine_client.h) */
 } ef_config;
 
 int ef_config_parse(ef_config *c, int argc, char **argv);   /* also writes ./config-dump.ini */
@@ -190,6 +191,8 @@ void sched_prepare(const ef_config *cfg, const ef_seq *gen);   /* optional: star
 void sched_set_order(const uint32_t *order);                       /* optional permutation of the items: dispatch order */
 int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_fn fn, void *user);
 void sched_stats(double *gpu_wait_s, uint64_t *batches, uint64_t *jobs);
+struct pc_session_stats;
+void sched_engine_stats(struct pc_session_stats *sum, const char **mode);   /* what the engine did for this run (all GPUs) */
 void sched_bytes(uint64_t *h2d, uint64_t *d2h);                    /* bytes staged to / from the devices */
 void sched_breakdown(double *fibers_s, double *gather_s, double *submit_s);   /* summed over worker threads */
 

@@ -30,7 +30,8 @@ static const optdef OPTS[] = {
 };
 #define NOPTS ((int)(sizeof OPTS / sizeof OPTS[0]))
 /* ours, outside the reference's option set (ignored by config-dump.ini) */
-static const char *EXTRA[] = {"threads", "fibers", "devices", "quiet", "no-aux-outputs"};
+static const char *EXTRA[] = {"threads", "fibers", "devices", "quiet", "no-aux-outputs", "engine"};
+#define NEXTRA 6
 
 typedef struct optval { char *s; bool given; } optval;
 
@@ -44,7 +45,9 @@ static void usage(FILE *f) {
     fputc('\n', f);
   }
   fprintf(f, "\nExecution (this build only):\n      --threads=N  --fibers=N (ESTs in flight per thread-group)  --devices=0,1,..\n"
-             "      --quiet  --no-aux-outputs (skip megs.txt, processed-megs.txt, meg-edges.txt)\n");
+             "      --quiet  --no-aux-outputs (skip megs.txt, processed-megs.txt, meg-edges.txt)\n"
+             "      --engine=auto|daemon|inproc  where the GPU engine runs: the resident server est-factd (started on demand\n"
+             "                                   with auto), or inside this process (environment: EST_FACT_ENGINE, EST_FACTD_SOCKET)\n");
 }
 
 static int find_opt(const char *name, size_t len) {
@@ -68,7 +71,8 @@ int ef_config_parse(ef_config *c, int argc, char **argv) {
   memset(vals, 0, sizeof vals);
   memset(c, 0, sizeof *c);
   c->aux_outputs = true;
-  struct option lo[NOPTS + 10];
+  { const char *e = getenv("EST_FACT_ENGINE"); snprintf(c->engine, sizeof c->engine, "%s", (e && (!strcmp(e, "daemon") || !strcmp(e, "inproc"))) ? e : "auto"); }
+  struct option lo[NOPTS + 16];
   int nlo = 0;
   char shorts[128] = "hV";
   for (int i = 0; i < NOPTS; ++i) {
@@ -78,7 +82,7 @@ int ef_config_parse(ef_config *c, int argc, char **argv) {
   lo[nlo++] = (struct option){"help", no_argument, NULL, 'h'};
   lo[nlo++] = (struct option){"detailed-help", no_argument, NULL, 'h'};
   lo[nlo++] = (struct option){"version", no_argument, NULL, 'V'};
-  for (int i = 0; i < 5; ++i) lo[nlo++] = (struct option){EXTRA[i], i < 3 ? required_argument : no_argument, NULL, 2000 + i};
+  for (int i = 0; i < NEXTRA; ++i) lo[nlo++] = (struct option){EXTRA[i], (i < 3 || i == 5) ? required_argument : no_argument, NULL, 2000 + i};
   lo[nlo] = (struct option){0, 0, 0, 0};
   optind = 1;
   int ch;
@@ -98,6 +102,10 @@ int ef_config_parse(ef_config *c, int argc, char **argv) {
         }
         case 3: c->quiet = true; break;
         case 4: c->aux_outputs = false; break;
+        case 5:
+          if (strcmp(optarg, "auto") && strcmp(optarg, "daemon") && strcmp(optarg, "inproc")) { fprintf(stderr, "est-fact: --engine takes auto, daemon or inproc\n"); return 1; }
+          snprintf(c->engine, sizeof c->engine, "%s", optarg);
+          break;
       }
       continue;
     }

@@ -10,6 +10,7 @@
  */
 #define _GNU_SOURCE
 #include "ef.h"
+#include "pintron_engine.h"
 #include <unistd.h>
 #include <pthread.h>
 #include <stdatomic.h>
@@ -165,13 +166,11 @@ int main(int argc, char **argv) {
   if (ef_config_parse(&cfg, argc, argv)) return 1;
   /* --devices on a multi-GPU box: show the CUDA runtime only the GPUs this process will use (initialising the driver
    * for eight GPUs to use one costs most of a second), and renumber them 0..n-1 */
-  if (cfg.n_devices > 0 && !getenv("CUDA_VISIBLE_DEVICES")) {
+  if (cfg.n_devices > 0 && !getenv("CUDA_VISIBLE_DEVICES")) {       /* only an in-process engine ever initialises CUDA here */
     char list[16 * 12 + 1]; size_t at = 0;
-    for (int i = 0; i < cfg.n_devices; ++i) {
-      at += (size_t)snprintf(list + at, sizeof list - at, i ? ",%d" : "%d", cfg.devices[i]);
-      cfg.devices[i] = i;
-    }
+    for (int i = 0; i < cfg.n_devices; ++i) at += (size_t)snprintf(list + at, sizeof list - at, i ? ",%d" : "%d", cfg.devices[i]);
     setenv("CUDA_VISIBLE_DEVICES", list, 1);
+    setenv("EF_DEVICES_NARROWED", "1", 1);                          /* engine_client.c: in-process ordinals are 0..n-1 now */
   }
   if (!cfg.quiet) fprintf(stderr, "* INFO  EST-FACTORIZATION v2 (B200 build)\n");
   char name[64];
@@ -264,11 +263,23 @@ int main(int argc, char **argv) {
   uint64_t h2d, d2h;
   sched_bytes(&h2d, &d2h);
   if (!cfg.quiet) fprintf(stderr, "* INFO  bytes host->device: %llu, device->host: %llu\n", (unsigned long long)h2d, (unsigned long long)d2h);
+  pc_session_stats es; const char *emode;
+  sched_engine_stats(&es, &emode);
   if (!cfg.quiet)
-    fprintf(stderr, "* INFO  device batches: %llu, device jobs: %llu, kernel launches: %llu, summed wait on device: %.3f s, ESTs/s: %.1f\n",
-            (unsigned long long)batches, (unsigned long long)jobs, (unsigned long long)pc_launch_count(), gpu_wait,
+    fprintf(stderr, "* INFO  lane batches: %llu, device jobs: %llu, kernel launches: %llu, summed wait on device: %.3f s, ESTs/s: %.1f\n",
+            (unsigned long long)batches, (unsigned long long)jobs, (unsigned long long)es.launches, gpu_wait,
             t_alg > 0 ? (double)nest / t_alg : 0.0);
-  pc_debug_dump();
+  if (!cfg.quiet)
+    fprintf(stderr, "* INFO  engine (%s): %llu merged device batches from %llu lane batches (%.1f lanes per batch), %llu retry rounds, busy %.3f s\n",
+            emode, (unsigned long long)es.batches, (unsigned long long)es.lanes_merged, es.batches ? (double)es.lanes_merged / (double)es.batches : 0.0,
+            (unsigned long long)es.retries, es.busy_s);
+  if (!cfg.quiet && getenv("PC_PROFILE")) {
+    static const char *on[PC_OP_COUNT] = {"ALIGN", "KBAND", "EDIT", "BORDERS", "GAP", "AFFIX", "SUFCUT", "PRECUT", "LCS", "SEED"};
+    fprintf(stderr, "* INFO  engine device ms per op:");
+    for (int o = 0; o < PC_OP_COUNT; ++o) if (es.op_ms[o] > 0) fprintf(stderr, " %s %.1f", on[o], es.op_ms[o]);
+    fprintf(stderr, "\n");
+  }
+  if (!strcmp(emode, "in-process")) pc_debug_dump();
   fflush(NULL);
 #ifdef EF_GPROF
   exit(0);         /* profiling build: let gmon.out be written */

@@ -2,18 +2,21 @@
  *
  * Replaces the sequential hot loop of the reference (src/main-est-fact.c:249-291): every EST runs the same
  * sequential per-EST code (compute_est_fact, src/compute-est-fact.c:192) on its own fiber; whenever that code needs
- * a DP it queues jobs and yields.  A worker thread owns two groups of fibers and one pc_stream per group: while
- * the jobs of group A are on the GPU it runs the fibers of group B, then swaps.  ESTs are dealt to threads from a
- * shared counter; threads are spread over the configured GPUs (genome + index replicated per GPU, no collective:
- * SURVEY.md §8(e)).
+ * a DP it queues jobs and yields.  A worker thread owns two groups of fibers and one engine LANE per group
+ * (include/pintron_engine.h): while the jobs of group A are with the engine it runs the fibers of group B, then swaps.
+ * The engine — inside this process or in the resident server est-factd — merges the lanes of all threads that are posted
+ * at the same moment into one device batch; no worker thread calls CUDA.  ESTs are dealt to threads from a shared
+ * counter; threads are spread over the configured GPUs (genome + index replicated per GPU, no collective: SURVEY.md §8(e)).
  */
 #define _GNU_SOURCE
 #include "ef.h"
+#include "engine_client.h"
 #include <errno.h>
 #include <pthread.h>
 #include <stdarg.h>
 #include <stdatomic.h>
 #include <sys/mman.h>
+#include <sys/resource.h>
 #include <sys/time.h>
 #include <ucontext.h>
 
@@ -168,24 +171,23 @@ typedef struct fiber {
 } fiber;
 
 typedef struct group {
-  pc_stream *st;
+  ef_conn *conn;              /* the engine session of this thread's GPU */
+  int lane_k;                 /* which of the session's lanes is ours */
   fiber *fibers;
   int nfibers;
   bool pending;
-  /* batch buffers (pinned) */
+  /* batch buffers = the lane's slab in the engine's pinned (shared) memory; refreshed by lane_refresh */
   uint8_t *arena; size_t arena_cap, arena_len;
   pc_job *jobs; int jobs_cap, njobs;
-  int32_t *res; size_t res_cap;
+  int32_t *res;
   uint8_t *var; size_t var_cap, var_len;
   struct worker *w;
-  uint64_t deferred, grows;   /* fibers put off to a later batch; staging re-allocations */
-  uint8_t *slab, *slab_end;   /* the initial pinned slab the four buffers above were carved from */
+  uint64_t deferred, grows;   /* fibers put off to a later batch; lane re-allocations */
 } group;
 
 typedef struct worker {
   pthread_t th;
   int id, device;
-  pc_ctx *ctx;
   group g[2];
   ucontext_t main_ctx;
   void *main_sp;
@@ -221,20 +223,24 @@ static inline void phase_account(void) {
 int ef_phase(int ph) { phase_account(); const int old = tl_phase; tl_phase = ph; return old; }
 const double *sched_phase_seconds(void) { return g_phase_s; }
 
-static void die_pc(const char *what) {
-  fprintf(stderr, "* FATAL est-fact: %s: %s\n", what, pc_last_error());
-  exit(1);
+/* the group's view of its lane: pointers into the (shared, pinned) segment that holds the slab */
+static void lane_refresh(group *g) {
+  pce_lane *l = efc_lane(g->conn, g->lane_k);
+  uint8_t *base = efc_seg(g->conn, l->seg);
+  if (!base) { fprintf(stderr, "* FATAL est-fact: cannot map lane segment %u of the engine\n", l->seg); exit(1); }
+  g->arena = base + l->arena_off; g->arena_cap = (size_t)l->arena_cap;
+  g->jobs = (pc_job *)(base + l->jobs_off); g->jobs_cap = (int)l->jobs_cap;
+  g->res = (int32_t *)(base + l->res_off);
+  g->var = base + l->var_off; g->var_cap = (size_t)l->var_cap;
 }
-
-static __thread uint8_t *tl_slab, *tl_slab_end;      /* pointers inside the group's slab are never freed one by one */
-static void pinned_release(void *p) {
-  if (p && !((uint8_t *)p >= tl_slab && (uint8_t *)p < tl_slab_end)) pc_host_free(p);
-}
-static void *pinned_grow(void *old, size_t old_bytes, size_t new_bytes) {
-  void *p = pc_host_alloc(new_bytes);
-  if (!p) die_pc("pc_host_alloc");
-  if (old) { memcpy(p, old, old_bytes); pinned_release(old); }
-  return p;
+/* a fiber's requests outgrew the lane: the engine moves it to a larger slab (what is already gathered travels along) */
+static void lane_grow(group *g, size_t arena_cap, int jobs_cap, size_t var_cap) {
+  if (efc_resize(g->conn, g->lane_k, arena_cap, (uint32_t)jobs_cap, var_cap, g->arena_len, (uint32_t)g->njobs)) {
+    fprintf(stderr, "* FATAL est-fact: the engine could not grow a lane to %zu + %zu bytes, %d jobs: %s\n", arena_cap, var_cap, jobs_cap, pc_last_error());
+    exit(1);
+  }
+  ++g->grows;
+  lane_refresh(g);
 }
 
 static void fiber_entry(void) {
@@ -361,15 +367,13 @@ ef_aln aln_from_ops(ef_task *T, const uint8_t *ops, int n, const char *est, cons
 
 /* ---- batching -------------------------------------------------------------------------------------------- */
 static void gather(group *g) {
-  tl_slab = g->slab; tl_slab_end = g->slab_end;
   g->arena_len = 0; g->njobs = 0; g->var_len = 0;
   for (int k = 0; k < g->nfibers; ++k) {
     fiber *f = &g->fibers[k];
     if (f->state != F_WAITING) continue;
-    /* Back-pressure instead of growth: the pinned staging (and its device mirror) keeps the size it was given at
-     * start-up; a fiber whose requests do not fit any more waits for the next batch.  Re-pinning memory or cudaMalloc
-     * in the middle of a run stalls every thread of the process, which is what long mRNAs used to trigger all the
-     * time.  Only a single fiber that is larger than an EMPTY batch makes the buffers grow. */
+    /* Back-pressure instead of growth: the lane keeps the size it was given at start-up; a fiber whose requests do not
+     * fit any more waits for the next batch.  Only a single fiber that is larger than an EMPTY lane makes the engine
+     * move the lane to a larger slab. */
     if (!f->need_valid) {
       size_t need_a = 0, need_v = 0;
       for (int i = 0; i < f->nreq; ++i) {
@@ -387,21 +391,11 @@ static void gather(group *g) {
     }
     f->submitted = true;
     f->base = g->njobs;
+    if (g->arena_len + f->need_a > g->arena_cap || g->var_len + f->need_v > g->var_cap || (size_t)g->njobs + (size_t)f->nreq > (size_t)g->jobs_cap)
+      lane_grow(g, MAX2(g->arena_cap * 2, g->arena_len + f->need_a + 1024), MAX2(g->jobs_cap * 2, g->njobs + f->nreq),
+                MAX2(g->var_cap * 2, g->var_len + f->need_v + 1024));
     for (int i = 0; i < f->nreq; ++i) {
       const ef_req *r = &f->reqs[i];
-      const size_t need = (size_t)r->a.len + (size_t)(r->b.in_genome ? 0 : r->b.len) + 8;
-      if (g->arena_len + need > g->arena_cap) {
-        size_t nc = MAX2(g->arena_cap * 2, g->arena_len + need + (1u << 20));
-        g->arena = pinned_grow(g->arena, g->arena_len, nc);
-        g->arena_cap = nc;
-        ++g->grows;
-      }
-      if (g->njobs == g->jobs_cap) {
-        int nc = g->jobs_cap ? g->jobs_cap * 2 : 4096;
-        g->jobs = pinned_grow(g->jobs, sizeof(pc_job) * (size_t)g->njobs, sizeof(pc_job) * (size_t)nc);
-        g->jobs_cap = nc;
-        ++g->grows;
-      }
       pc_job *j = &g->jobs[g->njobs++];
       memset(j, 0, sizeof *j);
       j->op = (uint32_t)r->op;
@@ -429,22 +423,6 @@ static void gather(group *g) {
     }
   }
   if (g->njobs == 0) return;
-  if ((size_t)g->njobs * PC_RES_INTS > g->res_cap) {
-    size_t nc = MAX2(g->res_cap * 2, (size_t)g->njobs * PC_RES_INTS + 4096);
-    pinned_release(g->res);
-    g->res = pc_host_alloc(nc * sizeof(int32_t));
-    ++g->grows;
-    if (!g->res) die_pc("pc_host_alloc");
-    g->res_cap = nc;
-  }
-  if (g->var_len > g->var_cap) {
-    size_t nc = MAX2(g->var_cap * 2, g->var_len + (1u << 20));
-    pinned_release(g->var);
-    g->var = pc_host_alloc(nc);
-    ++g->grows;
-    if (!g->var) die_pc("pc_host_alloc");
-    g->var_cap = nc;
-  }
   if (g->arena_len >= 0xfff00000u || g->var_len >= 0xfff00000u) {
     fprintf(stderr, "* FATAL est-fact: one batch exceeds 4 GiB; lower --fibers\n");
     exit(1);
@@ -455,7 +433,12 @@ static bool run_group(worker *w, group *g) {
   /* returns false when the group has nothing left to do and no new item could be started */
   if (g->pending) {
     const double t0 = ef_now();
-    if (pc_stream_sync(g->st)) die_pc("pc_stream_sync");
+    const int rc = pce_wait(efc_lane(g->conn, g->lane_k), efc_alive, g->conn);
+    if (rc) {
+      if (rc > 0) fprintf(stderr, "* FATAL est-fact: the engine (est-factd) went away while a batch was in flight\n");
+      else fprintf(stderr, "* FATAL est-fact: the engine failed a device batch (status %d; see the engine's log / stderr)\n", rc);
+      exit(1);
+    }
     w->gpu_wait += ef_now() - t0;
     g->pending = false;
     for (int k = 0; k < g->nfibers; ++k)
@@ -498,7 +481,9 @@ static bool run_group(worker *w, group *g) {
   const double tf2 = ef_now();
   w->t_gather += tf2 - tf1;
   if (g->njobs) {
-    if (pc_submit(g->st, g->arena, g->arena_len, g->jobs, g->njobs, g->res, g->var, g->var_len)) die_pc("pc_submit");
+    pce_lane *l = efc_lane(g->conn, g->lane_k);
+    l->njobs = (uint32_t)g->njobs; l->arena_len = g->arena_len; l->var_len = g->var_len;
+    pce_post(g->conn->hdr, l);
     g->pending = true;
     w->batches++; w->jobs += (uint64_t)g->njobs;
     w->h2d += g->arena_len + sizeof(pc_job) * (uint64_t)g->njobs;
@@ -512,29 +497,7 @@ static void *worker_main(void *arg) {
   worker *w = arg;
   tl_worker = w;
   const double tw0 = ef_now();
-  for (int i = 0; i < 2; ++i) {
-    group *g = &w->g[i];
-    g->st = pc_stream_create(w->ctx);
-    if (!g->st) die_pc("pc_stream_create");
-    g->w = w;
-    /* pinned staging sized up front and taken as ONE slab: pinning memory stalls every thread of the process, so it
-     * is done once per group; a buffer that outgrows its share later moves to its own allocation */
-    const size_t per_fiber = 4096;
-    g->arena_cap = MAX2((size_t)1 << 20, (size_t)g->nfibers * per_fiber);
-    g->jobs_cap = MAX2(4096, g->nfibers * 32);
-    {
-      const char *kb = getenv("EF_STAGING_KB");        /* tests: tiny staging, so that back-pressure and growth both happen */
-      if (kb && atol(kb) > 0) { g->arena_cap = (size_t)atol(kb) << 10; g->jobs_cap = (int)MAX2(64, atol(kb)); }
-    }
-    g->res_cap = (size_t)g->jobs_cap * PC_RES_INTS;
-    g->var_cap = g->arena_cap;
-    const size_t jobs_b = (sizeof(pc_job) * (size_t)g->jobs_cap + 255u) & ~(size_t)255u, res_b = g->res_cap * sizeof(int32_t);
-    uint8_t *slab = pc_host_alloc(g->arena_cap + jobs_b + res_b + g->var_cap);
-    if (!slab) die_pc("pc_host_alloc");
-    g->slab = slab; g->slab_end = slab + g->arena_cap + jobs_b + res_b + g->var_cap;
-    g->arena = slab; g->jobs = (pc_job *)(slab + g->arena_cap);
-    g->res = (int32_t *)(slab + g->arena_cap + jobs_b); g->var = slab + g->arena_cap + jobs_b + res_b;
-  }
+  for (int i = 0; i < 2; ++i) { w->g[i].w = w; lane_refresh(&w->g[i]); }
   const double tw1 = ef_now();
   bool alive[2] = {true, true};
   while (alive[0] || alive[1]) {
@@ -570,33 +533,64 @@ void sched_stats(double *gpu_wait_s, uint64_t *batches, uint64_t *jobs) {
   if (jobs) *jobs = g_jobs;
 }
 
-/* CUDA context creation and the genome index build take about a second: sched_prepare starts them on their own
- * thread as soon as the genome is in memory, so they overlap reading and preparing the ESTs. */
-static struct { pthread_t th; bool started; int rc, nuse, use[16]; pc_ctx *ctxs[16]; const ef_config *cfg; const ef_seq *gen; double secs; } g_prep;
+/* Opening the engine sessions (in-process: CUDA context + pinned lanes + genome index, about a second; server: a
+ * handshake and the index build, milliseconds) runs on its own thread as soon as the genome is in memory, so it overlaps
+ * reading and preparing the ESTs. */
+static struct {
+  pthread_t th; bool started; int rc, nuse, use[16], nthreads, per_group; ef_conn *conns[16];
+  const ef_config *cfg; const ef_seq *gen; double secs;
+} g_prep;
+static pc_session_stats g_engine_stats;
+static const char *g_engine_mode = "";
+
+/* VA budget: pintron.py runs est-fact under `ulimit -v` (3000 MiB by default, dist-scripts/pintron.py:207-213).  Fiber
+ * stacks are address space, not memory, but they count: keep them (and malloc's per-thread arenas) inside a third of it. */
+static size_t va_limit(void) {
+  struct rlimit rl;
+  if (getrlimit(RLIMIT_AS, &rl) != 0 || rl.rlim_cur == RLIM_INFINITY) return 0;
+  return (size_t)rl.rlim_cur;
+}
 
 static void *prepare_main(void *arg) {
   (void)arg;
   const double t0 = ef_now();
   const ef_config *cfg = g_prep.cfg;
   const ef_seq *gen = g_prep.gen;
-  int ndev = pc_device_count();
-  if (ndev <= 0) {
-    fprintf(stderr, "* FATAL est-fact: no CUDA device available (%s). This build has no CPU path.\n", pc_last_error());
-    g_prep.rc = 1;
-    return NULL;
+  if (cfg->n_devices > 0) for (int i = 0; i < cfg->n_devices; ++i) g_prep.use[g_prep.nuse++] = cfg->devices[i];
+  else g_prep.use[g_prep.nuse++] = -1;                 /* none named: the server picks its least loaded GPU, an in-process engine takes GPU 0 */
+  const int nuse = g_prep.nuse, nthreads = g_prep.nthreads;
+  const size_t per_fiber = 4096;
+  ef_conn_req req;
+  memset(&req, 0, sizeof req);
+  req.genome = gen->seq; req.genome_len = (size_t)gen->len; req.word_len = (int)cfg->min_factor_len; req.depth_rate = cfg->min_string_depth_rate;
+  req.arena_cap = MAX2((size_t)1 << 20, (size_t)g_prep.per_group * per_fiber);
+  req.jobs_cap = (uint32_t)MAX2(4096, g_prep.per_group * 32);
+  {
+    const char *kb = getenv("EF_STAGING_KB");        /* tests: tiny lanes, so that back-pressure and growth both happen */
+    if (kb && atol(kb) > 0) { req.arena_cap = (size_t)atol(kb) << 10; req.jobs_cap = (uint32_t)MAX2(64, atol(kb)); }
   }
-  if (cfg->n_devices > 0) {
-    for (int i = 0; i < cfg->n_devices; ++i) {
-      if (cfg->devices[i] < 0 || cfg->devices[i] >= ndev) { fprintf(stderr, "* FATAL est-fact: device %d not present\n", cfg->devices[i]); g_prep.rc = 1; return NULL; }
-      g_prep.use[g_prep.nuse++] = cfg->devices[i];
+  req.var_cap = req.arena_cap;
+  req.timers = getenv("PC_PROFILE") != NULL;
+  for (int d = 0; d < nuse; ++d) {
+    int nth = 0;
+    for (int i = 0; i < nthreads; ++i) if (i % nuse == d) ++nth;
+    if (nth == 0) continue;
+    req.nlanes = 2 * nth;
+    req.device = d;
+    char err[768];
+    ef_conn *c = efc_open(cfg->engine, g_prep.use, g_prep.use[0] >= 0 ? nuse : 0, &req, err, sizeof err);
+    if (!c) {
+      fprintf(stderr, "* FATAL est-fact: no CUDA device available (no GPU engine: %s).  This build has no CPU path", err);
+      if (va_limit()) fprintf(stderr, " (note: this process runs under a %zu MiB address-space limit, which a CUDA context does not fit: "
+                                      "start est-factd outside the limit and est-fact will use it)", va_limit() >> 20);
+      fprintf(stderr, "\n");
+      g_prep.rc = 1;
+      return NULL;
     }
-  } else g_prep.use[g_prep.nuse++] = 0;
-  for (int i = 0; i < g_prep.nuse; ++i) {
-    g_prep.ctxs[i] = pc_ctx_create(g_prep.use[i]);
-    if (!g_prep.ctxs[i]) die_pc("pc_ctx_create");
-    if (pc_genome_upload(g_prep.ctxs[i], gen->seq, (size_t)gen->len, (int)cfg->min_factor_len, cfg->min_string_depth_rate))
-      die_pc("pc_genome_upload");
+    if (d > 0 && c->daemon != g_prep.conns[0]->daemon) { fprintf(stderr, "* FATAL est-fact: engine sessions ended up in different places\n"); g_prep.rc = 1; return NULL; }
+    g_prep.conns[d] = c;
   }
+  g_engine_mode = g_prep.conns[0]->daemon ? "est-factd" : "in-process";
   g_prep.secs = ef_now() - t0;
   return NULL;
 }
@@ -607,9 +601,25 @@ void sched_prepare(const ef_config *cfg, const ef_seq *gen) {
   mallopt(M_TRIM_THRESHOLD, 1 << 30);
   memset(&g_prep, 0, sizeof g_prep);
   g_prep.cfg = cfg; g_prep.gen = gen;
+  /* defaults from measurements on a 16-core B200 host: all cores but two (the engine's submission threads and the output
+   * writer need them), 1024 ESTs in flight per group */
+  const int ncpu = (int)sysconf(_SC_NPROCESSORS_ONLN);
+  int nthreads = cfg->threads > 0 ? cfg->threads : (ncpu > 4 ? ncpu - 2 : ncpu);
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > PCE_MAX_SESSION_LANES / 2) nthreads = PCE_MAX_SESSION_LANES / 2;
+  int per_group = cfg->fibers > 0 ? cfg->fibers : 1024;
+  const size_t lim = va_limit();
+  if (lim) {
+    mallopt(M_ARENA_MAX, 2);
+    const size_t budget = lim / 3 / FIBER_STACK;               /* fibers in total */
+    if ((size_t)per_group * 2 * (size_t)nthreads > budget) per_group = (int)MAX2((size_t)8, budget / (2 * (size_t)nthreads));
+  }
+  g_prep.nthreads = nthreads; g_prep.per_group = per_group;
   if (pthread_create(&g_prep.th, NULL, prepare_main, NULL)) { perror("pthread_create"); exit(1); }
   g_prep.started = true;
 }
+
+void sched_engine_stats(pc_session_stats *sum, const char **mode) { if (sum) *sum = g_engine_stats; if (mode) *mode = g_engine_mode; }
 
 int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_fn fn, void *user) {
   const double ts0 = ef_now();
@@ -619,12 +629,12 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
   if (g_prep.rc) return 1;
   const int nuse = g_prep.nuse;
   int *use = g_prep.use;
-  pc_ctx **ctxs = g_prep.ctxs;
-  /* defaults from measurements on a 16-core B200 host: three quarters of the cores, 1024 ESTs in flight per group */
-  int nthreads = cfg->threads > 0 ? cfg->threads : (int)(sysconf(_SC_NPROCESSORS_ONLN) * 3 / 4);
-  if (nthreads < 1) nthreads = 1;
-  if ((size_t)nthreads > n_items) nthreads = n_items ? (int)n_items : 1;
-  int per_group = cfg->fibers > 0 ? cfg->fibers : 1024;
+  int nthreads = g_prep.nthreads;            /* lanes exist for this many; a short input uses fewer */
+  if ((size_t)nthreads > n_items) {
+    /* keep the thread -> lane mapping: only the first n threads run */
+    nthreads = n_items ? (int)n_items : 1;
+  }
+  int per_group = g_prep.per_group;
   if ((size_t)per_group * 2 * (size_t)nthreads > n_items) per_group = (int)(n_items / (2 * (size_t)nthreads)) + 1;
   atomic_store(&g_next_item, 0);
   g_n_items = n_items;
@@ -634,9 +644,11 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
   worker *ws = calloc((size_t)nthreads, sizeof(worker));
   for (int i = 0; i < nthreads; ++i) {
     worker *w = &ws[i];
-    w->id = i; w->device = use[i % nuse]; w->ctx = ctxs[i % nuse];
+    w->id = i; w->device = use[i % nuse];
     w->cfg = cfg; w->gen = gen; w->fn = fn; w->user = user;
     for (int k = 0; k < 2; ++k) {
+      w->g[k].conn = g_prep.conns[i % nuse];
+      w->g[k].lane_k = 2 * (i / nuse) + k;
       w->g[k].nfibers = per_group;
       w->g[k].fibers = calloc((size_t)per_group, sizeof(fiber));
     }
@@ -645,12 +657,22 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
   for (int i = 0; i < nthreads; ++i) pthread_join(ws[i].th, NULL);
   const double ts2 = ef_now();
   free(ws);
-  (void)ctxs;      /* contexts are left to process exit, see worker_main */
+  memset(&g_engine_stats, 0, sizeof g_engine_stats);
+  for (int d = 0; d < nuse; ++d) {
+    if (!g_prep.conns[d]) continue;
+    pc_session_stats st;
+    efc_close(g_prep.conns[d], &st);
+    g_engine_stats.batches += st.batches; g_engine_stats.lanes_merged += st.lanes_merged; g_engine_stats.jobs += st.jobs;
+    g_engine_stats.launches += st.launches; g_engine_stats.h2d_bytes += st.h2d_bytes; g_engine_stats.d2h_bytes += st.d2h_bytes;
+    g_engine_stats.retries += st.retries; g_engine_stats.busy_s += st.busy_s;
+    for (int o = 0; o < PC_OP_COUNT; ++o) g_engine_stats.op_ms[o] += st.op_ms[o];
+    g_prep.conns[d] = NULL;
+  }
   if (!cfg->quiet)
-    fprintf(stderr, "* INFO  scheduler: %d thread(s) x 2 x %d fibers on %d GPU(s); context + genome index %.3f s (%.3f s of it still to wait for), workers %.3f s "
-            "(stream set-up %.3f s, tear-down %.3f s per thread on average), context tear-down %.3f s; "
-            "%llu fiber deferrals, %llu staging re-allocations; threads idle at the end %.3f s on average (first done %.3f s before the last)\n",
-            nthreads, per_group, nuse, g_prep.secs, ts1 - ts0, ts2 - ts1, g_t_init / nthreads, g_t_fini / nthreads, ef_now() - ts2,
+    fprintf(stderr, "* INFO  scheduler: %d thread(s) x 2 x %d fibers on %d GPU(s), engine: %s; engine session(s) open after %.3f s (%.3f s of it still to wait for), workers %.3f s "
+            "(set-up %.3f s per thread on average), session close %.3f s; "
+            "%llu fiber deferrals, %llu lane re-allocations; threads idle at the end %.3f s on average (first done %.3f s before the last)\n",
+            nthreads, per_group, nuse, g_engine_mode, g_prep.secs, ts1 - ts0, ts2 - ts1, g_t_init / nthreads, ef_now() - ts2,
             (unsigned long long)g_deferred, (unsigned long long)g_grows, ts2 - g_t_end_sum / nthreads, ts2 - g_t_end_min);
   return 0;
 }

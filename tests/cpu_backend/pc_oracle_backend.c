@@ -4,9 +4,15 @@
  * tests/test_host_parity.py to exercise the C host program (pintron_b200/host/) in this GPU-less container:
  * tests/Makefile links the host sources with THIS file into tests/_build/est-fact-oracle-backend.  The shipped
  * est-fact links libpintron_cuda.so and nothing else; it has no CPU path (pc_ctx_create fails without a device).
- * Jobs run synchronously inside pc_submit; pc_stream_sync is a no-op.
+ * Jobs run synchronously inside pc_submit; pc_stream_sync is a no-op.  The engine half (pc_engine_*, the lane protocol of
+ * include/pintron_engine.h) is implemented too — memfd segments, one thread that serves posted lanes through the
+ * pc_submit below — so that the in-process and the est-factd forms of the host can both be exercised without a GPU.
  */
+#define _GNU_SOURCE
 #include "pintron_cuda.h"
+#include "pintron_engine.h"
+#include <pthread.h>
+#include <sys/mman.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -94,3 +100,148 @@ int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes, const pc_
   }
   return 0;
 }
+
+
+/* ---- engine: lanes in memfd segments, one serving thread ------------------------------------------------------------ */
+#define SEG_BYTES ((size_t)64 << 20)
+typedef struct slab { uint32_t seg; size_t off, bytes; } slab;
+typedef struct be_session { uint32_t id; pc_ctx *ctx; int nlanes; uint32_t lane[PCE_MAX_SESSION_LANES]; pc_session_stats st; int open; } be_session;
+struct pc_engine {
+  int nsegs, fd[PCE_MAX_SEGMENTS]; uint8_t *base[PCE_MAX_SEGMENTS]; size_t bytes[PCE_MAX_SEGMENTS], used[PCE_MAX_SEGMENTS];
+  pce_hdr *hdr;
+  be_session ses[64]; uint32_t next_id; int live;
+  pthread_mutex_t mu; pthread_t th[8]; int nth; volatile int stop;
+};
+
+static size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static int add_seg(pc_engine *e, size_t bytes) {
+  if (e->nsegs >= PCE_MAX_SEGMENTS) return -1;
+  const int k = e->nsegs;
+  e->fd[k] = memfd_create("pintron-lanes-test", MFD_CLOEXEC);
+  if (e->fd[k] < 0 || ftruncate(e->fd[k], (off_t)bytes)) return -1;
+  e->base[k] = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, e->fd[k], 0);
+  if (e->base[k] == MAP_FAILED) return -1;
+  e->bytes[k] = bytes; e->used[k] = k == 0 ? PCE_HDR_BYTES : 0;
+  if (k == 0) { e->hdr = (pce_hdr *)e->base[0]; memset(e->hdr, 0, sizeof(pce_hdr)); e->hdr->magic = PCE_MAGIC; e->hdr->version = PCE_VERSION; }
+  return e->nsegs++;
+}
+static int lane_slab(pc_engine *e, pce_lane *l, uint64_t arena_cap, uint32_t jobs_cap, uint64_t var_cap) {
+  const size_t a = up(arena_cap + 64, 256), j = up(sizeof(pc_job) * (size_t)jobs_cap, 256), r = up(4u * PC_RES_INTS * (size_t)jobs_cap, 256), v = up(var_cap + 64, 256);
+  const size_t total = up(a + j + r + v, 4096);
+  int k = -1;
+  for (int q = 0; q < e->nsegs; ++q) if (e->used[q] + total <= e->bytes[q]) { k = q; break; }
+  if (k < 0) k = add_seg(e, total > SEG_BYTES ? up(total, 1 << 21) : SEG_BYTES);
+  if (k < 0) return PC_E_NOMEM;
+  const size_t off = e->used[k];
+  e->used[k] += total;
+  l->seg = (uint32_t)k; l->jobs_cap = jobs_cap; l->arena_off = off; l->arena_cap = arena_cap; l->jobs_off = off + a; l->res_off = off + a + j;
+  l->var_off = off + a + j + r; l->var_cap = var_cap;
+  return 0;
+}
+
+static void *engine_main(void *arg) {
+  pc_engine *e = arg;
+  pc_stream st;
+  while (!e->stop) {
+    const uint32_t bell = __atomic_load_n(&e->hdr->doorbell, __ATOMIC_SEQ_CST);
+    int served = 0;
+    for (uint32_t i = 0; i < PCE_MAX_LANES; ++i) {
+      pce_lane *l = &e->hdr->lanes[i];
+      uint32_t expect = PCE_POSTED;
+      if (!__atomic_compare_exchange_n(&l->state, &expect, (uint32_t)PCE_RUNNING, 0, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) continue;
+      be_session *S = NULL;
+      pthread_mutex_lock(&e->mu);
+      for (int q = 0; q < 64; ++q) if (e->ses[q].open && e->ses[q].id == l->session) S = &e->ses[q];
+      pthread_mutex_unlock(&e->mu);
+      int rc = PC_E_ARG;
+      if (S && l->njobs <= l->jobs_cap && l->arena_len <= l->arena_cap && l->var_len <= l->var_cap) {
+        uint8_t *b = e->base[l->seg];
+        st.ctx = S->ctx;
+        rc = pc_submit(&st, b + l->arena_off, (size_t)l->arena_len, (const pc_job *)(b + l->jobs_off), (int)l->njobs, (int32_t *)(b + l->res_off),
+                       b + l->var_off, (size_t)l->var_len);
+        S->st.batches++; S->st.lanes_merged++; S->st.jobs += l->njobs;
+      }
+      l->rc = rc;
+      __atomic_store_n(&l->state, (uint32_t)PCE_DONE, __ATOMIC_RELEASE);
+      pce_futex(&l->state, FUTEX_WAKE, 64, NULL);
+      ++served;
+    }
+    if (!served) {
+      __atomic_fetch_add(&e->hdr->sleepers, 1u, __ATOMIC_SEQ_CST);
+      struct timespec to = {0, 20 * 1000 * 1000};
+      if (__atomic_load_n(&e->hdr->doorbell, __ATOMIC_SEQ_CST) == bell) pce_futex(&e->hdr->doorbell, FUTEX_WAIT, bell, &to);
+      __atomic_fetch_sub(&e->hdr->sleepers, 1u, __ATOMIC_SEQ_CST);
+    }
+  }
+  return NULL;
+}
+
+pc_engine *pc_engine_create(const int *devices, int ndev, size_t segment_bytes) {
+  (void)devices; (void)ndev;
+  pc_engine *e = calloc(1, sizeof *e);
+  pthread_mutex_init(&e->mu, NULL);
+  e->next_id = 1;
+  if (add_seg(e, segment_bytes ? up(segment_bytes, 1 << 21) : SEG_BYTES) < 0) { free(e); return NULL; }
+  e->nth = 8;                                    /* the oracle is slow: serve lanes in parallel */
+  for (int k = 0; k < e->nth; ++k) pthread_create(&e->th[k], NULL, engine_main, e);
+  return e;
+}
+void pc_engine_destroy(pc_engine *e) { if (!e) return; e->stop = 1; for (int k = 0; k < e->nth; ++k) pthread_join(e->th[k], NULL); free(e); }
+int pc_engine_gpu_count(const pc_engine *e) { (void)e; return 1; }
+const char *pc_engine_backend(void) { return "oracle-test"; }
+void pc_engine_enable_timers(pc_engine *e, int on) { (void)e; (void)on; }
+int pc_engine_open(pc_engine *e, const pc_session_req *req, pc_session_info *out) {
+  pthread_mutex_lock(&e->mu);
+  be_session *S = NULL;
+  for (int q = 0; q < 64 && !S; ++q) if (!e->ses[q].open) S = &e->ses[q];
+  if (!S || req->nlanes > PCE_MAX_SESSION_LANES) { pthread_mutex_unlock(&e->mu); return PC_E_NOMEM; }
+  memset(S, 0, sizeof *S);
+  S->id = e->next_id++; S->ctx = pc_ctx_create(0); S->nlanes = req->nlanes;
+  pc_genome_upload(S->ctx, req->genome, req->genome_len, req->word_len, req->depth_rate);
+  memset(out, 0, sizeof *out);
+  for (int k = 0; k < req->nlanes; ++k) {
+    uint32_t li = 0;
+    while (li < PCE_MAX_LANES && (e->hdr->lanes[li].session || e->hdr->lanes[li].state != PCE_FREE)) ++li;
+    if (li == PCE_MAX_LANES || lane_slab(e, &e->hdr->lanes[li], req->arena_cap, req->jobs_cap, req->var_cap)) { pthread_mutex_unlock(&e->mu); return PC_E_NOMEM; }
+    e->hdr->lanes[li].session = S->id; e->hdr->lanes[li].state = PCE_IDLE;
+    S->lane[k] = li; out->lane[k] = li;
+  }
+  out->session = S->id; out->gpu = 0; out->nlanes = req->nlanes;
+  S->open = 1; ++e->live;
+  pthread_mutex_unlock(&e->mu);
+  return 0;
+}
+int pc_engine_resize_lane(pc_engine *e, uint32_t session, uint32_t lane, uint64_t arena_cap, uint32_t jobs_cap, uint64_t var_cap, uint64_t keep_arena,
+                          uint32_t keep_jobs) {
+  (void)session;
+  pthread_mutex_lock(&e->mu);
+  pce_lane *l = &e->hdr->lanes[lane], old = *l;
+  int rc = lane_slab(e, l, arena_cap, jobs_cap, var_cap);          /* the old slab is simply left behind: test runs are short */
+  if (!rc) {
+    memcpy(e->base[l->seg] + l->arena_off, e->base[old.seg] + old.arena_off, (size_t)keep_arena);
+    memcpy(e->base[l->seg] + l->jobs_off, e->base[old.seg] + old.jobs_off, sizeof(pc_job) * (size_t)keep_jobs);
+  }
+  pthread_mutex_unlock(&e->mu);
+  return rc;
+}
+int pc_engine_close(pc_engine *e, uint32_t session, pc_session_stats *stats) {
+  pthread_mutex_lock(&e->mu);
+  for (int q = 0; q < 64; ++q) {
+    be_session *S = &e->ses[q];
+    if (!S->open || S->id != session) continue;
+    for (int k = 0; k < S->nlanes; ++k) {
+      pce_lane *l = &e->hdr->lanes[S->lane[k]];
+      while (__atomic_load_n(&l->state, __ATOMIC_ACQUIRE) == PCE_RUNNING) usleep(100);
+      memset(l, 0, sizeof *l);
+    }
+    if (stats) *stats = S->st;
+    pc_ctx_destroy(S->ctx);
+    S->open = 0;
+    if (--e->live == 0) for (int k = 0; k < e->nsegs; ++k) e->used[k] = k == 0 ? PCE_HDR_BYTES : 0;      /* nobody left: all slabs are free again */
+  }
+  pthread_mutex_unlock(&e->mu);
+  return 0;
+}
+int pc_engine_segment_count(pc_engine *e, int gpu) { (void)gpu; return e->nsegs; }
+int pc_engine_segment_fd(pc_engine *e, int gpu, int seg, size_t *bytes) { (void)gpu; if (seg < 0 || seg >= e->nsegs) return -1; if (bytes) *bytes = e->bytes[seg]; return e->fd[seg]; }
+void *pc_engine_segment_base(pc_engine *e, int gpu, int seg) { (void)gpu; return (seg < 0 || seg >= e->nsegs) ? NULL : e->base[seg]; }

@@ -26,6 +26,10 @@ def unpack(case, dst):
 
 
 def run(binary, cwd, *args, timeout=1200, env=None):
+    """Runs an est-fact binary.  Unless the caller names one, the engine is in-process: tests must not leave (or pick up)
+    a resident est-factd behind their back; the server form has its own tests, on private sockets."""
+    if binary != REF_BIN and "--engine" not in args and not (env and "EST_FACT_ENGINE" in env):
+        args = (*args, "--engine", "inproc")
     p = subprocess.run([binary, *args], cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout, env=env)
     assert p.returncode == 0, p.stderr.decode("latin1")[-2000:]
     with open(os.path.join(cwd, "stderr.txt"), "w") as f:
@@ -84,3 +88,32 @@ def check_options_vs_reference(binary, case, tmp_path, opts, *extra):
     run(REF_BIN, a, *opts)
     run(binary, b, *opts, *extra)
     assert md5s(a) == md5s(b), (case, opts)
+
+
+class Server:
+    """A private est-factd (own socket in `tmp`) for the tests of the server form; `binary` = the est-factd next to the
+    est-fact under test (tests/_build/est-factd for the CPU stand-in, pintron_b200/bin/est-factd on a GPU box)."""
+
+    def __init__(self, daemon_bin, tmp, *args):
+        import time
+        self.sock = os.path.join(str(tmp), "efd.sock")
+        self.log = open(os.path.join(str(tmp), "est-factd.log"), "wb")
+        self.proc = subprocess.Popen([daemon_bin, "--socket", self.sock, "--foreground", *args], stdout=self.log, stderr=self.log)
+        t0 = time.time()
+        while not os.path.exists(self.sock):
+            assert self.proc.poll() is None, "est-factd exited: " + open(self.log.name, "rb").read().decode("latin1")[-1500:]
+            assert time.time() - t0 < 120, "est-factd did not come up"
+            time.sleep(0.02)
+        self.env = dict(os.environ, EST_FACTD_SOCKET=self.sock, EST_FACT_NO_SPAWN="1")
+
+    def stop(self):
+        if self.proc.poll() is None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        self.log.close()
+
+    def text(self):
+        return open(self.log.name, "rb").read().decode("latin1")

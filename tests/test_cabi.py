@@ -20,9 +20,10 @@ def lib():
     return binding.load_library()
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "pintron_cuda.h")).read()
+def declared_symbols(header="pintron_cuda.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = text.split("client-side helpers")[0]          # the header-only lane protocol functions are not exports
     return sorted(set(re.findall(r"\b(pc_[a-z_0-9]+)\s*\(", text)))
 
 
@@ -32,6 +33,28 @@ def test_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/pintron_cuda.h but not exported"
     assert set(binding.EXPORTS) <= set(syms)
+
+
+def test_exports_every_engine_symbol(lib):
+    """include/pintron_engine.h: the batch engine + pc_submit_parts."""
+    syms = declared_symbols("pintron_engine.h")
+    assert len(syms) >= 12, syms
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/pintron_engine.h but not exported"
+    assert set(binding.ENGINE_EXPORTS) == set(syms)
+    assert lib.pc_engine_backend() == b"cuda-sm100a"
+
+
+def test_lane_struct_layout():
+    """The shared-memory lane table is read by C (host, engine) and by Python (tests, bench): same layout."""
+    import subprocess, tempfile
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "pintron_engine.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(pce_lane), ' \
+          'offsetof(pce_hdr, lanes), offsetof(pce_hdr, doorbell), offsetof(pce_lane, arena_off), offsetof(pce_lane, var_cap));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True).stdout.split()
+    assert [int(x) for x in out] == [128, binding.PCE_LANES_OFFSET, 8, binding.pce_lane.arena_off.offset, binding.pce_lane.var_cap.offset]
 
 
 def test_job_struct_layout():

