@@ -387,31 +387,29 @@ int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t 
   return 0;
 }
 
-int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned long long **keys_out, uint32_t **pos_out,
+int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, PcIndexBufs &bufs, unsigned long long **keys_out, uint32_t **pos_out,
                    uint32_t *n_out, uint32_t **bstart_out, int *shift_out, cudaStream_t s) {
   *keys_out = nullptr; *pos_out = nullptr; *n_out = 0; *bstart_out = nullptr; *shift_out = 63;
   if (len < (uint32_t)word) {                        // empty index: one empty bucket pair
-    if (cudaMalloc(bstart_out, 3 * sizeof(uint32_t)) || cudaMemset(*bstart_out, 0, 3 * sizeof(uint32_t))) return PC_E_NOMEM;
+    if (bufs.bstart.reserve(3 * sizeof(uint32_t)) || cudaMemsetAsync(bufs.bstart.p, 0, 3 * sizeof(uint32_t), s)) return PC_E_NOMEM;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return PC_E_CUDA;
+    *bstart_out = (uint32_t *)bufs.bstart.p;
     return 0;
   }
   const uint32_t n = len - word + 1;
-  unsigned long long *k_in, *k_out; uint32_t *p_in, *p_out;
-  if (cudaMalloc(&k_in, 8ull * n) || cudaMalloc(&k_out, 8ull * n) || cudaMalloc(&p_in, 4ull * n) || cudaMalloc(&p_out, 4ull * n))
-    return PC_E_NOMEM;
-  k_hash_windows<<<(n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048, 256, 0, s>>>(d_genome, n, word, k_in, p_in);
-  PC_COUNT_LAUNCH(1);
   size_t tmp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, 64, s);
-  void *tmp;
-  if (cudaMalloc(&tmp, tmp_bytes)) return PC_E_NOMEM;
-  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, 64, s);   // stable: equal keys keep ascending t
-  if (cudaStreamSynchronize(s) != cudaSuccess) return PC_E_CUDA;
-  cudaFree(tmp); cudaFree(k_in); cudaFree(p_in);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 64, s);
   int bits = 12;
   while (bits < 24 && (1u << bits) < 2u * n) ++bits;          // about half an entry per bucket
   const uint32_t nb = 1u << bits;
-  uint32_t *bstart;
-  if (cudaMalloc(&bstart, (nb + 2ull) * sizeof(uint32_t))) return PC_E_NOMEM;
+  if (bufs.keys_in.reserve(8ull * n) || bufs.keys_out.reserve(8ull * n) || bufs.pos_in.reserve(4ull * n) || bufs.pos_out.reserve(4ull * n) ||
+      bufs.tmp.reserve(tmp_bytes) || bufs.bstart.reserve((nb + 2ull) * sizeof(uint32_t)))
+    return PC_E_NOMEM;
+  unsigned long long *k_in = (unsigned long long *)bufs.keys_in.p, *k_out = (unsigned long long *)bufs.keys_out.p;
+  uint32_t *p_in = (uint32_t *)bufs.pos_in.p, *p_out = (uint32_t *)bufs.pos_out.p, *bstart = (uint32_t *)bufs.bstart.p;
+  k_hash_windows<<<(n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048, 256, 0, s>>>(d_genome, n, word, k_in, p_in);
+  PC_COUNT_LAUNCH(1);
+  cub::DeviceRadixSort::SortPairs(bufs.tmp.p, tmp_bytes, k_in, k_out, p_in, p_out, (int)n, 0, 64, s);   // stable: equal keys keep ascending t
   k_bucket_starts<<<(n + 256) / 256 < 2048 ? (n + 256) / 256 : 2048, 256, 0, s>>>(k_out, n, 64 - bits, nb, bstart);
   PC_COUNT_LAUNCH(1);
   if (cudaStreamSynchronize(s) != cudaSuccess) return PC_E_CUDA;

@@ -15,6 +15,8 @@ thread_local unsigned long long tl_pc_launches = 0;
 #include <chrono>
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const bool g_prof = getenv("PC_PROFILE") != nullptr;
+#define PC_MULTI_STREAM_MAX ((size_t)1 << 18)        /* batches below this many jobs run their segments on side streams */
+static const bool g_serial = getenv("PC_SERIAL_SEGMENTS") != nullptr;      /* experiments: keep every batch on one stream */
 #define PC_DEVICE_ORDER_MIN ((size_t)1 << 16)      /* batches from this size up are ordered on the device (k_order.cu) */
 /* PC_CAPTURE=<file>: every batch handed to pc_submit is appended to <file> (bench.py replays the job stream of a real
  * est-fact run as its device-resident workload).  Record = u32 njobs, u64 arena_bytes, jobs, arena. */
@@ -92,6 +94,9 @@ struct pc_ctx {
   uint32_t ix_n = 0;
   int ix_word = 0;
   double depth_rate = 0.2;
+  PcGrowBuf genome_buf;         /* the buffers behind d_genome / ix_*: kept (and grown) across pc_genome_upload calls */
+  PcIndexBufs ix_bufs;
+  cudaStream_t up = nullptr;    /* uploads and index builds run here, not on the legacy stream */
 };
 
 struct DevBuf {
@@ -166,6 +171,11 @@ struct pc_stream {
   double op_ms[PC_OP_COUNT] = {0};
   uint64_t op_launches[PC_OP_COUNT] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  /* side streams: the (op, class) segments of a SMALL batch are independent and each kernel is latency-bound (a grid
+   * of a few dozen CTAs waiting for its longest job), so they run side by side instead of one after the other */
+  static constexpr int NSIDE = 4;
+  cudaStream_t side[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;
   std::vector<cudaEvent_t> ev_free;
 };
@@ -187,31 +197,36 @@ extern "C" pc_ctx *pc_ctx_create(int device) {
   pc_ctx *c = new pc_ctx();
   c->device = device;
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->sm_count = sms;
+  else if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->up, cudaStreamNonBlocking) != cudaSuccess) { fail(PC_E_CUDA, "%s", "pc_ctx_create: stream"); delete c; return nullptr; }
   return c;
 }
 
 extern "C" void pc_ctx_destroy(pc_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_genome); cudaFree(c->ix_keys); cudaFree(c->ix_pos); cudaFree(c->ix_bstart);
+  c->genome_buf.release();
+  for (PcGrowBuf *b : {&c->ix_bufs.keys_in, &c->ix_bufs.keys_out, &c->ix_bufs.pos_in, &c->ix_bufs.pos_out, &c->ix_bufs.tmp, &c->ix_bufs.bstart}) b->release();
+  if (c->up) cudaStreamDestroy(c->up);
   delete c;
 }
 
 extern "C" int pc_genome_upload(pc_ctx *c, const char *genome, size_t len, int word_len, double depth_rate) {
   if (!c || !genome || word_len <= 0 || len >= 0xfffffff0ull) return fail(PC_E_ARG, "%s", "pc_genome_upload: bad argument");
   CU(cudaSetDevice(c->device));
-  cudaFree(c->d_genome); cudaFree(c->ix_keys); cudaFree(c->ix_pos); cudaFree(c->ix_bstart);
   c->d_genome = nullptr; c->ix_keys = nullptr; c->ix_pos = nullptr; c->ix_bstart = nullptr;
-  CU(cudaMalloc(&c->d_genome, len + 16));
-  CU(cudaMemset(c->d_genome, 0, len + 16));
-  CU(cudaMemcpy(c->d_genome, genome, len, cudaMemcpyHostToDevice));
+  if (c->genome_buf.reserve(len + 16)) return fail(PC_E_NOMEM, "%s", "pc_genome_upload: device allocation failed");
+  c->d_genome = (uint8_t *)c->genome_buf.p;
+  CU(cudaMemsetAsync(c->d_genome + len, 0, 16, c->up));
+  CU(cudaMemcpyAsync(c->d_genome, genome, len, cudaMemcpyHostToDevice, c->up));
   c->genome_len = (uint32_t)len;
   c->ix_word = word_len;
   c->depth_rate = depth_rate;
-  int rc = pc_build_index(c->d_genome, c->genome_len, word_len, &c->ix_keys, &c->ix_pos, &c->ix_n, &c->ix_bstart, &c->ix_shift, 0);
+  int rc = pc_build_index(c->d_genome, c->genome_len, word_len, c->ix_bufs, &c->ix_keys, &c->ix_pos, &c->ix_n, &c->ix_bstart, &c->ix_shift, c->up);
   if (rc) return fail(rc, "%s", "pc_genome_upload: index build failed");
-  CU(cudaDeviceSynchronize());
+  CU(cudaStreamSynchronize(c->up));
   return 0;
 }
 
@@ -239,6 +254,10 @@ extern "C" pc_stream *pc_stream_create(pc_ctx *c) {
   DevBuf *bufs[7] = {&st->pool, &st->arena, &st->var, &st->jobs, &st->res, &st->idx, &st->lcs_best};
   for (int i = 0; i < 7; ++i) bufs[i]->carve(cur, sizes[i]);
   if (st->pin_idx.reserve(1u << 16) || st->pin_lcs.reserve(1u << 14)) { pc_stream_destroy(st); return nullptr; }
+  bool ok = cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < pc_stream::NSIDE && ok; ++k)
+    ok = cudaStreamCreateWithFlags(&st->side[k], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&st->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { fail(PC_E_CUDA, "%s", "pc_stream_create: side streams"); pc_stream_destroy(st); return nullptr; }
   return st;
 }
 
@@ -255,6 +274,8 @@ extern "C" void pc_stream_destroy(pc_stream *st) {
   if (st->pin_parts.p) cudaFreeHost(st->pin_parts.p);
   for (auto &e : st->ev_pending) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
   for (auto e : st->ev_free) cudaEventDestroy(e);
+  if (st->ev_fork) cudaEventDestroy(st->ev_fork);
+  for (int k = 0; k < pc_stream::NSIDE; ++k) { if (st->ev_join[k]) cudaEventDestroy(st->ev_join[k]); if (st->side[k]) cudaStreamDestroy(st->side[k]); }
   cudaStreamDestroy(st->s);
   delete st;
 }
@@ -387,9 +408,26 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
   B.pool = (uint8_t *)st->pool.p; B.pool_cap = st->pool.cap; B.pool_need = st->d_pool_need;
   B.slots = 1; B.max_warps = st->max_warps; B.n_dev = nullptr;
   B.ix_keys = c->ix_keys; B.ix_pos = c->ix_pos; B.ix_bstart = c->ix_bstart; B.ix_shift = c->ix_shift; B.ix_n = c->ix_n; B.ix_word = c->ix_word; B.depth_rate = c->depth_rate;
+  int nseg_live = 0;
+  for (int sg = 0; sg < NSEG; ++sg) nseg_live += seg[sg].n != 0;
+  // small batch, several segments, no per-op timing wanted, not a retry round: fork over the side streams, each with
+  // its own quarter of the scratch pool
+  const bool multi = nseg_live > 1 && nsel < PC_MULTI_STREAM_MAX && !(st->timers || g_prof) && st->max_warps == 0 && !g_serial;
+  constexpr int NS = pc_stream::NSIDE;
+  if (multi) CU(cudaEventRecord(st->ev_fork, st->s));
+  unsigned used_side = 0;
+  int next_side = 0;
   size_t i = 0;
   for (int sg = 0; sg < NSEG; ++sg) {
     if (!seg[sg].n) continue;
+    cudaStream_t ss = st->s;
+    if (multi) {
+      const int k = next_side++ % NS;
+      ss = st->side[k];
+      if (!(used_side >> k & 1u)) { CU(cudaStreamWaitEvent(ss, st->ev_fork, 0)); used_side |= 1u << k; }
+      const unsigned long long share = (st->pool.cap / NS) & ~255ull;
+      B.pool = (uint8_t *)st->pool.p + share * (unsigned long long)k; B.pool_cap = share;
+    }
     const uint32_t op = (uint32_t)(sg / 4);
     const int cls = sg & 3;
     const size_t j = i + seg[sg].n;
@@ -399,10 +437,10 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
     B.n = (int)(j - i);
     if (op == PC_OP_SEED && !c->d_genome) return fail(PC_E_ARG, "%s", "PC_OP_SEED before pc_genome_upload");
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (st->timers || g_prof) { e0 = get_event(st); e1 = get_event(st); cudaEventRecord(e0, st->s); }
+    if (st->timers || g_prof) { e0 = get_event(st); e1 = get_event(st); cudaEventRecord(e0, ss); }
     const unsigned long long before = tl_pc_launches;
     if (op == PC_OP_SEED) {
-      pc_launch_seed(B, st->s, c->sm_count);
+      pc_launch_seed(B, ss, c->sm_count);
     } else if (op == PC_OP_LCS) {
       // [best slots | block prefix] in one device buffer; the prefix comes from the host copy of the jobs
       const size_t best_b = (8ull * B.n + 255u) & ~(size_t)255u;
@@ -411,7 +449,7 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
       uint64_t tot = 0;
       if (on_device) {
         tot = seg[sg].lcs_blocks;
-        pc_lcs_prefix(d_jobs, d_order + i, B.n, PC_LCS_TPB, PC_LCS_MAX_S2, d_prefix, st->s);
+        pc_lcs_prefix(d_jobs, d_order + i, B.n, PC_LCS_TPB, PC_LCS_MAX_S2, d_prefix, ss);
       } else {
         PinBuf &pl = st->pin_lcs;
         if (pl.reserve((size_t)B.n + 1)) return PC_E_NOMEM;
@@ -421,34 +459,37 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
           tot += (uint64_t)pc_lcs_blocks(jb.b_len, (int)jb.a_len);
         }
         pl.p[B.n] = (uint32_t)tot;
-        CU(cudaMemcpyAsync(d_prefix, pl.p, 4ull * (B.n + 1), cudaMemcpyHostToDevice, st->s));
+        CU(cudaMemcpyAsync(d_prefix, pl.p, 4ull * (B.n + 1), cudaMemcpyHostToDevice, ss));
       }
       if (tot >= 0x7fffffffull) return fail(PC_E_RANGE, "%s", "LCS batch too large for one launch");
-      pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, d_prefix, (uint32_t)tot, max_l2, st->s);
+      pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, d_prefix, (uint32_t)tot, max_l2, ss);
     } else if (op == PC_OP_GAP && cls < 3) {
-      pc_launch_gap_pairs(cls, B, (int)max_l1, st->s, c->sm_count);
+      pc_launch_gap_pairs(cls, B, (int)max_l1, ss, c->sm_count);
     } else if (op == PC_OP_BORDERS && cls < 3) {
-      pc_launch_borders_packed(cls, B, (int)std::min<uint32_t>(seg[sg].max_t, PC_BORDERS_FAST_MAX_T), st->s, c->sm_count);
+      pc_launch_borders_packed(cls, B, (int)std::min<uint32_t>(seg[sg].max_t, PC_BORDERS_FAST_MAX_T), ss, c->sm_count);
     } else if (op == PC_OP_BORDERS) {
       // taller than the packed classes: row-chunked packed sweep; what does not fit 16-bit scores goes to the wavefront kernel
-      pc_launch_borders_chunked(B, d_slow + i, d_slow_count + sg, st->s, c->sm_count);
+      pc_launch_borders_chunked(B, d_slow + i, d_slow_count + sg, ss, c->sm_count);
       PcDevBatch S = B;
       S.idx = d_slow + i; S.n_dev = d_slow_count + sg;
-      pc_launch_dp((int)op, S, st->s, c->sm_count);
+      pc_launch_dp((int)op, S, ss, c->sm_count);
     } else if ((op == PC_OP_EDIT || op == PC_OP_KBAND) && cls < 3) {
       // one job per thread, bit-parallel; what it cannot answer bit-exactly is listed for the wavefront kernel
-      pc_launch_myers((int)op, cls, B, d_slow + i, d_slow_count + sg, st->s, c->sm_count);
+      pc_launch_myers((int)op, cls, B, d_slow + i, d_slow_count + sg, ss, c->sm_count);
       PcDevBatch S = B;
       S.idx = d_slow + i; S.n_dev = d_slow_count + sg;
-      pc_launch_dp((int)op, S, st->s, c->sm_count);
+      pc_launch_dp((int)op, S, ss, c->sm_count);
     } else {
-      pc_launch_dp((int)op, B, st->s, c->sm_count);
+      pc_launch_dp((int)op, B, ss, c->sm_count);
     }
     st->op_launches[op] += tl_pc_launches - before;
     if (g_prof) g_op_launches[op] += 1;
-    if (st->timers || g_prof) { cudaEventRecord(e1, st->s); st->ev_pending.push_back({(int)op, {e0, e1}}); }
+    if (st->timers || g_prof) { cudaEventRecord(e1, ss); st->ev_pending.push_back({(int)op, {e0, e1}}); }
     i = j;
   }
+  if (multi)
+    for (int k = 0; k < NS; ++k)
+      if (used_side >> k & 1u) { CU(cudaEventRecord(st->ev_join[k], st->side[k])); CU(cudaStreamWaitEvent(st->s, st->ev_join[k], 0)); }
   CU(cudaMemcpyAsync(st->h_pool_need, st->d_pool_need, 8, cudaMemcpyDeviceToHost, st->s));
   CU(cudaGetLastError());
   PROF(4, tp);
@@ -562,6 +603,14 @@ extern "C" int pc_submit_parts(pc_stream *st, pc_ctx *genome_ctx, const pc_part 
     nv = (nv + p.var_out_bytes + 15u) & ~(size_t)15u;
   }
   if (nj == 0) return 0;
+  if (g_capture) {                                            /* every part as the batch its lane was */
+    std::lock_guard<std::mutex> lk(g_capture_mu);
+    for (const Pending::Part &q : P.parts) {
+      const uint32_t n32 = (uint32_t)q.p.njobs; const uint64_t ab = q.p.arena_bytes;
+      fwrite(&n32, 4, 1, g_capture); fwrite(&ab, 8, 1, g_capture);
+      fwrite(q.p.jobs, sizeof(pc_job), (size_t)q.p.njobs, g_capture); fwrite(q.p.arena, 1, q.p.arena_bytes, g_capture);
+    }
+  }
   if (nj >= 0x7fffffffull || na >= 0xfff00000ull || nv >= 0xfff00000ull) return fail(PC_E_RANGE, "%s", "pc_submit_parts: merged batch exceeds 32-bit offsets");
   CU(cudaSetDevice(c->device));
   const size_t np = P.parts.size();

@@ -156,7 +156,23 @@ void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count);
 int pc_lcs_blocks(long long l1, int l2);
 int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t *d_blk_prefix, uint32_t total_blocks, int max_l2,
                   cudaStream_t s);
-int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, unsigned long long **keys, uint32_t **pos,
+/* device buffers of one genome index; they only grow, so a context that is reused for the next genome (the engine keeps
+ * idle contexts) builds its index without a single cudaMalloc / cudaFree */
+struct PcGrowBuf {
+  void *p = nullptr; size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return PC_E_NOMEM; }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PcIndexBufs { PcGrowBuf keys_in, keys_out, pos_in, pos_out, tmp, bstart; };
+int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, PcIndexBufs &bufs, unsigned long long **keys, uint32_t **pos,
                    uint32_t *n_out, uint32_t **bstart, int *shift, cudaStream_t s);
 extern unsigned long long g_pc_launches;
 extern thread_local unsigned long long tl_pc_launches;      /* launches issued by the calling thread (per-stream accounting) */

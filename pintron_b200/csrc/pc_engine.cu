@@ -76,6 +76,7 @@ struct Gpu {
   std::mutex mu;                               // sessions, segments, lane ownership
   std::map<uint32_t, Session *> sessions;
   std::vector<std::thread> threads;
+  std::vector<pc_ctx *> idle_ctx;              // contexts of closed sessions: their device buffers serve the next genome
   size_t default_seg = 0;
 };
 
@@ -146,7 +147,7 @@ void wake_lane(pce_lane *l, int rc) {
 }
 
 // One submission loop.  Claims every POSTED lane of one session (a batch runs against one genome), runs them as one
-// device batch, marks them DONE.  Two loops per GPU: while one waits for its batch the other gathers the next.
+// device batch, marks them DONE.  One loop per GPU by default (PC_ENGINE_THREADS overrides).
 void engine_loop(pc_engine *e, Gpu *g, int which) {
   cudaSetDevice(g->device);
   pc_stream *st = pc_stream_create(g->base_ctx);
@@ -214,7 +215,7 @@ void engine_loop(pc_engine *e, Gpu *g, int which) {
     const unsigned long long launches0 = tl_pc_launches;
     if (!rc) rc = pc_submit_parts(st, S->ctx, parts.data(), (int)parts.size());
     if (!rc) rc = pc_stream_sync(st);
-    else pc_stream_sync(st);                   // drain whatever was enqueued before the failure
+    else { pc_stream_sync(st); cudaDeviceSynchronize(); }      // drain whatever was enqueued before the failure (side streams included)
     if (rc && S) fprintf(stderr, "* ERROR pc_engine: batch of %zu lane(s) failed: %s\n", mine.size(), pc_last_error());
     if (S) {
       std::lock_guard<std::mutex> lk(g->mu);
@@ -243,7 +244,7 @@ extern "C" pc_engine *pc_engine_create(const int *devices, int ndev, size_t segm
   pc_engine *e = new pc_engine();
   const char *env = getenv("PC_ENGINE_SEGMENT_MB");
   if (segment_bytes == 0) segment_bytes = (env && atol(env) > 0 ? (size_t)atol(env) : 384) << 20;
-  int nthreads = 2;
+  int nthreads = 1;          // one submission loop keeps a B200 fed (side streams overlap the kernels of a batch); measured: more only split the batches
   if (const char *t = getenv("PC_ENGINE_THREADS")) if (atoi(t) >= 1 && atoi(t) <= 8) nthreads = atoi(t);
   for (int i = 0; i < ndev; ++i) {
     Gpu *g = new Gpu();
@@ -266,6 +267,7 @@ extern "C" void pc_engine_destroy(pc_engine *e) {
     if (g->hdr) { __atomic_fetch_add(&g->hdr->doorbell, 1u, __ATOMIC_SEQ_CST); pce_futex(&g->hdr->doorbell, FUTEX_WAKE, 64, nullptr); }
     for (auto &t : g->threads) t.join();
     for (auto &kv : g->sessions) { pc_ctx_destroy(kv.second->ctx); delete kv.second; }
+    for (pc_ctx *c : g->idle_ctx) pc_ctx_destroy(c);
     cudaSetDevice(g->device);
     for (Segment &s : g->segs) {
       if (s.registered) cudaHostUnregister(s.base);
@@ -299,7 +301,11 @@ extern "C" int pc_engine_open(pc_engine *e, const pc_session_req *req, pc_sessio
   S->id = e->next_session.fetch_add(1);
   S->gpu = gi;
   // genome + k-mer index of this session (replaces the per-process suffix tree, src/main-est-fact.c:223-240)
-  S->ctx = pc_ctx_create(g->device);
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (!g->idle_ctx.empty()) { S->ctx = g->idle_ctx.back(); g->idle_ctx.pop_back(); }
+  }
+  if (!S->ctx) S->ctx = pc_ctx_create(g->device);
   if (!S->ctx || pc_genome_upload(S->ctx, req->genome, req->genome_len, req->word_len, req->depth_rate)) {
     pc_ctx_destroy(S->ctx); delete S;
     return PC_E_CUDA;
@@ -393,6 +399,7 @@ extern "C" int pc_engine_close(pc_engine *e, uint32_t session, pc_session_stats 
     }
     g->sessions.erase(S->id);
     if (stats) *stats = S->stats;
+    if (g->idle_ctx.size() < 8) { g->idle_ctx.push_back(S->ctx); S->ctx = nullptr; }
   }
   pc_ctx_destroy(S->ctx);
   delete S;

@@ -115,7 +115,9 @@ typedef struct ef_task {
   ef_arena ar;
   /* outputs of this EST (concatenated in input order by the writer) */
   ef_buf out_raw, out_pest, out_megs, out_pmegs, out_edges;
-  double t_start;
+  /* --max-single-factorization-time: charged with the time this EST's own code has RUN (fibers are suspended while
+   * thousands of others run and while batches are with the engine; the reference times one EST running alone) */
+  uint64_t run_ticks, run_mark, t_start;
 } ef_task;
 
 void pl_push(ef_task *T, ef_plist *l, ef_pairing *x);
@@ -173,6 +175,9 @@ bool add_if_not_exists(ef_task *T, ef_fz *z, ef_fzlist *L);
 
 bool ef_timeout_expired(ef_task *T);
 double ef_now(void);
+uint64_t ef_ticks(void);                    /* cheap monotonic counter (TSC) */
+double ef_ticks_to_s(uint64_t ticks);
+uint64_t ef_task_ticks(const ef_task *T);   /* ticks this task's code has run so far */
 
 /* CPU-time accounting of the per-EST code (diagnostics; printed with the timers) */
 enum { EF_PH_OTHER = 0, EF_PH_SEED, EF_PH_MEG, EF_PH_EMBED, EF_PH_CAND, EF_PH_FILTER, EF_PH_INTRON, EF_PH_REFINE, EF_PH_SMALLEX, EF_PH_OUTPUT, EF_PH_COUNT };

@@ -69,7 +69,10 @@ static void *serve(void *arg) {
   pc_session_req r = {h.gpu, (const char *)pl + sizeof h, (size_t)h.genome_len, h.word_len, h.depth_rate, h.nlanes, h.arena_cap, h.var_cap, h.jobs_cap};
   pc_session_info info;
   atomic_fetch_add(&g_sessions, 1);
+  struct timespec o0, o1;
+  clock_gettime(CLOCK_MONOTONIC, &o0);
   const int rc = pc_engine_open(g_eng, &r, &info);
+  clock_gettime(CLOCK_MONOTONIC, &o1);
   free(pl); pl = NULL;
   if (rc) {
     char msg[600];
@@ -90,13 +93,17 @@ static void *serve(void *arg) {
     memcpy(ok.lane, info.lane, sizeof(uint32_t) * (size_t)info.nlanes);
     if (efd_send(s, EFD_HELLO_OK, &ok, sizeof ok, fds, ok.nsegs)) goto out;
   }
-  say("session %u opened on gpu %d: %d lanes, genome %llu bp", session, gpu, info.nlanes, (unsigned long long)h.genome_len);
+  say("session %u opened on gpu %d: %d lanes, genome %llu bp (genome index + lanes in %.1f ms)", session, gpu, info.nlanes, (unsigned long long)h.genome_len,
+      1e3 * (double)(o1.tv_sec - o0.tv_sec) + 1e-6 * (double)(o1.tv_nsec - o0.tv_nsec));
   for (;;) {
     if (efd_recv(s, &type, &pl, &plen, NULL, 0, NULL)) break;            /* EOF: the client is gone */
     if (type == EFD_BYE) {
       pc_session_stats st;
+      clock_gettime(CLOCK_MONOTONIC, &o0);
       pc_engine_close(g_eng, session, &st);
-      say("session %u closed: %llu batches (%llu lanes merged), %llu jobs, %llu launches, engine busy %.3f s", session,
+      clock_gettime(CLOCK_MONOTONIC, &o1);
+      say("session %u closed in %.1f ms: %llu batches (%llu lanes merged), %llu jobs, %llu launches, engine busy %.3f s", session,
+          1e3 * (double)(o1.tv_sec - o0.tv_sec) + 1e-6 * (double)(o1.tv_nsec - o0.tv_nsec),
           (unsigned long long)st.batches, (unsigned long long)st.lanes_merged, (unsigned long long)st.jobs, (unsigned long long)st.launches, st.busy_s);
       session = 0;
       efd_send(s, EFD_STATS, &st, sizeof st, NULL, 0);

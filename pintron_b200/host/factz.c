@@ -54,7 +54,7 @@ void fzl_remove(ef_fzlist *L, int at) {
 }
 
 bool ef_timeout_expired(ef_task *T) {
-  return ef_now() - T->t_start > (double)T->cfg->max_single_factorization_time;
+  return ef_ticks_to_s(ef_task_ticks(T) - T->t_start) > (double)T->cfg->max_single_factorization_time;
 }
 
 /* ---- embeddings ------------------------------------------------------------------------------------------------ */

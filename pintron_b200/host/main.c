@@ -72,7 +72,7 @@ static bool compute_est_fact(ef_task *T, const run_ctx *R, est_item *it, const e
     }
     prev_p = tp; prev_e = te;
     const double t_meg1 = ef_now();
-    T->t_start = ef_now();
+    T->t_start = ef_task_ticks(T);
     bool timed_out = false;
     ef_phase(EF_PH_EMBED);
     ef_fzlist *L = est_factorizations(T, e, M, &timed_out);
@@ -185,10 +185,13 @@ int main(int argc, char **argv) {
   ef_seq *gen = &gens[0];
   ef_parse_genomic_header(gen);
   ef_ntails_removal(gen);
+  const double tl_genome = ef_now();
   sched_prepare(&cfg, gen);
-  ef_small_exon_index_build(gen->seq, (size_t)gen->len);      /* host-side 6-mer index, while the CUDA context comes up */
+  ef_small_exon_index_build(gen->seq, (size_t)gen->len);      /* host-side 6-mer index, while the engine session opens */
+  const double tl_index = ef_now();
   ef_seq *ests = NULL; size_t nest = 0;
   if (ef_read_fasta("ests.txt", &ests, &nest)) { fprintf(stderr, "* FATAL File ests.txt not found! Terminating\n"); return 1; }
+  const double tl_ests = ef_now();
   FILE *f_raw = open_out("raw-multifasta-out.txt"), *f_megs = open_out("megs.txt"), *f_pmegs = open_out("processed-megs.txt");
   FILE *f_info = open_out("processed-megs-info.txt"), *f_pest = open_out("processed-ests.txt"), *f_edges = open_out("meg-edges.txt");
   double t_io = ef_now() - t_io0;
@@ -232,6 +235,9 @@ int main(int argc, char **argv) {
   const double t_alg0 = ef_now();
   if (sched_run(&cfg, gen, nest, est_task, &R)) return 1;
   const double t_alg = ef_now() - t_alg0;
+  if (!cfg.quiet)
+    fprintf(stderr, "* INFO  timeline (s since start): genome read %.3f, small-exon index %.3f, ESTs read %.3f, dispatch order %.3f, workers done %.3f\n",
+            tl_genome - t0, tl_index - t0, tl_ests - t0, t_alg0 - t0, t_alg0 + t_alg - t0);
 
   const double t_io1 = ef_now();
   pthread_join(wth, NULL);

@@ -46,6 +46,25 @@ double ef_now(void) {
   return (double)tv.tv_sec + 1e-6 * (double)tv.tv_usec;
 }
 
+/* Phase accounting and the per-EST timeout read the clock twice per yield (a hundred yields per EST): the TSC costs a
+ * third of a vDSO gettimeofday.  Its rate is measured against the wall clock over the life of the process. */
+#if defined(__x86_64__)
+#include <x86intrin.h>
+uint64_t ef_ticks(void) { return __rdtsc(); }
+#else
+uint64_t ef_ticks(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec; }
+#endif
+static uint64_t g_tick0;
+static double g_wall0;
+__attribute__((constructor)) static void ticks_init(void) { g_wall0 = ef_now(); g_tick0 = ef_ticks(); }
+double ef_ticks_to_s(uint64_t ticks) {
+  double dt = ef_now() - g_wall0;
+  if (dt < 0.002) { struct timespec ts = {0, 2000000}; nanosleep(&ts, NULL); dt = ef_now() - g_wall0; }      /* too early for a rate: wait 2 ms */
+  const double rate = (double)(ef_ticks() - g_tick0) / dt;
+  return (double)ticks / rate;
+}
+uint64_t ef_task_ticks(const ef_task *T) { return T->run_ticks + (ef_ticks() - T->run_mark); }
+
 /* ---- arena / buffers ------------------------------------------------------------------------------- */
 /* Chunks are kept across ESTs (ar_reset only rewinds): giving big chunks back to the system means munmap, and
  * every munmap interrupts all threads of the process to flush their TLBs — with a dozen workers handling long mRNAs
@@ -212,11 +231,11 @@ static pthread_mutex_t g_stat_mu = PTHREAD_MUTEX_INITIALIZER;
 
 /* ---- where the host time goes: CPU seconds per phase of the per-EST code (fibers only run between yields) ------ */
 static __thread int tl_phase;
-static __thread double tl_mark;
-static __thread double tl_phase_s[EF_PH_COUNT];
+static __thread uint64_t tl_mark;
+static __thread uint64_t tl_phase_s[EF_PH_COUNT];      /* ticks */
 static double g_phase_s[EF_PH_COUNT];
 static inline void phase_account(void) {
-  const double t = ef_now();
+  const uint64_t t = ef_ticks();
   tl_phase_s[tl_phase] += t - tl_mark;
   tl_mark = t;
 }
@@ -246,7 +265,8 @@ static void lane_grow(group *g, size_t arena_cap, int jobs_cap, size_t var_cap) 
 static void fiber_entry(void) {
   fiber *f = tl_fiber;
   worker *w = tl_worker;
-  tl_phase = EF_PH_OTHER; tl_mark = ef_now();
+  tl_phase = EF_PH_OTHER; tl_mark = ef_ticks();
+  f->task.run_ticks = 0; f->task.run_mark = tl_mark;
   w->fn(&f->task, f->index, w->user);
   phase_account();
   f->state = F_DONE;
@@ -310,6 +330,7 @@ void dp_wait(void) {
   f->state = F_WAITING;
   f->need_valid = false;
   phase_account();
+  f->task.run_ticks += tl_mark - f->task.run_mark;
   f->phase = tl_phase;
 #if EF_FAST_SWITCH
   ctx_switch(&f->sp, tl_worker->main_sp);
@@ -317,7 +338,8 @@ void dp_wait(void) {
   swapcontext(&f->ctx, &tl_worker->main_ctx);
 #endif
   /* resumed: results are in the group's batch buffers */
-  tl_phase = f->phase; tl_mark = ef_now();
+  tl_phase = f->phase; tl_mark = ef_ticks();
+  f->task.run_mark = tl_mark;
   for (int i = 0; i < f->nreq; ++i) {
     const int32_t st = f->grp->res[(size_t)(f->base + i) * PC_RES_INTS];
     if (st < 0 && st != PC_E_OUTCAP) {
@@ -514,7 +536,7 @@ static void *worker_main(void *arg) {
   g_t_fibers += w->t_fibers; g_t_gather += w->t_gather; g_t_submit += w->t_submit;
   g_t_init += tw1 - tw0; g_t_fini += ef_now() - tw2;
   g_t_end_sum += tw2; if (g_t_end_min == 0 || tw2 < g_t_end_min) g_t_end_min = tw2;
-  for (int i = 0; i < EF_PH_COUNT; ++i) g_phase_s[i] += tl_phase_s[i];
+  for (int i = 0; i < EF_PH_COUNT; ++i) g_phase_s[i] += ef_ticks_to_s(tl_phase_s[i]);
   pthread_mutex_unlock(&g_stat_mu);
   return NULL;
 }

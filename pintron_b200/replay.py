@@ -20,7 +20,7 @@ def capture(exe, workdir, threads=None, device=None):
     """Run est-fact in `workdir` with PC_CAPTURE set; returns the capture file path."""
     cap = os.path.join(workdir, "jobs.capture")
     env = dict(os.environ, PC_CAPTURE=cap)
-    cmd = [exe, "--no-aux-outputs"]
+    cmd = [exe, "--no-aux-outputs", "--engine", "inproc"]      # the capture hook lives in the library of THIS process
     if threads:
         cmd += ["--threads", str(threads)]
     if device is not None:

@@ -73,6 +73,11 @@ def main():
         json.dump(exp, open(os.path.join(dst, "expected.json"), "w"), indent=1, sort_keys=True)
         shutil.rmtree(tmp)
         print(case, exp["raw-multifasta-out.txt"])
+    # the reference's own pipeline-level golden for test-AMBN (regressionTest/test-AMBN/referenceOutput/full.json, older key
+    # names): the 13 predicted introns as (relative start, relative end, supporting ESTs) — tests/test_pipeline.py
+    full = json.load(open(os.path.join(REF, "regressionTest", "test-AMBN", "referenceOutput", "full.json")))
+    introns = sorted((v["relative start"], v["relative end"], v["number supporting EST"]) for v in full["introns"].values())
+    json.dump(introns, open(os.path.join(out_root, "test-AMBN", "golden_introns.json"), "w"))
 
 
 if __name__ == "__main__":
