@@ -1,26 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — est-fact hot path on synthetic data of BASELINE.json's shapes (default C3: 200 kbp genomic region x ESTs of
-300-800 nt, 100 000 per GPU; --workload C4: 2 Mbp multi-gene locus x ESTs and mRNAs), one rank per GPU.
+"""bench.py — PIntron est-fact on B200: ESTs/s on synthetic data of BASELINE.json's shapes, one rank per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--workload C3|C4]     our arm (CUDA through the C ABI)
-  python bench.py --impl reference ...                                                   the reference est-fact on the host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C4|C5]     our arm (CUDA through the C ABI)
+  python bench.py --impl reference ...                                          the reference est-fact on the host cores
 
-Two legs per run, ESTs/s as the metric:
-  value  one step = one pass of the DEVICE hot path over a batch that is already resident in HBM: EVERY device job the
-         shipped est-fact program issues for R ESTs of this rank (maximal-pairing discovery, compute_alignment,
-         K_band_edit_distance, edit_distance, refine_borders, compute_gap_alignment, find_longest_affix, the genome LCS
-         scan ...), recorded from a real run (PC_CAPTURE, pintron_b200/replay.py) and merged into ONE batch; timed with
-         CUDA events on the launching stream, L2 flushed between steps.
-  e2e    one step = one run of the shipped est-fact PROGRAM (pintron_b200/bin/est-fact: C host + libpintron_cuda.so
-         through the C ABI) on E ESTs per GPU, exactly as pintron.py calls it: genomic.txt / ests.txt in the working
-         directory, process start, CUDA context, index build, every H2D / D2H copy, the host control flow and the six
-         output files are all inside the timed region (wall clock of the process).  This is the number to hold
-         against the reference arm (`--impl reference`: the unmodified est-fact, one process per host core).
-ESTs shard across ranks with no data-path collective: weak scaling, genome index replicated.
+Workload (default C3 = BASELINE.json configs[2]: 200 kbp genomic region x 100 000 ESTs of 300-800 nt per GPU, weak
+scaling; ESTs shard across ranks with no data-path collective, genome index replicated: SURVEY.md §8(e)).
+
+  value   device-resident leg.  One step = EVERY device batch the shipped est-fact really issues for R ESTs of this rank
+          — the engine's merged lane batches exactly as it formed them in a real run (PC_CAPTURE, pintron_b200/replay.py),
+          all inputs already in HBM — submitted one after the other through pc_submit_device + pc_stream_sync, timed
+          with CUDA events on the library's stream, L2 flushed between steps.  Launch overheads of the real batching are
+          inside; host control flow and copies are not.
+  e2e     the shipped est-fact PROGRAM on E ESTs per GPU exactly as pintron.py calls it (genomic.txt / ests.txt in the
+          working directory, no arguments beyond execution knobs): process start, FASTA parsing, engine session (genome
+          upload + index build), all host control flow, every H2D / D2H copy through pinned lanes, six output files;
+          wall clock of the process.  The GPU server est-factd is resident, as deployed (started before the warm-up);
+          `e2e_cold` is one run with the engine inside the process (CUDA context creation inside the timed region).
+          This is the number to hold against `--impl reference`.
+  kernels the same jobs as ONE merged batch with per-op CUDA-event timers: GCUPS and INT-ALU fractions per kernel
+          (`roofline` = the dominant one) at full occupancy.
+  parity  our five output files on the first P ESTs == the reference's (the cpu_baseline run's outputs, md5).
 """
 import argparse
+import hashlib
 import json
-import math
 import os
 import shutil
 import subprocess
@@ -35,13 +39,25 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "est_fact_ESTs_per_sec"
-WORKLOADS = {"C3": "C3: synthetic 200 kbp genomic region x ESTs of 300-800 nt",
-             "C4": "C4: synthetic 2 Mbp multi-gene locus x ESTs (80 %) and mRNAs of 1-6 kbp (20 %), long introns, polyA tails"}
-OPS_PER_CELL = {"ALIGN": 5, "KBAND": 5, "EDIT": 5, "BORDERS": 5, "GAP": 9, "AFFIX": 5, "SUFCUT": 5, "PRECUT": 5}      # useful int ops per DP cell, SURVEY.md §8(d)
-KERNEL_OF = {"GAP": "k_gap_pairs<8> (compute_gap_alignment)", "BORDERS": "k_warp_per_job<BORDERS> (general_refine_borders)",
-             "EDIT": "k_warp_per_job<EDIT> (edit_distance)", "KBAND": "k_warp_per_job<KBAND> (K_band_edit_distance)",
+WORKLOADS = {"C3": ("C3: synthetic 200 kbp genomic region x 100000 ESTs of 300-800 nt per GPU", 100000, 20000),
+             "C4": ("C4: synthetic 2 Mbp multi-gene locus x 30000 reads per GPU (80 % ESTs, 20 % mRNAs of 1-6 kbp, long introns, polyA tails)", 30000, 10000),
+             "C5": ("C5: synthetic 200-exon titin-like gene x 200 full-length / partial mRNAs of 10-100 kbp per GPU", 200, 100)}
+# useful integer ops per cell of the REFERENCE's recurrences.  GAP cells are plane-cells (3 per DP
+# position: L, G, R), 9 ops per position = 3 per plane-cell; LCS: compare, two N tests, run update
+OPS_PER_CELL = {"ALIGN": 5, "KBAND": 5, "EDIT": 5, "BORDERS": 5, "GAP": 3, "AFFIX": 5, "SUFCUT": 5, "PRECUT": 5, "LCS": 4}
+KERNEL_OF = {"GAP": "k_gap_pairs (compute_gap_alignment)", "BORDERS": "k_borders_packed (general_refine_borders)",
+             "EDIT": "k_myers<EDIT> (edit_distance)", "KBAND": "k_myers<KBAND> (K_band_edit_distance)",
              "ALIGN": "k_warp_per_job<ALIGN> (compute_alignment)", "AFFIX": "k_warp_per_job<AFFIX> (find_longest_affix)",
              "LCS": "k_lcs (find_longest_common_factor_dp)", "SEED": "k_seed (build_vertex_set)"}
+FILES = ["raw-multifasta-out.txt", "processed-ests.txt", "megs.txt", "processed-megs.txt", "meg-edges.txt"]
+OP_NAMES = ["ALIGN", "KBAND", "EDIT", "BORDERS", "GAP", "AFFIX", "SUFCUT", "PRECUT", "LCS", "SEED"]
+
+
+def config_of(workload):
+    """The SAME object in both arms (the driver compares it)."""
+    return {"workload": WORKLOADS[workload][0], "ests_per_gpu": WORKLOADS[workload][1],
+            "sharding": "ESTs dealt to ranks, genome index replicated per GPU, no data-path collective",
+            "l2": "flushed between timed steps (256 MB write)"}
 
 
 class ClockSampler(threading.Thread):
@@ -92,84 +108,93 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
 
 
-def run_reference(args, rank, world):
-    """The UNMODIFIED reference est-fact (oracle/_ref/est-fact), one process per host core over EST shards."""
-    if rank != 0:
-        return
-    from pintron_b200.synth import Synth
-    exe = os.path.join(ROOT, "oracle", "_ref", "est-fact")
-    cores = os.cpu_count() or 1
-    if not os.path.exists(exe):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/est-fact not built (make -C oracle ref)"}))
-        return
-    per_core = args.ref_reads_per_core
-    synth = Synth(args.workload, reads=cores * per_core)
-    gtxt = synth.genome_fasta()
-    tmp = tempfile.mkdtemp(prefix="pintron_ref_")
-    dirs = []
-    for c in range(cores):
-        d = os.path.join(tmp, f"shard{c}")
-        os.makedirs(d)
-        open(os.path.join(d, "genomic.txt"), "wb").write(gtxt)
-        open(os.path.join(d, "ests.txt"), "wb").write(synth.ests_fasta(c * per_core, per_core))
-        dirs.append(d)
+def _log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
-    def one_step():
+
+def md5_files(d):
+    return {f: hashlib.md5(open(os.path.join(d, f), "rb").read()).hexdigest() for f in FILES}
+
+
+class RefShards:
+    """The UNMODIFIED reference est-fact (oracle/_ref/est-fact), one process per host core over contiguous EST shards
+    (each rebuilding its suffix tree: the reference's real cost)."""
+
+    def __init__(self, workload, per_core, cores=None):
+        from pintron_b200.synth import Synth, ests_fasta_parallel
+        self.exe = os.path.join(ROOT, "oracle", "_ref", "est-fact")
+        self.cores = cores or (os.cpu_count() or 1)
+        self.per_core, self.n = per_core, per_core * self.cores
+        self.tmp = tempfile.mkdtemp(prefix="pintron_ref_")
+        gtxt = Synth(workload, reads=1).genome_fasta()
+        ests = ests_fasta_parallel(workload, self.n, 0, self.n, procs=max(1, self.cores - 1))
+        recs = ests.split(b"\n>")
+        recs = [recs[0]] + [b">" + r for r in recs[1:]]
+        assert len(recs) == self.n, (len(recs), self.n)
+        self.all_ests = ests
+        self.dirs = []
+        for c in range(self.cores):
+            d = os.path.join(self.tmp, f"shard{c:03d}")
+            os.makedirs(d)
+            open(os.path.join(d, "genomic.txt"), "wb").write(gtxt)
+            open(os.path.join(d, "ests.txt"), "wb").write(b"\n".join(recs[c * per_core:(c + 1) * per_core]) + (b"\n" if not recs[(c + 1) * per_core - 1].endswith(b"\n") else b""))
+            self.dirs.append(d)
+        self.genome_fasta = gtxt
+
+    def available(self):
+        return os.path.exists(self.exe)
+
+    def step(self):
         t0 = time.perf_counter()
-        procs = [subprocess.Popen([exe], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for d in dirs]
+        procs = [subprocess.Popen([self.exe], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for d in self.dirs]
         rcs = [p.wait() for p in procs]
         assert all(r == 0 for r in rcs), rcs
         return time.perf_counter() - t0
 
+    def md5s(self):
+        """md5 of the shard outputs concatenated in shard order (== the single run: ESTs are independent)."""
+        out = {}
+        for f in FILES:
+            h = hashlib.md5()
+            for d in self.dirs:
+                h.update(open(os.path.join(d, f), "rb").read())
+            out[f] = h.hexdigest()
+        return out
+
+    def close(self):
+        shutil.rmtree(self.tmp, ignore_errors=True)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cfg = config_of(args.workload)
+    sh = RefShards(args.workload, args.ref_reads_per_core)
+    if not sh.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/est-fact not built (make -C oracle ref)"}))
+        return
     for _ in range(args.warmup):
-        one_step()
-    times = [one_step() for _ in range(args.steps)]
-    shutil.rmtree(tmp, ignore_errors=True)
-    n = cores * per_core
+        sh.step()
+    times = [sh.step() for _ in range(args.steps)]
     sec = sum(times) / len(times)
-    v = n / sec
-    sample = f"{n} {args.workload} ESTs per step = {cores} shards x {per_core}, one est-fact process per core, each rebuilding its suffix tree"
+    v = sh.n / sec
+    sample = (f"{sh.n} of the {cfg['ests_per_gpu']} {args.workload} ESTs per step = {sh.cores} shards x {sh.per_core}, one unmodified est-fact process "
+              f"per host core, each building its own suffix tree; whole-process wall clock")
+    sh.close()
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "ESTs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload] + " (bounded sample)", "reads_per_step": n},
-        "cpu_baseline": {"value": v, "unit": "ESTs/s", "cores": cores, "kind": "reference", "sample": sample},
+        "dtype": "int32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": v, "unit": "ESTs/s", "cores": sh.cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "ESTs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def cpu_baseline_sample(workload="C3", seconds_budget=20.0):
-    """Reference est-fact on a bounded sample with every host core (kind=reference), else the oracle port."""
-    from pintron_b200.synth import Synth
-    exe = os.path.join(ROOT, "oracle", "_ref", "est-fact")
+def host_threads(world_gpus_on_box):
+    """est-fact worker threads per GPU: this GPU's share of the host cores (cores // GPUs of the BOX, whatever N is, so
+    that the N = 1 run of a scaling series uses what one GPU gets at N = 8), minus room for the engine and the writer."""
     cores = os.cpu_count() or 1
-    if not os.path.exists(exe):
-        return None
-    per_core = 150 if workload == "C3" else 100
-    synth = Synth(workload, reads=cores * per_core)
-    tmp = tempfile.mkdtemp(prefix="pintron_cpu_")
-    gtxt = synth.genome_fasta()
-    dirs = []
-    for c in range(cores):
-        d = os.path.join(tmp, f"s{c}")
-        os.makedirs(d)
-        open(os.path.join(d, "genomic.txt"), "wb").write(gtxt)
-        open(os.path.join(d, "ests.txt"), "wb").write(synth.ests_fasta(c * per_core, per_core))
-        dirs.append(d)
-    t0 = time.perf_counter()
-    procs = [subprocess.Popen([exe], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for d in dirs]
-    rcs = [p.wait() for p in procs]
-    sec = time.perf_counter() - t0
-    shutil.rmtree(tmp, ignore_errors=True)
-    if any(rcs):
-        return None
-    n = cores * per_core
-    return {"value": n / sec, "unit": "ESTs/s", "cores": cores, "kind": "reference",
-            "sample": f"{n} {workload} ESTs, {cores} est-fact processes (one per core, {per_core} ESTs each), wall {sec:.2f} s"}
-
-
-def _log(msg):
-    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+    share = max(1, cores // max(1, world_gpus_on_box))
+    return share - 2 if share >= 8 else max(1, share - 1)
 
 
 def main():
@@ -178,37 +203,37 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C3", choices=["C3", "C4"],
-                    help="synthetic shape (pintron_b200/synth.py).  C3 = BASELINE.json configs[2] (200 kbp x 100 000 ESTs per GPU), the default: "
-                         "it finishes in two minutes.  C4 = configs[3] (2 Mbp multi-gene locus, ESTs + mRNAs): about one read per thousand is an "
-                         "mRNA with a thousand candidate embeddings and end exons of several kbp (a minute each for the reference), so a run "
-                         "is longer and noisier")
-    ap.add_argument("--reads", type=int, default=None, help="ESTs per GPU per step, device leg (default 20000 for C3, 10000 for C4)")
-    ap.add_argument("--e2e-reads", type=int, default=None, help="ESTs per GPU per step, whole-program leg (default 100000 C3, 30000 C4)")
-    ap.add_argument("--e2e-max-steps", type=int, default=2)
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=None, help="ESTs per GPU per step, device legs (default 20000 C3)")
+    ap.add_argument("--e2e-reads", type=int, default=None, help="ESTs per GPU per step, whole-program leg (default = the workload's count)")
+    ap.add_argument("--e2e-max-steps", type=int, default=3)
     ap.add_argument("--e2e-max-warmup", type=int, default=1)
-    ap.add_argument("--ref-reads-per-core", type=int, default=None, help="reference arm: ESTs per host core per step (default 200 C3, 150 C4)")
+    ap.add_argument("--threads", type=int, default=None, help="est-fact worker threads per GPU (default: this GPU's share of the cores)")
+    ap.add_argument("--ref-reads-per-core", type=int, default=None, help="reference arm / cpu baseline: ESTs per host core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the whole-program leg (profiling runs: ncu would follow the child)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the whole-program legs (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short C4 / C5 whole-program legs appended to the default run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    c4 = args.workload == "C4"
-    args.reads = args.reads or (10000 if c4 else 20000)
-    args.e2e_reads = args.e2e_reads or (30000 if c4 else 100000)
-    args.ref_reads_per_core = args.ref_reads_per_core or (150 if c4 else 200)
+    name, e2e_default, dev_default = WORKLOADS[args.workload]
+    args.reads = args.reads or dev_default
+    args.e2e_reads = args.e2e_reads or e2e_default
+    if args.ref_reads_per_core is None:
+        args.ref_reads_per_core = {"C3": 1000, "C4": 150, "C5": 2}[args.workload] if args.impl == "reference" else {"C3": 200, "C4": 100, "C5": 1}[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     import torch
     import torch.distributed as dist
     import pintron_b200
+    from pintron_b200 import replay
     from pintron_b200.binding import PC_RES_INTS
-    from pintron_b200.synth import Synth
+    from pintron_b200.synth import Synth, ests_fasta_parallel
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the est-fact hot path has no CPU fallback")
@@ -217,69 +242,134 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     exe = os.path.join(ROOT, "pintron_b200", "bin", "est-fact")
-    if not os.path.exists(exe):
-        raise SystemExit("bench.py: pintron_b200/bin/est-fact is not built (python __graft_entry__.py)")
+    daemon = os.path.join(ROOT, "pintron_b200", "bin", "est-factd")
+    if not (os.path.exists(exe) and os.path.exists(daemon)):
+        raise SystemExit("bench.py: pintron_b200/bin/est-fact / est-factd are not built (python __graft_entry__.py)")
     cores = os.cpu_count() or 1
-    per_gpu = max(1, cores // world)
-    threads = per_gpu if per_gpu <= 4 else per_gpu * 3 // 4      # est-fact worker threads per GPU (few cores per GPU: use them all)
+    gpus_on_box = torch.cuda.device_count()
+    threads = args.threads or host_threads(gpus_on_box)
+    gen_procs = max(1, cores // world - 1)
 
-    # ---- the device workload: the job stream of a real est-fact run over this rank's R ESTs, merged into one batch ----
-    from pintron_b200 import replay
-    from pintron_b200.synth import ests_fasta_parallel
-    synth = Synth(args.workload, reads=args.reads * world)
+    # ---- the resident server (one per box, all GPUs), as deployed ------------------------------------------------
+    tag = os.environ.get("MASTER_PORT", str(os.getpid())) if world > 1 else str(os.getpid())
+    srv_dir = os.path.join(tempfile.gettempdir(), f"pintron_bench_{tag}")
+    sock = os.path.join(srv_dir, "efd.sock")
+    srv = None
+    if local == 0:
+        shutil.rmtree(srv_dir, ignore_errors=True)
+        os.makedirs(srv_dir)
+        t0 = time.perf_counter()
+        srv = subprocess.Popen([daemon, "--socket", sock, "--foreground"], stdout=open(os.path.join(srv_dir, "efd.log"), "wb"), stderr=subprocess.STDOUT)
+        while not os.path.exists(sock):
+            if srv.poll() is not None:
+                raise SystemExit("bench.py: est-factd exited: " + open(os.path.join(srv_dir, "efd.log")).read()[-1500:])
+            time.sleep(0.02)
+        _log(f"est-factd up in {time.perf_counter() - t0:.2f} s ({gpus_on_box} GPU(s))")
+    barrier()
+    env_srv = dict(os.environ, EST_FACTD_SOCKET=sock, EST_FACT_NO_SPAWN="1")
+
+    def est_fact(cwd, form, extra=(), env=None):
+        """One run of the shipped program; returns (seconds, info parsed from its log)."""
+        cmd = [exe, "--threads", str(threads), "--devices", str(local), "--engine", form, *extra]
+        t0 = time.perf_counter()
+        p = subprocess.run(cmd, cwd=cwd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env_srv if form == "daemon" else (env or os.environ))
+        sec = time.perf_counter() - t0
+        err = p.stderr.decode("latin1")
+        assert p.returncode == 0, err[-2000:]
+        info = {}
+        for line in err.splitlines():
+            w = line.replace(",", "").replace(";", "").split()
+            if "bytes host->device" in line:
+                info["h2d"], info["d2h"] = int(w[w.index("host->device:") + 1]), int(w[w.index("device->host:") + 1])
+            if "scheduler:" in line and "workers" in line:
+                info["workers_s"] = float(w[w.index("workers") + 1])
+                info["session_open_s"] = float(w[w.index("after") + 1])
+            if "timeline" in line:
+                info["ests_read_s"] = float(w[w.index("ESTs") + 2])
+            if "@Timer Total" in line:
+                info["program_total_s"] = int(line.split()[-2]) / 1e6
+            if "kernel launches:" in line:
+                info["launches"] = int(w[w.index("launches:") + 1])
+                info["jobs"] = int(w[w.index("jobs:") + 1])
+                info["lane_batches"] = int(w[w.index("batches:") + 1])
+            if "merged device batches" in line:
+                info["device_batches"] = int(w[w.index("merged") - 1])
+            if "thread-seconds" in line:
+                info["per_est_code_thread_s"] = float(w[w.index("code") + 1])
+                info["wait_on_device_thread_s"] = float(w[w.index("device") + 1])
+        return sec, info
+
+    def write_inputs(d, workload, total, start, count):
+        open(os.path.join(d, "genomic.txt"), "wb").write(Synth(workload, reads=1).genome_fasta())
+        open(os.path.join(d, "ests.txt"), "wb").write(ests_fasta_parallel(workload, total, start, count, procs=gen_procs))
+
+    # ---- device workload: the device batches of a real run over this rank's first R ESTs --------------------------
+    synth = Synth(args.workload, reads=1)
     cap_dir = tempfile.mkdtemp(prefix=f"pintron_cap_r{rank}_")
-    open(os.path.join(cap_dir, "genomic.txt"), "wb").write(synth.genome_fasta())
-    open(os.path.join(cap_dir, "ests.txt"), "wb").write(ests_fasta_parallel(args.workload, args.reads * world, rank * args.reads, args.reads,
-                                                                             procs=max(1, cores // world - 1)))
-    _log("inputs written; capture run of est-fact")
-    cap = replay.capture(exe, cap_dir, threads=threads, device=local)
-    _log("capture done; merging")
-    for l in getattr(replay.capture, "last_log", []):
-        _log("  est-fact: " + l.strip()[:400])
-    arena, jobs, var_bytes, n_batches = replay.merge(cap)
+    write_inputs(cap_dir, args.workload, args.e2e_reads * world, rank * args.e2e_reads, args.reads)
+    _log("inputs written; capture run of est-fact (engine in-process, PC_CAPTURE)")
+    cap_file = os.path.join(cap_dir, "jobs.capture")
+    est_fact(cap_dir, "inproc", ("--no-aux-outputs",), env=dict(os.environ, PC_CAPTURE=cap_file))
+    batches = replay.device_batches(cap_file)
+    m_arena, m_jobs, m_var, n_records = replay.merge(cap_file)
     shutil.rmtree(cap_dir, ignore_errors=True)
-    # the genome bytes the device holds are est-fact's: N tails stripped (io-multifasta.c:830); for synthetic ACGT genomes = as is
-    cells = replay.algorithmic_cells(arena, synth.genome, jobs)
-    n = len(jobs)
-    n_reads = args.reads
-    seed_sel = jobs["op"] == 9
-    seed_bytes = int(jobs["a_len"][seed_sel].sum())
-    jobs_per_op = {nm: int((jobs["op"] == i).sum()) for i, nm in enumerate(replay.OP_NAMES) if (jobs["op"] == i).any()}
+    cells = replay.algorithmic_cells(m_arena, synth.genome, m_jobs)
+    n_jobs = len(m_jobs)
+    jobs_per_op = {nm: int((m_jobs["op"] == i).sum()) for i, nm in enumerate(OP_NAMES) if (m_jobs["op"] == i).any()}
+    _log(f"{n_jobs} jobs in {len(batches)} device batches ({n_records} lane batches), arena {len(m_arena) >> 20} MB")
 
-    _log(f"merged {len(jobs)} jobs from {n_batches} batches, arena {len(arena) >> 20} MB")
     cu = pintron_b200.Cuda(local)
     L = cu.L
     cu.genome_upload(synth.genome, 15, 0.2)
     int_peak = L.pc_measure_int_peak(cu.ctx)
-
-    # pinned host buffers (e2e leg) and device-resident copies (value leg)
-    h_arena = torch.from_numpy(arena).pin_memory()
-    h_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).pin_memory()
-    h_res = torch.zeros(n * PC_RES_INTS, dtype=torch.int32).pin_memory()
-    h_var = torch.zeros(max(var_bytes, 1), dtype=torch.uint8).pin_memory()
-    d_arena = torch.zeros(len(arena) + 16, dtype=torch.uint8, device="cuda")      # pc_submit_device: readable 16 bytes past the arena
-    d_arena[:len(arena)].copy_(h_arena)
-    d_jobs = h_jobs.cuda()
-    d_res = torch.zeros(n * PC_RES_INTS, dtype=torch.int32, device="cuda")
-    d_var = torch.zeros(max(var_bytes, 1) + 16, dtype=torch.uint8, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
     stream = torch.cuda.ExternalStream(L.pc_stream_cuda_stream(cu.st))
-    jobs_host_ptr = jobs.ctypes.data
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
-    def step_device():
-        rc = L.pc_submit_device(cu.st, d_arena.data_ptr(), len(arena), d_jobs.data_ptr(), jobs_host_ptr, n,
-                                d_res.data_ptr(), d_var.data_ptr(), var_bytes)
+    # every device batch resident in HBM: one arena / jobs / res / var tensor, a slice per batch
+    tot_a = sum(len(b[0]) + 32 for b in batches)
+    tot_j = sum(len(b[1]) for b in batches)
+    tot_v = sum(b[2] + 32 for b in batches)
+    d_arena = torch.zeros(tot_a + 64, dtype=torch.uint8, device="cuda")
+    d_jobs = torch.zeros(max(tot_j, 1) * 44, dtype=torch.uint8, device="cuda")
+    d_res = torch.zeros(max(tot_j, 1) * PC_RES_INTS, dtype=torch.int32, device="cuda")
+    d_var = torch.zeros(tot_v + 64, dtype=torch.uint8, device="cuda")
+    plan, oa, oj, ov = [], 0, 0, 0
+    for arena, jobs, var_bytes, _ in batches:
+        d_arena[oa:oa + len(arena)].copy_(torch.from_numpy(arena))
+        d_jobs[oj * 44:(oj + len(jobs)) * 44].copy_(torch.from_numpy(jobs.view(np.uint8)))
+        plan.append((d_arena.data_ptr() + oa, len(arena), d_jobs.data_ptr() + oj * 44, len(jobs), d_res.data_ptr() + oj * PC_RES_INTS * 4,
+                     d_var.data_ptr() + ov, var_bytes))
+        oa += (len(arena) + 32 + 15) & ~15; oj += len(jobs); ov += (var_bytes + 32 + 15) & ~15
+    torch.cuda.synchronize()
+
+    def step_batches():
+        for a, ab, j, n, r, v, vb in plan:
+            rc = L.pc_submit_device(cu.st, a, ab, j, None, n, r, v, vb)
+            assert rc == 0, L.pc_last_error()
+            assert L.pc_stream_sync(cu.st) == 0, L.pc_last_error()
+
+    # the same jobs as ONE batch (kernel-level leg)
+    md_arena = torch.zeros(len(m_arena) + 16, dtype=torch.uint8, device="cuda")
+    md_arena[:len(m_arena)].copy_(torch.from_numpy(m_arena))
+    md_jobs = torch.from_numpy(m_jobs.view(np.uint8).copy()).cuda()
+    md_res = torch.zeros(n_jobs * PC_RES_INTS, dtype=torch.int32, device="cuda")
+    md_var = torch.zeros(max(m_var, 1) + 16, dtype=torch.uint8, device="cuda")
+
+    def step_merged():
+        rc = L.pc_submit_device(cu.st, md_arena.data_ptr(), len(m_arena), md_jobs.data_ptr(), None, n_jobs, md_res.data_ptr(), md_var.data_ptr(), m_var)
         assert rc == 0, L.pc_last_error()
+        assert L.pc_stream_sync(cu.st) == 0, L.pc_last_error()
 
-    def step_host():
-        rc = L.pc_submit(cu.st, h_arena.data_ptr(), len(arena), h_jobs.data_ptr(), n, h_res.data_ptr(),
-                         h_var.data_ptr(), var_bytes)
-        assert rc == 0, L.pc_last_error()
-
-    def timed(step_fn, steps, with_timers=False):
-        """K steps, each bracketed by CUDA events on the launching stream, L2 flushed between steps.  The closing event
-        is recorded after pc_stream_sync, so re-runs of jobs whose scratch slot was too small are inside the interval."""
+    def timed(step_fn, steps):
+        """K steps, each bracketed by CUDA events on the launching stream (pc_stream_sync waits for the side streams, so the
+        closing event is after all of them), L2 flushed between steps."""
         ms = []
         for _ in range(steps):
             with torch.cuda.stream(stream):
@@ -287,184 +377,219 @@ def main():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
                 step_fn()
-                assert L.pc_stream_sync(cu.st) == 0, L.pc_last_error()
                 e1.record(stream)
             e1.synchronize()
             ms.append(e0.elapsed_time(e1))
         return ms
 
     _log("device warm-up")
-    timed(step_device, args.warmup)
-    _log("device warm-up done")
-    st0 = d_res.view(n, PC_RES_INTS)[:, 0]
+    timed(step_batches, args.warmup)
+    st0 = d_res.view(-1, PC_RES_INTS)[:tot_j, 0]
     PC_E_OUTCAP = -2      # a SEED job whose triples did not fit: est-fact re-issues it with the reported capacity (both are in the stream)
     assert int(((st0 != 0) & (st0 != PC_E_OUTCAP)).sum().item()) == 0, "a job failed on the device"
-    timed(step_host, 1)
-
-    # ---- whole-program leg: the shipped est-fact on E ESTs of this rank ------------------------------------------
-    work = tempfile.mkdtemp(prefix=f"pintron_e2e_r{rank}_")
-    if not args.no_e2e:
-        open(os.path.join(work, "genomic.txt"), "wb").write(Synth(args.workload, reads=1).genome_fasta())
-        open(os.path.join(work, "ests.txt"), "wb").write(ests_fasta_parallel(args.workload, args.e2e_reads * world, rank * args.e2e_reads,
-                                                                             args.e2e_reads, procs=max(1, cores // world - 1)))
-    e2e_info = {}
-
-    def step_program():
-        t0 = time.perf_counter()
-        p = subprocess.run([exe, "--devices", str(local), "--threads", str(threads)], cwd=work, stdout=subprocess.DEVNULL,
-                           stderr=subprocess.PIPE)
-        sec = time.perf_counter() - t0
-        assert p.returncode == 0, p.stderr.decode("latin1")[-2000:]
-        for line in p.stderr.decode("latin1").splitlines():
-            if "bytes host->device" in line:
-                w = line.replace(",", "").split()
-                e2e_info["h2d"], e2e_info["d2h"] = int(w[w.index("host->device:") + 1]), int(w[w.index("device->host:") + 1])
-            if "scheduler:" in line and "workers" in line:
-                w = line.replace(",", "").split()
-                e2e_info["context_index_s"] = float(w[w.index("index") + 1])
-                e2e_info["workers_s"] = float(w[w.index("workers") + 1])
-            if "@Timer Total" in line:
-                e2e_info["program_total_s"] = int(line.split()[-2]) / 1e6
-            if "kernel launches:" in line:
-                w = line.replace(",", "").split()
-                e2e_info["launches"] = int(w[w.index("launches:") + 1])
-                e2e_info["jobs"] = int(w[w.index("jobs:") + 1])
-        return sec
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    timed(step_merged, 2)
+    st1 = md_res.view(-1, PC_RES_INTS)[:, 0]
+    assert int(((st1 != 0) & (st1 != PC_E_OUTCAP)).sum().item()) == 0, "a job failed on the device (merged batch)"
 
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
+    launches0 = cu.launch_count()
+    ms_dev = timed(step_batches, args.steps)
+    launches_dev = cu.launch_count() - launches0
+    barrier()
+    _log("device leg timed; kernel-level leg")
+    import ctypes as C
     L.pc_stream_enable_timers(cu.st, 1)
     L.pc_stream_reset_timers(cu.st)
-    launches0 = cu.launch_count()
-    ms_dev = timed(step_device, args.steps)
-    _log("device leg timed")
-    launches = cu.launch_count() - launches0
-    import ctypes as C
-    op_names = ["ALIGN", "KBAND", "EDIT", "BORDERS", "GAP", "AFFIX", "SUFCUT", "PRECUT", "LCS", "SEED"]
+    ksteps = min(args.steps, 5)
+    ms_merged = timed(step_merged, ksteps)
     op_ms, op_launch = {}, {}
-    for i, nm in enumerate(op_names):
+    for i, nm in enumerate(OP_NAMES):
         m, k = C.c_double(), C.c_uint64()
         L.pc_stream_op_time(cu.st, i, C.byref(m), C.byref(k))
         if k.value:
-            op_ms[nm], op_launch[nm] = m.value / args.steps, k.value // args.steps
+            op_ms[nm], op_launch[nm] = m.value / ksteps, k.value // ksteps
     L.pc_stream_enable_timers(cu.st, 0)
     barrier()
-    ms_host = timed(step_host, args.steps)                  # the same device batch, submitted from pinned host buffers
-    barrier()
+
+    # ---- whole-program legs ------------------------------------------------------------------------------------------
+    work = tempfile.mkdtemp(prefix=f"pintron_e2e_r{rank}_")
+    e2e_info, cold = {}, None
     n_out = None
     if args.no_e2e:
         ms_e2e = [float("nan")]
     else:
-        # one run takes seconds to tens of seconds: W and K are capped for this leg (stated in the JSON line)
+        write_inputs(work, args.workload, args.e2e_reads * world, rank * args.e2e_reads, args.e2e_reads)
         e2e_warmup, e2e_steps = min(args.warmup, args.e2e_max_warmup), min(args.steps, args.e2e_max_steps)
-        _log("whole-program leg")
+        _log("whole-program leg (client of the resident est-factd)")
         for _ in range(e2e_warmup):
-            step_program()
-        _log("whole-program warm-up done")
+            est_fact(work, "daemon")
         barrier()
-        ms_e2e = [step_program() * 1e3 for _ in range(e2e_steps)]
+        ms_e2e = []
+        for _ in range(e2e_steps):
+            sec, e2e_info = est_fact(work, "daemon")
+            ms_e2e.append(sec * 1e3)
         barrier()
         n_out = sum(1 for _ in open(os.path.join(work, "processed-ests.txt"), "rb")) // 2
-    shutil.rmtree(work, ignore_errors=True)
+        if rank == 0:
+            _log("whole-program, cold: engine inside the process")
+            sec, ci = est_fact(work, "inproc")
+            cold = {"value": args.e2e_reads / sec, "unit": "ESTs/s", "ms_per_step": sec * 1e3, "gpus": 1,
+                    "what": "one run with --engine inproc: CUDA context creation, kernel loading and lane pinning inside the timed region",
+                    "session_open_s": ci.get("session_open_s"), "workers_s": ci.get("workers_s")}
+        barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    t_dev = torch.tensor([sum(ms_dev) / len(ms_dev), sum(ms_e2e) / len(ms_e2e), sum(ms_host) / len(ms_host)], device="cuda",
-                         dtype=torch.float64)
+    t_dev = torch.tensor([sum(ms_dev) / len(ms_dev), sum(ms_e2e) / len(ms_e2e)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    ms_step, ms_step_e2e, ms_step_host = t_dev.tolist()
-    total_reads = n_reads * world
-    value = total_reads / (ms_step * 1e-3)
+    ms_step, ms_step_e2e = t_dev.tolist()
+    value = args.reads * world / (ms_step * 1e-3)
     e2e = args.e2e_reads * world / (ms_step_e2e * 1e-3)
 
-    dp_ops = [k for k in OPS_PER_CELL if k in cells]
-    dp_cells = sum(cells[k] for k in dp_ops)
-    dom = max(op_ms, key=op_ms.get)
-    peaks = {}
+    # ---- roofline of the dominant kernel (kernel-level leg) ----------------------------------------------------------
+    peaks, ncu = {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        ent = tr.get(args.workload, {}).get(KERNEL_OF.get(dom, dom))
-        if ent and ent.get("reads") == args.reads:
-            traffic = ent["dram_bytes_per_launch"]
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_kernels.json"))).get(args.workload, {})
     except Exception:
         pass
+    dom = max(op_ms, key=op_ms.get)
+
+    def kernel_entry(k):
+        e = {"ms": op_ms[k], "launches": op_launch.get(k)}
+        if k in cells and k in OPS_PER_CELL:
+            e["cells"] = cells[k]
+            e["gcups"] = cells[k] / (op_ms[k] * 1e-3) / 1e9
+            e["int_alu_frac"] = cells[k] * OPS_PER_CELL[k] / (op_ms[k] * 1e-3) / int_peak if int_peak else None
+            e["ops_per_cell"] = OPS_PER_CELL[k]
+        n = ncu.get(k)
+        if n:
+            e["ncu"] = n
+        return e
+    per_kernel = {k: kernel_entry(k) for k in op_ms}
     if dom in OPS_PER_CELL:
         ach = cells[dom] * OPS_PER_CELL[dom] / (op_ms[dom] * 1e-3) / 1e12
-        roof = {"bound": "int_alu", "kernel": KERNEL_OF.get(dom, dom), "achieved": ach, "peak": int_peak / 1e12,
-                "unit": "Tlane-op/s", "frac": ach / (int_peak / 1e12) if int_peak else None, "traffic": traffic,
-                "traffic_note": "DRAM bytes per launch from the committed ncu capture (profiles/r1_traffic.json), null when that capture "
-                                "was taken on another batch size",
-                "peak_source": "pc_measure_int_peak (VIADDMNMX chains, measured live on this GPU)",
-                "gcups": cells[dom] / (op_ms[dom] * 1e-3) / 1e9, "ops_per_cell": OPS_PER_CELL[dom]}
+        n = ncu.get(dom, {})
+        roof = {"bound": "int_alu", "kernel": KERNEL_OF.get(dom, dom), "achieved": ach, "peak": int_peak / 1e12, "unit": "Tlane-op/s",
+                "frac": ach / (int_peak / 1e12) if int_peak else None,
+                "traffic": n.get("dram_bytes_per_launch") if n.get("reads") == args.reads else None,
+                "ncu_alu_pipe_pct": n.get("alu_pipe_pct"), "ncu_issue_active_pct": n.get("issue_active_pct"),
+                "ncu_source": "profiles/r2_ncu_kernels.json (ncu --set full of this command; null when captured at another batch size)",
+                "peak_source": "pc_measure_int_peak: VIADDMNMX chains measured live on this GPU = 148 SMs x 64 lanes/clk x SM clock "
+                               "(MEASURED_PEAKS.json has no integer figure)",
+                "gcups": cells[dom] / (op_ms[dom] * 1e-3) / 1e9, "ops_per_cell": OPS_PER_CELL[dom],
+                "cells_note": "GAP cells are plane-cells: 3 per DP position, 9 reference ops per position" if dom == "GAP" else None}
     else:
-        # SEED: EST bytes + 12 B per emitted pairing; LCS: one byte of genome prefix per job and scanned position
-        if dom == "SEED":
-            emitted = int(d_res.view(n, PC_RES_INTS)[torch.from_numpy(np.nonzero(seed_sel)[0]).cuda(), 1].clamp(min=0).sum().item())
-            alg_bytes = seed_bytes + 12 * emitted
-        else:
-            alg_bytes = int(jobs["b_len"][jobs["op"] == 8].sum())
+        seed_sel = m_jobs["op"] == 9
+        emitted = int(md_res.view(n_jobs, PC_RES_INTS)[torch.from_numpy(np.nonzero(seed_sel)[0]).cuda(), 1].clamp(min=0).sum().item())
+        alg_bytes = int(m_jobs["a_len"][seed_sel].sum()) + 12 * emitted
         ach = alg_bytes / (op_ms[dom] * 1e-3) / 1e9
         pk = peaks.get("hbm_gbs", 6650.0)
-        roof = {"bound": "hbm", "kernel": KERNEL_OF.get(dom, dom), "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk,
-                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                "note": "genome and index are L2-resident at these sizes: the kernel is latency / ALU bound, the HBM fraction is reported as the contract asks"}
-    # every DP kernel against the INT-ALU peak (the dominant one is `roofline`)
-    per_kernel = {k: {"ms": op_ms[k], "gcups": cells[k] / (op_ms[k] * 1e-3) / 1e9,
-                      "int_alu_frac": cells[k] * OPS_PER_CELL[k] / (op_ms[k] * 1e-3) / int_peak if int_peak else None}
-                  for k in dp_ops if k in op_ms and op_ms[k] > 0}
+        roof = {"bound": "hbm", "kernel": KERNEL_OF.get(dom, dom), "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "note": "genome and index are L2-resident at these sizes: the kernel is latency bound, the HBM fraction is reported as the contract asks"}
 
     if rank == 0:
-        _log("cpu baseline sample")
-        cpu = None if args.no_cpu_baseline else cpu_baseline_sample(args.workload)
+        # ---- parity + CPU baseline: the reference on a bounded sample with every host core, its bytes against ours -------
+        cpu = parity = None
+        if not args.no_cpu_baseline:
+            _log("reference on the host cores (cpu_baseline) and byte parity on the same ESTs")
+            sh = RefShards(args.workload, args.ref_reads_per_core)
+            if sh.available():
+                sec = sh.step()
+                if world == 1:
+                    cpu = {"value": sh.n / sec, "unit": "ESTs/s", "cores": sh.cores, "kind": "reference",
+                           "sample": f"the first {sh.n} {args.workload} ESTs, {sh.cores} unmodified est-fact processes (one per core, {sh.per_core} ESTs each, "
+                                     f"each building its suffix tree), wall {sec:.2f} s"}
+                pd = tempfile.mkdtemp(prefix="pintron_parity_")
+                open(os.path.join(pd, "genomic.txt"), "wb").write(sh.genome_fasta)
+                open(os.path.join(pd, "ests.txt"), "wb").write(sh.all_ests)
+                est_fact(pd, "daemon")
+                ours, ref = md5_files(pd), sh.md5s()
+                bad = [f for f in FILES if ours[f] != ref[f]]
+                parity = {"status": "identical" if not bad else "MISMATCH", "ests": sh.n, "files": FILES, "differing": bad,
+                          "how": "md5 of our five output files (client of est-factd) == md5 of the reference's shard outputs concatenated"}
+                shutil.rmtree(pd, ignore_errors=True)
+            sh.close()
+        extra = {}
+        if not (args.no_e2e or args.no_extra) and args.workload == "C3" and world == 1:
+            extra = extra_workloads(est_fact, write_inputs, exe)
         line = {
             "metric": METRIC, "value": value, "unit": "ESTs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload] + "; `value`: every device job the shipped est-fact issues for these ESTs "
-                                   "(recorded from a real run, merged into one HBM-resident batch); `e2e`: the whole est-fact program",
-                       "reads_per_gpu_per_step": n_reads, "jobs_per_gpu_per_step": n, "jobs_per_op": jobs_per_op,
-                       "batches_merged": n_batches, "l2": "flushed between steps (256 MB write)",
-                       "sharding": f"ESTs dealt to {world} rank(s), genome index replicated, no collective"},
-            "dp_gcups": dp_cells * world / (sum(op_ms.get(k, 0) for k in dp_ops) * 1e-3) / 1e9,
-            "dp_cells_per_step": dp_cells * world, "dp_kernels": per_kernel,
-            "kernel_ms_per_step": op_ms, "kernel_launches_per_step": op_launch,
-            "roofline": roof, "cpu_baseline": cpu,
+            "data": "synthetic", "config": config_of(args.workload),
+            "value_what": f"device-resident leg: the {len(batches)} device batches est-fact's engine really formed for {args.reads} ESTs per GPU "
+                          f"({n_jobs} jobs, {n_records} lane batches merged by the engine), inputs in HBM, pc_submit_device + pc_stream_sync per batch",
+            "device_leg": {"ests_per_gpu_per_step": args.reads, "jobs_per_step": n_jobs, "device_batches_per_step": len(batches),
+                           "lane_batches_per_step": n_records, "launches_per_step": launches_dev // args.steps, "jobs_per_op": jobs_per_op},
+            "kernels": {"what": "the same jobs as ONE merged batch, per-op CUDA-event timers (single stream)", "ms_per_step": sum(ms_merged) / len(ms_merged),
+                        "ests_per_sec": args.reads / (sum(ms_merged) / len(ms_merged) * 1e-3), "per_kernel": per_kernel,
+                        "gcups_basis": "cells of the jobs OUR host issues, counted with the reference's formulas (SURVEY.md §8(d)); the host issues some "
+                                       "DP calls speculatively (all four splice-shift variants), so EDIT counts more cells than the reference would compute"},
+            "roofline": roof, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e, "unit": "ESTs/s", "ms_per_step": ms_step_e2e,
                     "h2d_bytes_per_step": e2e_info.get("h2d"), "d2h_bytes_per_step": e2e_info.get("d2h"),
-                    "what": "one run of the shipped est-fact program per step (process start, CUDA context, index build, "
-                            "host control flow, every H2D/D2H copy, six output files): wall clock of the process",
+                    "what": "one run of the shipped est-fact program per step as pintron.py calls it (process start, FASTA parsing, engine session with "
+                            "genome upload + index build, host control flow, every H2D/D2H copy through pinned lanes, six output files), client of the "
+                            "resident est-factd; wall clock of the process, max over ranks",
                     "ests_per_gpu_per_step": args.e2e_reads, "steps": min(args.steps, args.e2e_max_steps),
                     "warmup": min(args.warmup, args.e2e_max_warmup), "ests_aligned_rank0": n_out, "host_threads_per_gpu": threads,
+                    "host_cores": cores, "gpus_on_box": gpus_on_box,
                     "device_jobs_per_step": e2e_info.get("jobs"), "gpu_launches_per_step": e2e_info.get("launches"),
-                    "last_step_breakdown_s": {"cuda_context_and_genome_index": e2e_info.get("context_index_s"),
-                                              "all_ests_through_workers": e2e_info.get("workers_s"),
-                                              "program_total": e2e_info.get("program_total_s")}},
-            "host_buffers_device_path": {"value": total_reads / (ms_step_host * 1e-3), "unit": "ESTs/s", "ms_per_step": ms_step_host,
-                                         "h2d_bytes_per_step": int(len(arena) + jobs.nbytes),
-                                         "d2h_bytes_per_step": int(n * PC_RES_INTS * 4 + var_bytes),
-                                         "what": "the `value` batch submitted from pinned host buffers through pc_submit"},
-            "gpu_launches": int(launches) + (0 if args.no_e2e else min(args.steps, args.e2e_max_steps)) * int(e2e_info.get("launches") or 0), "clocks": sampler.summary(),
-            "int_alu_peak_tlaneops": int_peak / 1e12,
+                    "lane_batches_per_step": e2e_info.get("lane_batches"), "device_batches_per_step": e2e_info.get("device_batches"),
+                    "last_step_breakdown_s": {k: e2e_info.get(k) for k in ("ests_read_s", "session_open_s", "workers_s", "program_total_s",
+                                                                           "per_est_code_thread_s", "wait_on_device_thread_s")}},
+            "e2e_cold": cold,
+            "gpu_launches": int(launches_dev) + (0 if args.no_e2e else min(args.steps, args.e2e_max_steps)) * int(e2e_info.get("launches") or 0),
+            "clocks": sampler.summary(), "int_alu_peak_tlaneops": int_peak / 1e12,
         }
+        line.update(extra)
         print(json.dumps(line))
+    shutil.rmtree(work, ignore_errors=True)
     if os.environ.get("PC_PROFILE"):
         L.pc_debug_dump()
+    barrier()
+    if srv is not None:
+        subprocess.run([daemon, "--socket", sock, "--stop"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        try:
+            srv.wait(timeout=20)
+        except subprocess.TimeoutExpired:
+            srv.kill()
+        shutil.rmtree(srv_dir, ignore_errors=True)
     if world > 1:
         dist.destroy_process_group()
     cu.close()
+
+
+def extra_workloads(est_fact, write_inputs, exe):
+    """Short whole-program runs of the other BASELINE.json shapes appended to the default (C3) line, so that the driver's
+    record carries them: C4 (configs[3]) and C5 (configs[4]) subsamples, with the reference on the same reads beside them."""
+    out = {}
+    for wl, reads, ref_per_core in (("C4", 20000, 25), ("C5", 48, 1)):
+        try:
+            d = tempfile.mkdtemp(prefix=f"pintron_{wl}_")
+            write_inputs(d, wl, reads, 0, reads)
+            est_fact(d, "daemon")                              # warm-up
+            sec, info = est_fact(d, "daemon")
+            ent = {"e2e": {"value": reads / sec, "unit": "reads/s", "ms_per_step": sec * 1e3, "reads": reads, "workload": WORKLOADS[wl][0],
+                           "subsample": f"{reads} reads (BASELINE.json names {WORKLOADS[wl][1]} per GPU for the default leg of this shape)",
+                           "workers_s": info.get("workers_s"), "device_jobs": info.get("jobs"), "gpu_launches": info.get("launches")}}
+            shutil.rmtree(d, ignore_errors=True)
+            sh = RefShards(wl, ref_per_core)
+            if sh.available():
+                rs = sh.step()
+                ent["reference"] = {"value": sh.n / rs, "unit": "reads/s", "cores": sh.cores, "sample": f"{sh.n} reads, one process per core, wall {rs:.1f} s"}
+            sh.close()
+            out[wl.lower()] = ent
+        except Exception as e:      # noqa: BLE001 — an extra leg never takes the main line down
+            out[wl.lower()] = {"error": repr(e)[:300]}
+    return out
 
 
 if __name__ == "__main__":

@@ -101,7 +101,9 @@ int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes, const pc_
 
 /* Same, for inputs that are ALREADY in device memory (bench "value" leg, chained device pipelines):
  * d_arena / d_jobs / d_res / d_var_out are device pointers; nothing is copied.  d_arena must be readable (and zero)
- * for 16 bytes past arena_bytes, d_var_out writable for 16 bytes past var_out_bytes (pc_submit pads its own copies). */
+ * for 16 bytes past arena_bytes, d_var_out writable for 16 bytes past var_out_bytes (pc_submit pads its own copies).
+ * h_jobs (a host copy of the jobs) may be NULL: the batch is then validated, keyed and ordered on the device whatever
+ * its size (what the engine does with merged lanes, include/pintron_engine.h). */
 int pc_submit_device(pc_stream *st, const uint8_t *d_arena, size_t arena_bytes, const pc_job *d_jobs,
                      const pc_job *h_jobs, int njobs, int32_t *d_res, uint8_t *d_var_out, size_t var_out_bytes);
 
@@ -122,18 +124,19 @@ int pc_build_vertex_set_batch(pc_stream *, const uint8_t *arena, size_t, const p
 /* ---- instrumentation ----------------------------------------------------------------------------- */
 /* Environment (read once when the library is loaded): PC_PROFILE=1 makes pc_debug_dump() print host-side phase times,
  * device time / jobs per op, hand-over and re-run counts; PC_CAPTURE=<file> appends every batch given to pc_submit to
- * <file> (u32 njobs, u64 arena_bytes, jobs, arena) — bench.py replays such a recording as its device workload and
- * tools/check_capture.py checks every recorded job against the oracle. */
+ * <file> (u32 njobs, u64 arena_bytes, jobs, arena; pc_submit_parts writes u32 0xffffffff, u64 nparts before the parts it ran
+ * as one device batch) — bench.py replays such a recording as its device workload and tools/check_capture.py checks every
+ * recorded job against the oracle. */
 uint64_t pc_launch_count(void);                  /* kernels launched by this library in this process */
 /* Device time (ms, CUDA events on the stream) and launches of the kernels of `op` since the last reset. */
 int pc_stream_op_time(pc_stream *st, int op, double *ms, uint64_t *launches);
 void pc_stream_reset_timers(pc_stream *st);
 void pc_stream_enable_timers(pc_stream *st, int on);
-void *pc_stream_cuda_stream(pc_stream *st);
+void *pc_stream_cuda_stream(pc_stream *st);    /* the cudaStream_t, for callers that interoperate */
 /* INT32 ALU micro-benchmark: lane-operations per second of independent add/min chains (the roofline
  * denominator for the DP kernels; SURVEY.md §8(d) asks for a measured figure). */
 double pc_measure_int_peak(pc_ctx *ctx);
-void pc_debug_dump(void);                     /* prints library-side timings to stderr when PC_PROFILE is set */      /* the cudaStream_t, for callers that interoperate */
+void pc_debug_dump(void);                     /* prints library-side timings to stderr when PC_PROFILE is set */
 
 #ifdef __cplusplus
 }

@@ -99,12 +99,43 @@ struct pc_ctx {
   cudaStream_t up = nullptr;    /* uploads and index builds run here, not on the legacy stream */
 };
 
+/* PC_GUARD=1 (debugging aid; compute-sanitizer is not available on every pool): every device buffer of a stream is
+ * allocated at exactly the size asked for, between two 4 KB guard bands filled with 0xA5 — the buffers themselves start
+ * out as 0xA5 too — and pc_stream_sync checks the bands after every batch: an out-of-bounds WRITE by any kernel fails the
+ * batch loudly, and a result that depends on bytes nobody wrote changes with the fill pattern. */
+static const bool g_guard = getenv("PC_GUARD") != nullptr;
+constexpr size_t GUARD = 4096;
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
   bool in_slab = false;        /* carved from the stream's single start-up allocation: never freed on its own */
+  void *g_base = nullptr; size_t g_bytes = 0;      /* guard mode: the real allocation and the exact size in use */
   void carve(uint8_t *&cursor, size_t bytes) { p = cursor; cap = bytes; in_slab = true; cursor += (bytes + 255u) & ~(size_t)255u; }
+  int reserve_guarded(size_t bytes) {
+    const size_t b16 = (bytes + 15u) & ~(size_t)15u;
+    if (g_base && b16 == g_bytes) return 0;
+    if (g_base) cudaFree(g_base);
+    g_base = nullptr; p = nullptr; cap = 0;
+    if (cudaMalloc(&g_base, b16 + 2 * GUARD) != cudaSuccess) { g_base = nullptr; return fail(PC_E_NOMEM, "%s", "cudaMalloc (guard mode)"); }
+    cudaMemset(g_base, 0xA5, b16 + 2 * GUARD);
+    p = (uint8_t *)g_base + GUARD; cap = b16; g_bytes = b16;
+    return 0;
+  }
+  int check_guards(const char *name) const {
+    if (!g_base) return 0;
+    static thread_local std::vector<uint8_t> h(2 * GUARD);
+    if (cudaMemcpy(h.data(), g_base, GUARD, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(h.data() + GUARD, (uint8_t *)g_base + GUARD + g_bytes, GUARD, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(PC_E_CUDA, "%s", "guard read-back");
+    for (size_t i = 0; i < 2 * GUARD; ++i)
+      if (h[i] != 0xA5) {
+        static thread_local char msg[160];
+        snprintf(msg, sizeof msg, "PC_GUARD: a kernel wrote %s the '%s' buffer (%zu bytes): guard byte %zu", i < GUARD ? "BEFORE" : "PAST THE END of", name, g_bytes, i % GUARD);
+        return fail(PC_E_CUDA, "%s", msg);
+      }
+    return 0;
+  }
   int reserve(size_t bytes) {
+    if (g_guard) return reserve_guarded(bytes);
     if (bytes <= cap) return 0;
     if (p && !in_slab) cudaFree(p);
     p = nullptr; in_slab = false;
@@ -115,7 +146,7 @@ struct DevBuf {
     cap = want;
     return 0;
   }
-  void release() { if (p && !in_slab) cudaFree(p); p = nullptr; cap = 0; in_slab = false; }
+  void release() { if (g_base) cudaFree(g_base); else if (p && !in_slab) cudaFree(p); p = nullptr; g_base = nullptr; cap = 0; g_bytes = 0; in_slab = false; }
 };
 
 // Pinned host staging that only grows (job order and LCS block prefix travel to the device from here: a pageable
@@ -247,12 +278,16 @@ extern "C" pc_stream *pc_stream_create(pc_ctx *c) {
   /* scratch pool and staging as ONE allocation made up front: cudaMalloc / cudaFree while other streams run
    * serialise the whole device.  Buffers that outgrow their share later get their own allocation. */
   const size_t sizes[7] = {256ull << 20, 8u << 20, 8u << 20, sizeof(pc_job) << 16, (sizeof(int32_t) * PC_RES_INTS) << 16, 4u << 16, 8u << 14};
-  size_t total = 0;
-  for (size_t z : sizes) total += (z + 255u) & ~(size_t)255u;
-  if (cudaMalloc(&st->slab, total) != cudaSuccess) { st->slab = nullptr; fail(PC_E_NOMEM, "%s", "pc_stream_create: device allocation failed"); pc_stream_destroy(st); return nullptr; }
-  uint8_t *cur = (uint8_t *)st->slab;
   DevBuf *bufs[7] = {&st->pool, &st->arena, &st->var, &st->jobs, &st->res, &st->idx, &st->lcs_best};
-  for (int i = 0; i < 7; ++i) bufs[i]->carve(cur, sizes[i]);
+  if (g_guard) {               /* no slab: every buffer on its own, exactly sized, between guard bands (only the pool is sized up front) */
+    if (st->pool.reserve(sizes[0])) { pc_stream_destroy(st); return nullptr; }
+  } else {
+    size_t total = 0;
+    for (size_t z : sizes) total += (z + 255u) & ~(size_t)255u;
+    if (cudaMalloc(&st->slab, total) != cudaSuccess) { st->slab = nullptr; fail(PC_E_NOMEM, "%s", "pc_stream_create: device allocation failed"); pc_stream_destroy(st); return nullptr; }
+    uint8_t *cur = (uint8_t *)st->slab;
+    for (int i = 0; i < 7; ++i) bufs[i]->carve(cur, sizes[i]);
+  }
   if (st->pin_idx.reserve(1u << 16) || st->pin_lcs.reserve(1u << 14)) { pc_stream_destroy(st); return nullptr; }
   bool ok = cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; k < pc_stream::NSIDE && ok; ++k)
@@ -556,13 +591,15 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
 
 extern "C" int pc_submit_device(pc_stream *st, const uint8_t *d_arena, size_t arena_bytes, const pc_job *d_jobs,
                                 const pc_job *h_jobs, int njobs, int32_t *d_res, uint8_t *d_var_out, size_t var_out_bytes) {
-  if (!st || njobs < 0 || (njobs && (!d_jobs || !h_jobs || !d_res))) return fail(PC_E_ARG, "%s", "pc_submit_device: bad argument");
+  if (!st || njobs < 0 || (njobs && (!d_jobs || !d_res))) return fail(PC_E_ARG, "%s", "pc_submit_device: bad argument");
   if (st->pend.active) return fail(PC_E_ARG, "%s", "pc_submit_device: previous batch not synced");
   if (njobs == 0) return 0;
   CU(cudaSetDevice(st->ctx->device));
-  int rc = (size_t)njobs >= PC_DEVICE_ORDER_MIN ? 0 : check_jobs(st, h_jobs, njobs, arena_bytes, var_out_bytes);
+  /* no host copy of the jobs: validated, keyed and ordered on the device whatever the size (the engine's path) */
+  int rc = ((size_t)njobs >= PC_DEVICE_ORDER_MIN || !h_jobs) ? 0 : check_jobs(st, h_jobs, njobs, arena_bytes, var_out_bytes);
   if (rc) return rc;
-  rc = launch_selected(st, st->ctx, h_jobs, nullptr, (size_t)njobs, d_arena, d_jobs, d_res, d_var_out, arena_bytes, var_out_bytes);
+  st->pend.merged.clear();
+  rc = launch_selected(st, st->ctx, h_jobs, nullptr, (size_t)njobs, d_arena, d_jobs, d_res, d_var_out, arena_bytes, var_out_bytes, h_jobs == nullptr);
   if (rc) return rc;
   Pending &P = st->pend;
   P.active = true; P.device_mode = true; P.jobs = h_jobs; P.njobs = njobs; P.res = nullptr; P.var_out = nullptr;
@@ -605,6 +642,8 @@ extern "C" int pc_submit_parts(pc_stream *st, pc_ctx *genome_ctx, const pc_part 
   if (nj == 0) return 0;
   if (g_capture) {                                            /* every part as the batch its lane was */
     std::lock_guard<std::mutex> lk(g_capture_mu);
+    const uint32_t mark = 0xffffffffu; const uint64_t npart = P.parts.size();      /* "the next npart records ran as one device batch" */
+    fwrite(&mark, 4, 1, g_capture); fwrite(&npart, 8, 1, g_capture);
     for (const Pending::Part &q : P.parts) {
       const uint32_t n32 = (uint32_t)q.p.njobs; const uint64_t ab = q.p.arena_bytes;
       fwrite(&n32, 4, 1, g_capture); fwrite(&ab, 8, 1, g_capture);
@@ -653,6 +692,11 @@ extern "C" int pc_stream_sync(pc_stream *st) {
   if (!P.active) return 0;
   // every job that ran out of scratch also raised the pool_need counter (pc_pool_alloc, k_gap): zero = nothing to re-run,
   // and the statuses need not be read at all
+  if (g_guard) {
+    const char *nm[8] = {"arena", "jobs", "idx", "res", "var", "pool", "lcs_best", "parts"};
+    DevBuf *bb[8] = {&st->arena, &st->jobs, &st->idx, &st->res, &st->var, &st->pool, &st->lcs_best, &st->d_parts};
+    for (int i = 0; i < 8; ++i) if (bb[i]->check_guards(nm[i])) { P.active = false; return PC_E_CUDA; }
+  }
   if (*st->h_pool_need == 0) { P.active = false; return 0; }
   // Jobs whose scratch did not fit their warp's pool slot are re-run with fewer warps (= larger slots: the launchers
   // give exactly max_warps warps a slot); the pool itself grows only when a single job needs more than all of it.
@@ -660,6 +704,10 @@ extern "C" int pc_stream_sync(pc_stream *st) {
   if (!P.parts.empty()) {           // merged batch: the host copy of the jobs is only put together now that it is needed
     P.merged.resize((size_t)P.njobs);     // (lengths, op and parameters only: the offsets stay un-rebased and are not read)
     for (const Pending::Part &q : P.parts) memcpy(P.merged.data() + q.j_base, q.p.jobs, sizeof(pc_job) * (size_t)q.p.njobs);
+    h_jobs = P.merged.data();
+  } else if (!h_jobs) {             // device-resident batch submitted without a host copy: fetch the jobs for the retry's ordering pass
+    P.merged.resize((size_t)P.njobs);
+    CU(cudaMemcpy(P.merged.data(), P.d_jobs, sizeof(pc_job) * (size_t)P.njobs, cudaMemcpyDeviceToHost));
     h_jobs = P.merged.data();
   }
   size_t left = 0;

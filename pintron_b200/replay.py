@@ -32,30 +32,46 @@ def capture(exe, workdir, threads=None, device=None):
     return cap
 
 
-def merge(path, max_arena_bytes=3 << 30):
-    """-> (arena uint8[], jobs JOB_DTYPE[], var_bytes, n_batches).  Stops before the merged arena would pass
-    `max_arena_bytes` (job offsets are 32-bit)."""
+def records(path):
+    """Yields (group, jobs, arena) for every record of a capture file: group = running number of the DEVICE batch the
+    record was part of (pc_submit_parts writes a marker u32 0xffffffff, u64 nparts before the parts it merged; a plain
+    pc_submit record is its own batch)."""
     raw = np.fromfile(path, dtype=np.uint8)
-    at, base, nb = 0, 0, 0
-    arenas, jobs = [], []
+    at, group, left = 0, -1, 0
     while at + 12 <= raw.size:
         n = int(raw[at:at + 4].view("<u4")[0])
         ab = int(raw[at + 4:at + 12].view("<u8")[0])
         at += 12
-        if base + ab > max_arena_bytes:
-            break
+        if n == 0xffffffff:
+            group += 1
+            left = ab
+            continue
+        if left == 0:
+            group += 1
+        else:
+            left -= 1
         j = raw[at:at + n * JOB_DTYPE.itemsize].view(JOB_DTYPE).copy()
         at += n * JOB_DTYPE.itemsize
+        yield group, j, raw[at:at + ab]
+        at += ab
+
+
+def _concat(parts, pad):
+    """[(jobs, arena)] -> one arena + one job array: offsets rebased, output regions laid out again (4-aligned).  pad =
+    spare bytes after every part's arena (the engine leaves 16: BORDERS reads t[len_t], word loads run past the end)."""
+    base, arenas, jobs = 0, [], []
+    for j, ar in parts:
+        j = j.copy()
         j["a_off"] += np.uint32(base)
         in_arena = ((j["flags"] & PC_B_IN_GENOME) == 0) & (j["op"] != PC_OP.SEED)
         j["b_off"][in_arena] += np.uint32(base)
-        arenas.append(raw[at:at + ab])
-        at += ab
-        base += ab
+        arenas.append(ar)
+        step = len(ar) + pad
+        if pad:
+            step = (step + 15) & ~15
+            arenas.append(np.zeros(step - len(ar), np.uint8))
+        base += step
         jobs.append(j)
-        nb += 1
-    if not jobs:
-        return np.zeros(1, np.uint8), np.zeros(0, JOB_DTYPE), 0, 0
     jobs = np.concatenate(jobs)
     arena = np.concatenate(arenas) if base else np.zeros(1, np.uint8)
     op = jobs["op"]
@@ -63,10 +79,41 @@ def merge(path, max_arena_bytes=3 << 30):
                     np.where(op == PC_OP.SEED, 12 * jobs["out_cap"].astype(np.int64), 0))
     size = (size + 3) & ~3
     off = np.concatenate(([0], np.cumsum(size)))
-    if off[-1] >= (1 << 32) - 64:
-        raise RuntimeError("merged output region passes 4 GiB: capture fewer ESTs")
+    if off[-1] >= (1 << 32) - 64 or base >= (1 << 32) - 64:
+        raise RuntimeError("merged batch passes 4 GiB: capture fewer ESTs")
     jobs["out_off"] = off[:-1].astype(np.uint32)
-    return arena, jobs, int(off[-1]), nb
+    return arena, jobs, int(off[-1])
+
+
+def merge(path, max_arena_bytes=3 << 30):
+    """-> (arena uint8[], jobs JOB_DTYPE[], var_bytes, n_records): EVERY recorded job as ONE batch (kernel-level timing at
+    full occupancy).  Stops before the merged arena would pass `max_arena_bytes` (job offsets are 32-bit)."""
+    parts, tot = [], 0
+    for _, j, ar in records(path):
+        if tot + len(ar) > max_arena_bytes:
+            break
+        parts.append((j, ar))
+        tot += len(ar)
+    if not parts:
+        return np.zeros(1, np.uint8), np.zeros(0, JOB_DTYPE), 0, 0
+    arena, jobs, var_bytes = _concat(parts, 0)
+    return arena, jobs, var_bytes, len(parts)
+
+
+def device_batches(path):
+    """-> list of (arena, jobs, var_bytes, n_lanes): the capture as the DEVICE batches the engine really ran (the lanes it
+    merged stay merged, nothing else is), each laid out the way pc_submit_parts lays it out."""
+    out, cur, cur_g = [], [], None
+    for g, j, ar in records(path):
+        if cur and g != cur_g:
+            out.append(_concat(cur, 16) + (len(cur),))
+            cur = []
+        cur_g = g
+        if len(j):
+            cur.append((j, ar))
+    if cur:
+        out.append(_concat(cur, 16) + (len(cur),))
+    return out
 
 
 def _equal_pairs(arena, genome, jobs, sel):

@@ -211,3 +211,19 @@ def test_large_intron_window_option_vs_reference(tmp_path):
     if not os.path.exists(U.REF_BIN):
         pytest.skip("oracle/_ref/est-fact not built")
     U.check_options_vs_reference(U.GPU_BIN, "test-mattia1", tmp_path, ["--suff-pref-length-intron", "2000"], "--quiet")
+
+
+def test_guard_bands_stay_intact(tmp_path):
+    """PC_GUARD=1: every device buffer exactly sized between 0xA5 guard bands, buffers pre-filled with 0xA5, bands checked
+    after every batch (compute-sanitizer is closed on this GPU pool; this is the bounds check of our own).  The C-ABI
+    parity tests and the program on three regression cases must pass unchanged: no kernel writes out of bounds, no
+    result depends on bytes nobody wrote."""
+    import sys
+    env = dict(os.environ, PC_GUARD="1")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(U.HERE, "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "mixed_batch or golden or packed or bit_parallel or lcs or edge_cases or long_alignment"],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert p.returncode == 0, p.stdout[-2500:]
+    for case in ("test-AMBN", "test-CPB2", "test_gtf7"):
+        d = tmp_path / case; d.mkdir()
+        U.check_case(U.GPU_BIN, case, d, "--quiet", "--threads", "6", "--engine", "inproc", env=env)

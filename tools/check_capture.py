@@ -28,6 +28,8 @@ at, nb, bad, total = 0, 0, 0, 0
 names = ["ALIGN", "KBAND", "EDIT", "BORDERS", "GAP", "AFFIX", "SUFCUT", "PRECUT", "LCS", "SEED"]
 while at + 12 <= raw.size:
     n = int(raw[at:at + 4].view("<u4")[0]); ab = int(raw[at + 4:at + 12].view("<u8")[0]); at += 12
+    if n == 0xffffffff:      # marker written by pc_submit_parts: the next `ab` records ran as one device batch
+        continue
     jobs = raw[at:at + n * 44].view(JOB_DTYPE).copy(); at += n * 44
     arena = raw[at:at + ab].copy(); at += ab
     arena = np.concatenate([arena, np.zeros(16, np.uint8)])
