@@ -17,6 +17,8 @@
 // Direction bytes go to the warp's scratch slot as [lane][column][8 rows] = one 8-byte store per job per step and
 // stay L2/L1-resident for the traceback, which lanes 0 and 1 of the group walk for the two jobs.
 #include "pc_device.cuh"
+#include <cstdlib>
+#define PC_GAP_MINB_DEFAULT 4
 
 namespace {
 
@@ -49,41 +51,65 @@ __device__ __forceinline__ GapJob gap_job(const PcDevBatch &B, int slot) {
 
 // Walk the direction bytes back from (n, m).  Same bookkeeping as the reference's recursive
 // TracebackGapAlignment (refine-intron.c:828-890): ops are produced last column first, the caller reverses them.
-__device__ int gap_traceback(const GapJob &J, const uint8_t *dir, int mstride, int Le, int Ge, int Re) {
+//
+// The whole group walks together.  A single lane chasing one direction byte per step through global memory spends
+// the latency of a dependent L2 / DRAM load on every alignment column (~260 of them) while the other lanes of its warp
+// wait: that was half of the kernel's time (ncu: long-scoreboard stalls 2.6 per issue).  Here lane t fetches the
+// 8-row word of column j - t, so one round of loads covers LANES columns of the current row block; the walk inside
+// that window reads the words by shuffle.  Every lane follows the same (i, j, plane) state; lane 0 writes.
+template <int LANES>
+__device__ int gap_traceback(const GapJob &J, const uint8_t *dir, int mstride, int Le, int Ge, int Re, int k, unsigned gmask) {
   int state;
   if (Re >= Ge) state = (Re >= Le) ? 2 : 0; else state = (Ge >= Le) ? 1 : 0;
   int pos0 = 0, pos1 = 0, pos2 = 0, k_end = -1, k_start = -1;
-  int i = J.n, j = J.m, k = 0;
+  int i = J.n, j = J.m, n_ops = 0;
   uint8_t *ops = J.ops;
-  while (i > 0 || j > 0) {
-    if (i > 0 && j > 0) {
-      const int lane = (i - 1) >> 3, r = (i - 1) & 7;
-      const uint32_t c = dir[((size_t)lane * mstride + j) * 8 + r];
+  const uint2 *dir64 = reinterpret_cast<const uint2 *>(dir);
+  while (i > 0 && j > 0) {
+    const int lb = (i - 1) >> 3, j0 = j;
+    const int col = j0 - k;
+    uint2 w = make_uint2(0u, 0u);
+    if (col >= 1) w = dir64[(size_t)lb * mstride + col];
+    while (i > 0 && j > 0 && ((i - 1) >> 3) == lb && j > j0 - LANES) {
+      const int src = j0 - j;
+      const uint32_t lo = __shfl_sync(gmask, w.x, src, LANES), hi = __shfl_sync(gmask, w.y, src, LANES);
+      const int r = (i - 1) & 7;
+      const uint32_t c = ((r < 4 ? lo : hi) >> (8 * (r & 3))) & 0xffu;
       int dd;
       if (state == 2) dd = (c & 32) ? 1 : ((c & 16) ? 3 : ((c & 8) ? 2 : 0));
       else if (state == 1) dd = (c & 4) ? 3 : 2;
       else dd = (c & 2) ? 2 : ((c & 1) ? 1 : 0);
-      if (dd == 0) { ops[k++] = 0; --i; --j; }
-      else if (dd == 1) { ops[k++] = 1; --i; }
+      uint8_t op;
+      if (dd == 0) { op = 0; --i; --j; }
+      else if (dd == 1) { op = 1; --i; }
       else {
         if (dd == 3) {
-          if (state == 2) { pos2 = j - 1; pos0 = i; k_end = k; } else { pos1 = j - 1; k_start = k; }
+          if (state == 2) { pos2 = j - 1; pos0 = i; k_end = n_ops; } else { pos1 = j - 1; k_start = n_ops; }
           --state;
         }
-        ops[k++] = 2; --j;
+        op = 2; --j;
       }
-    } else if (i > 0) { ops[k++] = 1; --i; }
-    else { ops[k++] = 2; --j; }
+      if (k == 0) ops[n_ops] = op;
+      ++n_ops;
+    }
   }
-  J.res[0] = PC_OK; J.res[1] = k;
-  J.res[2] = pos0; J.res[3] = pos1; J.res[4] = pos2;
-  J.res[5] = k_start >= 0 ? k - 1 - k_start : 0;
-  J.res[6] = k_end >= 0 ? k - 1 - k_end : 0;
-  return k;
+  for (int a = k; a < i; a += LANES) ops[n_ops + a] = 1;            // what is left runs along a border
+  n_ops += i;
+  for (int a = k; a < j; a += LANES) ops[n_ops + a] = 2;
+  n_ops += j;
+  if (k == 0) {
+    J.res[0] = PC_OK; J.res[1] = n_ops;
+    J.res[2] = pos0; J.res[3] = pos1; J.res[4] = pos2;
+    J.res[5] = k_start >= 0 ? n_ops - 1 - k_start : 0;
+    J.res[6] = k_end >= 0 ? n_ops - 1 - k_end : 0;
+  }
+  return n_ops;
 }
 
-template <int LANES>
-__global__ void __launch_bounds__(128) k_gap_pairs(PcDevBatch B, int mcap) {
+// MINB = resident CTAs per SM the register allocation is held to (occupancy against register pressure: the sweep is a
+// chain of dependent DPX operations, so the issue rate follows the number of resident warps)
+template <int LANES, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_gap_pairs(PcDevBatch B, int mcap) {
   extern __shared__ uint32_t sh_codes[];                   // [4 warps][G groups][mcap + 1] packed column codes
   constexpr int G = 32 / LANES;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -199,18 +225,20 @@ __global__ void __launch_bounds__(128) k_gap_pairs(PcDevBatch B, int mcap) {
                    aR = __shfl_sync(0xffffffffu, fR, base + (live ? laneA : 0));
     const uint32_t bL = __shfl_sync(0xffffffffu, fL, base + (live ? laneB : 0)), bG = __shfl_sync(0xffffffffu, fG, base + (live ? laneB : 0)),
                    bR = __shfl_sync(0xffffffffu, fR, base + (live ? laneB : 0));
-    int klen = 0;
-    if (live && k < 2 && (k == 0 || hasB)) {
-      const GapJob &J = k == 0 ? A : Bj;
-      if (!fits) J.res[0] = PC_E_POOL;
-      else if (!J.ok) J.res[0] = PC_E_OUTCAP;
-      else if (k == 0)
-        klen = gap_traceback(J, dirA, mstride, (int)(aL & 0xffffu) - 0x4000, (int)(aG & 0xffffu) - 0x4000, (int)(aR & 0xffffu) - 0x4000);
-      else
-        klen = gap_traceback(J, dirB, mstride, (int)(bL >> 16) - 0x4000, (int)(bG >> 16) - 0x4000, (int)(bR >> 16) - 0x4000);
+    int lenA = 0, lenB = 0;
+    if (live) {                                            // live / fits / ok are the same for all lanes of a group
+      const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << base);
+      if (!fits) { if (k == 0) A.res[0] = PC_E_POOL; if (k == 1 && hasB) Bj.res[0] = PC_E_POOL; }
+      else {
+        if (!A.ok) { if (k == 0) A.res[0] = PC_E_OUTCAP; }
+        else lenA = gap_traceback<LANES>(A, dirA, mstride, (int)(aL & 0xffffu) - 0x4000, (int)(aG & 0xffffu) - 0x4000, (int)(aR & 0xffffu) - 0x4000, k, gmask);
+        if (hasB) {
+          if (!Bj.ok) { if (k == 0) Bj.res[0] = PC_E_OUTCAP; }
+          else lenB = gap_traceback<LANES>(Bj, dirB, mstride, (int)(bL >> 16) - 0x4000, (int)(bG >> 16) - 0x4000, (int)(bR >> 16) - 0x4000, k, gmask);
+        }
+      }
     }
     __syncwarp();
-    const int lenA = __shfl_sync(0xffffffffu, klen, base), lenB = __shfl_sync(0xffffffffu, klen, base + 1);
     if (live) {
       for (int a = k; a < lenA / 2; a += LANES) { uint8_t t = A.ops[a]; A.ops[a] = A.ops[lenA - 1 - a]; A.ops[lenA - 1 - a] = t; }
       for (int a = k; a < lenB / 2; a += LANES) { uint8_t t = Bj.ops[a]; Bj.ops[a] = Bj.ops[lenB - 1 - a]; Bj.ops[lenB - 1 - a] = t; }
@@ -219,29 +247,37 @@ __global__ void __launch_bounds__(128) k_gap_pairs(PcDevBatch B, int mcap) {
   }
 }
 
-template <int LANES>
+template <int LANES, int MINB>
 void launch_pairs(const PcDevBatch &B, int mcap, cudaStream_t s, int sm_count) {
   constexpr int G = 32 / LANES;
   const int npairs = (B.n + 1) / 2;
   const int ctas_needed = (npairs + 4 * G - 1) / (4 * G);
   const size_t sh = (size_t)4 * G * (mcap + 1) * sizeof(uint32_t);
-  pc_smem_optin((const void *)k_gap_pairs<LANES>, 200 * 1024);
+  pc_smem_optin((const void *)k_gap_pairs<LANES, MINB>, 200 * 1024);
   // persistent CTAs: exactly as many as are resident at once (registers limit this kernel), else the rest runs as a tail wave
-  const int per_sm = pc_cached_occupancy((const void *)k_gap_pairs<LANES>, 128, sh);
+  const int per_sm = pc_cached_occupancy((const void *)k_gap_pairs<LANES, MINB>, 128, sh);
   int grid = ctas_needed < sm_count * per_sm ? ctas_needed : sm_count * per_sm;
   if (B.max_warps > 0 && grid > (B.max_warps + 3) / 4) grid = (B.max_warps + 3) / 4;
   if (grid < 1) grid = 1;
   PcDevBatch C = B;
   C.slots = (B.max_warps > 0 && B.max_warps < grid * 4) ? B.max_warps : grid * 4;
-  k_gap_pairs<LANES><<<grid, 128, sh, s>>>(C, mcap);
+  k_gap_pairs<LANES, MINB><<<grid, 128, sh, s>>>(C, mcap);
   PC_COUNT_LAUNCH(1);
 }
 
 }  // namespace
 
 // cls 0/1/2: n <= 64 / 128 / 256 with 1 <= m <= PC_GAP_FAST_MAX_M (the generic wavefront kernel takes the rest).
+template <int MINB>
+static void launch_cls(int cls, const PcDevBatch &B, int max_m, cudaStream_t s, int sm_count) {
+  if (cls == 0) launch_pairs<8, MINB>(B, max_m, s, sm_count);
+  else if (cls == 1) launch_pairs<16, MINB>(B, max_m, s, sm_count);
+  else launch_pairs<32, MINB>(B, max_m, s, sm_count);
+}
 void pc_launch_gap_pairs(int cls, const PcDevBatch &B, int max_m, cudaStream_t s, int sm_count) {
-  if (cls == 0) launch_pairs<8>(B, max_m, s, sm_count);
-  else if (cls == 1) launch_pairs<16>(B, max_m, s, sm_count);
-  else launch_pairs<32>(B, max_m, s, sm_count);
+  static const int variant = getenv("PC_GAP_MINB") ? atoi(getenv("PC_GAP_MINB")) : PC_GAP_MINB_DEFAULT;      /* experiments */
+  if (variant == 3) launch_cls<3>(cls, B, max_m, s, sm_count);
+  else if (variant == 5) launch_cls<5>(cls, B, max_m, s, sm_count);
+  else if (variant == 6) launch_cls<6>(cls, B, max_m, s, sm_count);
+  else launch_cls<4>(cls, B, max_m, s, sm_count);
 }

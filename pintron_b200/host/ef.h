@@ -77,6 +77,10 @@ typedef struct ef_seq {        /* mirrors struct _EST_info (include/types.h:140-
 } ef_seq;
 
 int ef_read_fasta(const char *path, ef_seq **out, size_t *n_out);
+typedef struct ef_fasta ef_fasta;                     /* streaming reader: one record per call */
+ef_fasta *ef_fasta_open(const char *path);
+int ef_fasta_next(ef_fasta *r, ef_seq *out);
+void ef_fasta_close(ef_fasta *r);
 void ef_parse_genomic_header(ef_seq *g);
 void ef_ntails_removal(ef_seq *g);
 void ef_set_gb(ef_seq *e);
@@ -191,10 +195,12 @@ typedef struct ef_job_result {          /* per input EST, filled by the workers 
   volatile int done;
 } ef_job_result;
 
-typedef void (*ef_task_fn)(ef_task *T, size_t index, void *user);
+typedef void (*ef_task_fn)(ef_task *T, size_t handle, void *user);
+/* the source of work: 1 = *handle is the next item, 0 = none available yet (the reader is behind), -1 = no more items, ever */
+typedef int (*ef_next_fn)(void *user, size_t *handle);
 void sched_prepare(const ef_config *cfg, const ef_seq *gen);   /* optional: start device set-up early, in the background */
-void sched_set_order(const uint32_t *order);                       /* optional permutation of the items: dispatch order */
-int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_fn fn, void *user);
+/* n_hint: the number of items when the whole input is already known (short inputs get fewer threads / fibers), else SIZE_MAX */
+int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_hint, ef_next_fn next, ef_task_fn fn, void *user);
 void sched_stats(double *gpu_wait_s, uint64_t *batches, uint64_t *jobs);
 struct pc_session_stats;
 void sched_engine_stats(struct pc_session_stats *sum, const char **mode);   /* what the engine did for this run (all GPUs) */

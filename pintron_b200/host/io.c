@@ -188,36 +188,59 @@ int ef_config_parse(ef_config *c, int argc, char **argv) {
 /* ---- FASTA ------------------------------------------------------------------------------------------------ */
 /* Lines are right-trimmed of bytes < 0x20 (src/util.c:166-173); a record is a '>' line followed by sequence lines
  * concatenated verbatim up to the next '>' line (or a line equal to "#\#", io-multifasta.c:102). */
-int ef_read_fasta(const char *path, ef_seq **out, size_t *n_out) {
+struct ef_fasta { FILE *f; char *line; size_t lcap; char *pending; };      /* pending: a header line already consumed */
+
+/* Streaming form (the reference reads the whole file into a list first, io-multifasta.c:93-167; a 27 GB mRNA set does not
+ * fit that way): one record per call, the file is read through a 4 MB stdio buffer. */
+ef_fasta *ef_fasta_open(const char *path) {
   FILE *f = fopen(path, "r");
-  if (!f) return -1;
-  ef_seq *v = NULL;
-  size_t n = 0, cap = 0;
-  char *line = NULL;
-  size_t lcap = 0;
+  if (!f) return NULL;
+  setvbuf(f, NULL, _IOFBF, (size_t)4 << 20);
+  ef_fasta *r = calloc(1, sizeof *r);
+  r->f = f;
+  return r;
+}
+
+void ef_fasta_close(ef_fasta *r) { if (!r) return; fclose(r->f); free(r->line); free(r->pending); free(r); }
+
+int ef_fasta_next(ef_fasta *r, ef_seq *out) {     /* 1 = *out holds the next record (id / seq / orig malloc'ed), 0 = end of file */
   ssize_t len;
   ef_buf cur = {0};
-  bool in_rec = false;
-  while ((len = getline(&line, &lcap, f)) != -1) {
+  char *hdr = r->pending;
+  r->pending = NULL;
+  for (;;) {
+    len = getline(&r->line, &r->lcap, r->f);
+    if (len == -1) break;
+    char *line = r->line;
     while (len > 0 && line[len - 1] < ' ') line[--len] = 0;   /* plain (signed) char, as util.c:168 */
     if (line[0] == '>') {
-      if (in_rec) { v[n - 1].seq = cur.p ? cur.p : strdup(""); v[n - 1].len = (int)cur.len; memset(&cur, 0, sizeof cur); }
-      if (n == cap) { cap = cap ? cap * 2 : 1024; v = realloc(v, cap * sizeof *v); }
-      memset(&v[n], 0, sizeof v[n]);
-      v[n].id = strdup(line + 1);
-      v[n].strand = 1;
-      ++n; in_rec = true;
-    } else if (in_rec) {
-      if (strcmp(line, "#\\#") == 0) {
-        v[n - 1].seq = cur.p ? cur.p : strdup(""); v[n - 1].len = (int)cur.len; memset(&cur, 0, sizeof cur);
-        in_rec = false;
-      } else if (len > 0) buf_write(&cur, line, (size_t)len);
+      if (hdr) { r->pending = strdup(line + 1); break; }       /* the next record starts: this one is complete */
+      hdr = strdup(line + 1);
+    } else if (hdr) {
+      if (strcmp(line, "#\\#") == 0) break;                    /* explicit record terminator (io-multifasta.c:102) */
+      if (len > 0) buf_write(&cur, line, (size_t)len);
     }
   }
-  if (in_rec) { v[n - 1].seq = cur.p ? cur.p : strdup(""); v[n - 1].len = (int)cur.len; }
-  free(line);
-  fclose(f);
-  for (size_t i = 0; i < n; ++i) v[i].orig = strdup(v[i].seq);
+  if (!hdr) { buf_free(&cur); return 0; }
+  memset(out, 0, sizeof *out);
+  out->id = hdr;
+  out->strand = 1;
+  out->seq = cur.p ? cur.p : strdup("");
+  out->len = (int)cur.len;
+  out->orig = strdup(out->seq);
+  return 1;
+}
+
+int ef_read_fasta(const char *path, ef_seq **out, size_t *n_out) {
+  ef_fasta *r = ef_fasta_open(path);
+  if (!r) return -1;
+  ef_seq *v = NULL, e;
+  size_t n = 0, cap = 0;
+  while (ef_fasta_next(r, &e)) {
+    if (n == cap) { cap = cap ? cap * 2 : 16; v = realloc(v, cap * sizeof *v); }
+    v[n++] = e;
+  }
+  ef_fasta_close(r);
   *out = v; *n_out = n;
   return 0;
 }

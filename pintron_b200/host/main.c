@@ -18,16 +18,49 @@
 typedef struct est_item {
   ef_seq fwd, rc;
   bool has_rc;
-  ef_buf raw, pest, megs, pmegs, edges, info;
+  ef_buf out[6];                  /* raw, processed-ests, megs, processed-megs, meg-edges, processed-megs-info */
   _Atomic int done;               /* set by the worker when every buffer above is final */
+  _Atomic int written;            /* writers that are through with this item (the last one frees its strings) */
 } est_item;
+enum { O_RAW = 0, O_PEST, O_MEGS, O_PMEGS, O_EDGES, O_INFO, O_COUNT };
+
+/* Streaming (the reference loads every EST first, io-multifasta.c:93-167): a reader thread parses
+ * ests.txt into WINDOWS of records; the scheduler hands the items of the windows out as they become ready (inside a
+ * window longest first, so ESTs in flight together have similar sizes); one writer per output file emits the windows in
+ * input order and releases them.  The reader stays at most WIN_AHEAD windows in front of the slowest writer, which bounds
+ * the memory of a run whatever the size of ests.txt. */
+#define WIN_BITS 20
+#define WIN_RECORDS 8192u
+#define WIN_BYTES ((size_t)48 << 20)
+#define WIN_AHEAD 10
+#define MAX_WINDOWS ((size_t)1 << 22)
+typedef struct window {
+  uint32_t n;
+  est_item *items;
+  uint32_t *order;                /* dispatch order inside the window */
+  _Atomic uint32_t next;          /* items handed out so far */
+  _Atomic int writers_done;
+} window;
 
 typedef struct run_ctx {
   const ef_config *cfg;
   const ef_seq *gen;
   const char *gen_orig;          /* the genome before N-tail removal (output bytes come from here) */
-  est_item *items;
+  window **win;                  /* MAX_WINDOWS slots; slot w is valid once n_ready > w */
+  _Atomic size_t n_ready, cur;
+  _Atomic size_t n_written[O_COUNT];
+  _Atomic int eof;
+  _Atomic size_t n_records;
+  FILE *f[O_COUNT];
+  double writer_busy[O_COUNT];
+  int rc;
 } run_ctx;
+#define it_raw out[O_RAW]
+#define it_pest out[O_PEST]
+#define it_megs out[O_MEGS]
+#define it_pmegs out[O_PMEGS]
+#define it_edges out[O_EDGES]
+#define it_info out[O_INFO]
 
 static void write_est_record(ef_buf *b, const ef_seq *e) { buf_printf(b, ">%s\n", e->id); buf_write(b, e->orig, strlen(e->orig)); buf_write(b, "\n", 1); }
 
@@ -88,20 +121,20 @@ static bool compute_est_fact(ef_task *T, const run_ctx *R, est_item *it, const e
     const double t_comp1 = ef_now();
     const bool got = L && L->n > 0;
     if ((!timed_out || got) && R->cfg->aux_outputs) {
-      buf_printf(&it->megs, "\n\n***********\n\n");
-      write_est_record(&it->megs, e);
-      meg_write(&it->megs, M);
+      buf_printf(&it->it_megs, "\n\n***********\n\n");
+      write_est_record(&it->it_megs, e);
+      meg_write(&it->it_megs, M);
     }
     if (got) {
       if (R->cfg->aux_outputs) {
-        buf_printf(&it->edges, ">%s\n", e->id);
-        meg_write_edges(&it->edges, M);
-        write_est_record(&it->pmegs, e);
-        meg_write(&it->pmegs, M);
+        buf_printf(&it->it_edges, ">%s\n", e->id);
+        meg_write_edges(&it->it_edges, M);
+        write_est_record(&it->it_pmegs, e);
+        meg_write(&it->it_pmegs, M);
       }
-      buf_printf(&it->info, "%llu %llu %zu\n", (unsigned long long)((t_meg1 - t_meg0) * 1e6), (unsigned long long)((t_comp1 - t_meg1) * 1e6), (size_t)L->n);
-      write_factorizations(&it->raw, R, e, L, polya, polyad);
-      write_est_record(&it->pest, e);
+      buf_printf(&it->it_info, "%llu %llu %zu\n", (unsigned long long)((t_meg1 - t_meg0) * 1e6), (unsigned long long)((t_comp1 - t_meg1) * 1e6), (size_t)L->n);
+      write_factorizations(&it->it_raw, R, e, L, polya, polyad);
+      write_est_record(&it->it_pest, e);
       return true;
     }
     if (!timed_out) return false;
@@ -110,9 +143,9 @@ static bool compute_est_fact(ef_task *T, const run_ctx *R, est_item *it, const e
 }
 
 static void est_task_body(ef_task *T, run_ctx *R, est_item *it);
-static void est_task(ef_task *T, size_t index, void *user) {
+static void est_task(ef_task *T, size_t handle, void *user) {
   run_ctx *R = user;
-  est_item *it = &R->items[index];
+  est_item *it = &R->win[handle >> WIN_BITS]->items[handle & (((size_t)1 << WIN_BITS) - 1)];
   est_task_body(T, R, it);
   atomic_store_explicit(&it->done, 1, memory_order_release);
 }
@@ -131,23 +164,100 @@ static void est_task_body(ef_task *T, run_ctx *R, est_item *it) {
   }
 }
 
-/* The writer: streams the per-EST records to the six files in INPUT order while the workers are still running. */
-typedef struct writer_ctx { est_item *items; size_t n; FILE *f[6]; double busy_s; } writer_ctx;
-
-static void *writer_main(void *arg) {
-  writer_ctx *W = arg;
-  for (size_t i = 0; i < W->n; ++i) {
-    est_item *it = &W->items[i];
-    while (!atomic_load_explicit(&it->done, memory_order_acquire)) usleep(200);
-    const double t0 = ef_now();
-    ef_buf *b[6] = {&it->raw, &it->pest, &it->megs, &it->pmegs, &it->edges, &it->info};
-    for (int k = 0; k < 6; ++k) {
-      if (b[k]->len) fwrite(b[k]->p, 1, b[k]->len, W->f[k]);
-      buf_free(b[k]);
-    }
-    W->busy_s += ef_now() - t0;
+/* ---- the source of work: windows filled by the reader ---------------------------------------------------------- */
+static int next_item(void *user, size_t *handle) {
+  run_ctx *R = user;
+  for (;;) {
+    const size_t w = atomic_load(&R->cur);
+    const int eof = atomic_load(&R->eof);                           /* read before n_ready: the reader sets it last */
+    if (w >= atomic_load_explicit(&R->n_ready, memory_order_acquire)) return eof ? -1 : 0;
+    window *W = R->win[w];
+    const uint32_t k = atomic_fetch_add(&W->next, 1);
+    if (k < W->n) { *handle = (w << WIN_BITS) | W->order[k]; return 1; }
+    size_t expect = w;
+    atomic_compare_exchange_strong(&R->cur, &expect, w + 1);      /* this window is handed out: on to the next */
   }
+}
+
+static void close_window(run_ctx *R, window *W) {
+  /* longest first (counting sort on min(len / 64, 63), descending) */
+  uint32_t cnt[65];
+  memset(cnt, 0, sizeof cnt);
+  W->order = malloc(sizeof(uint32_t) * (W->n ? W->n : 1));
+  for (uint32_t i = 0; i < W->n; ++i) { size_t b = (size_t)W->items[i].fwd.len >> 6; if (b > 63) b = 63; ++cnt[63 - b + 1]; }
+  for (int b = 0; b < 64; ++b) cnt[b + 1] += cnt[b];
+  for (uint32_t i = 0; i < W->n; ++i) { size_t b = (size_t)W->items[i].fwd.len >> 6; if (b > 63) b = 63; W->order[cnt[63 - b]++] = i; }
+  const size_t w = atomic_load(&R->n_ready);
+  R->win[w] = W;
+  atomic_fetch_add(&R->n_records, W->n);
+  atomic_store_explicit(&R->n_ready, w + 1, memory_order_release);
+}
+
+static void *reader_main(void *arg) {
+  run_ctx *R = arg;
+  ef_fasta *fa = ef_fasta_open("ests.txt");
+  if (!fa) { fprintf(stderr, "* FATAL File ests.txt not found! Terminating\n"); R->rc = 1; atomic_store(&R->eof, 1); return NULL; }
+  window *W = NULL;
+  size_t bytes = 0, cap = 0;
+  ef_seq e;
+  uint32_t win_records = WIN_RECORDS;
+  size_t win_ahead = WIN_AHEAD;
+  { const char *ov = getenv("EF_WINDOW"); if (ov && atol(ov) > 0 && atol(ov) < (1 << WIN_BITS)) win_records = (uint32_t)atol(ov); }     /* tests: tiny windows */
+  { const char *ov = getenv("EF_WINDOW_AHEAD"); if (ov && atol(ov) > 0) win_ahead = (size_t)atol(ov); }
+  while (ef_fasta_next(fa, &e)) {
+    if (!W) { W = calloc(1, sizeof *W); cap = 0; bytes = 0; }
+    if (W->n == cap) { cap = cap ? cap * 2 : 256; W->items = realloc(W->items, cap * sizeof(est_item)); }
+    memset(&W->items[W->n], 0, sizeof(est_item));
+    W->items[W->n++].fwd = e;       /* strand / reverse-complement / polyA masking happen in est_task, on the worker threads */
+    bytes += (size_t)e.len;
+    if (W->n >= win_records || bytes >= WIN_BYTES) {
+      if (atomic_load(&R->n_ready) + 1 >= MAX_WINDOWS) { fprintf(stderr, "* FATAL est-fact: too many input windows\n"); exit(1); }
+      close_window(R, W);
+      W = NULL;
+      /* stay at most WIN_AHEAD windows in front of the slowest writer */
+      for (;;) {
+        size_t slowest = (size_t)-1;
+        for (int k = 0; k < O_COUNT; ++k) { const size_t v = atomic_load(&R->n_written[k]); if (v < slowest) slowest = v; }
+        if (atomic_load(&R->n_ready) < slowest + win_ahead) break;
+        usleep(200);
+      }
+    }
+  }
+  if (W) close_window(R, W);
+  ef_fasta_close(fa);
+  atomic_store(&R->eof, 1);
   return NULL;
+}
+
+/* ---- writers: one per output file, each streams the records of its file in INPUT order while the workers run ----- */
+static void item_release(est_item *it) {
+  free(it->fwd.id); free(it->fwd.gb); free(it->fwd.seq); free(it->fwd.orig);
+  if (it->has_rc) { free(it->rc.id); free(it->rc.gb); free(it->rc.seq); free(it->rc.orig); }
+}
+
+typedef struct writer_arg { run_ctx *R; int k; } writer_arg;
+static void *writer_main(void *arg) {
+  run_ctx *R = ((writer_arg *)arg)->R;
+  const int k = ((writer_arg *)arg)->k;
+  for (size_t w = 0;; ++w) {
+    while (w >= atomic_load_explicit(&R->n_ready, memory_order_acquire)) {
+      if (atomic_load(&R->eof) && w >= atomic_load(&R->n_ready)) return NULL;
+      usleep(200);
+    }
+    window *W = R->win[w];
+    for (uint32_t i = 0; i < W->n; ++i) {
+      est_item *it = &W->items[i];
+      while (!atomic_load_explicit(&it->done, memory_order_acquire)) usleep(100);
+      const double t0 = ef_now();
+      ef_buf *b = &it->out[k];
+      if (b->len) fwrite_unlocked(b->p, 1, b->len, R->f[k]);
+      buf_free(b);
+      if (atomic_fetch_add(&it->written, 1) == O_COUNT - 1) item_release(it);
+      R->writer_busy[k] += ef_now() - t0;
+    }
+    if (atomic_fetch_add(&W->writers_done, 1) == O_COUNT - 1) { free(W->items); W->items = NULL; }   /* the struct itself stays: late next_item calls read n */
+    atomic_store(&R->n_written[k], w + 1);
+  }
 }
 
 static FILE *open_out(const char *name) {
@@ -189,60 +299,36 @@ int main(int argc, char **argv) {
   sched_prepare(&cfg, gen);
   ef_small_exon_index_build(gen->seq, (size_t)gen->len);      /* host-side 6-mer index, while the engine session opens */
   const double tl_index = ef_now();
-  ef_seq *ests = NULL; size_t nest = 0;
-  if (ef_read_fasta("ests.txt", &ests, &nest)) { fprintf(stderr, "* FATAL File ests.txt not found! Terminating\n"); return 1; }
-  const double tl_ests = ef_now();
-  FILE *f_raw = open_out("raw-multifasta-out.txt"), *f_megs = open_out("megs.txt"), *f_pmegs = open_out("processed-megs.txt");
-  FILE *f_info = open_out("processed-megs-info.txt"), *f_pest = open_out("processed-ests.txt"), *f_edges = open_out("meg-edges.txt");
+  static run_ctx R;
+  R.cfg = &cfg; R.gen = gen; R.gen_orig = gen->orig;
+  R.win = calloc(MAX_WINDOWS, sizeof(window *));              /* 32 MB of address space, touched as windows appear */
+  if (access("ests.txt", R_OK) != 0) { fprintf(stderr, "* FATAL File ests.txt not found! Terminating\n"); return 1; }
+  R.f[O_RAW] = open_out("raw-multifasta-out.txt"); R.f[O_MEGS] = open_out("megs.txt"); R.f[O_PMEGS] = open_out("processed-megs.txt");
+  R.f[O_INFO] = open_out("processed-megs-info.txt"); R.f[O_PEST] = open_out("processed-ests.txt"); R.f[O_EDGES] = open_out("meg-edges.txt");
   double t_io = ef_now() - t_io0;
-  if (!cfg.quiet) fprintf(stderr, "* INFO  Read %zu sequences.\n", nest);
-
-  est_item *items = calloc(nest ? nest : 1, sizeof *items);
-  for (size_t i = 0; i < nest; ++i) {
-    est_item *it = &items[i];
-    it->fwd = ests[i];       /* strand / reverse-complement / polyA masking happen in est_task, on the worker threads */
-  }
-
-  /* EST batcher: inside windows of input records the ESTs are dispatched longest first, so the ESTs in flight together
-   * (and the jobs of one device batch) have similar sizes; the writer still emits input order, so it can only stream a
-   * window out once that window is done.  Reads of similar length (ESTs): windows of 32 768, the output streams while
-   * later windows run.  Mixed inputs (a few long mRNAs carry most of the work): 262 144, so that the long ones all
-   * start early and the threads run dry together. */
-  size_t WIN = 262144;
-  {
-    size_t maxl = 0; double sum = 0;
-    for (size_t i = 0; i < nest; ++i) { const size_t l = strlen(ests[i].seq); sum += (double)l; if (l > maxl) maxl = l; }
-    if (nest && (double)maxl <= 4.0 * sum / (double)nest) WIN = 32768;
-    const char *ov = getenv("EF_WINDOW");            /* experiments only */
-    if (ov && atol(ov) > 0) WIN = (size_t)atol(ov);
-  }
-  uint32_t *order = malloc(sizeof(uint32_t) * (nest ? nest : 1));
-  {
-    uint32_t cnt[65];
-    for (size_t w0 = 0; w0 < nest; w0 += WIN) {
-      const size_t w1 = MIN2(nest, w0 + WIN);
-      memset(cnt, 0, sizeof cnt);                       /* counting sort on min(len / 64, 63), descending */
-      for (size_t i = w0; i < w1; ++i) { size_t b = strlen(ests[i].seq) >> 6; if (b > 63) b = 63; ++cnt[63 - b + 1]; }
-      for (int b = 0; b < 64; ++b) cnt[b + 1] += cnt[b];
-      for (size_t i = w0; i < w1; ++i) { size_t b = strlen(ests[i].seq) >> 6; if (b > 63) b = 63; order[w0 + cnt[63 - b]++] = (uint32_t)i; }
-    }
-  }
-  sched_set_order(order);
-  run_ctx R = {&cfg, gen, gen->orig, items};
-  writer_ctx W = {items, nest, {f_raw, f_pest, f_megs, f_pmegs, f_edges, f_info}, 0.0};
-  pthread_t wth;
-  if (pthread_create(&wth, NULL, writer_main, &W)) { perror("pthread_create"); return 1; }
+  pthread_t rth, wth[O_COUNT];
+  writer_arg wa[O_COUNT];
+  if (pthread_create(&rth, NULL, reader_main, &R)) { perror("pthread_create"); return 1; }
+  for (int k = 0; k < O_COUNT; ++k) { wa[k].R = &R; wa[k].k = k; if (pthread_create(&wth[k], NULL, writer_main, &wa[k])) { perror("pthread_create"); return 1; } }
+  /* short inputs are known in full before the first window closes: they get fewer threads and fibers (sched_run) */
+  while (!atomic_load(&R.eof) && atomic_load(&R.n_ready) == 0) usleep(100);
+  const size_t n_hint = atomic_load(&R.eof) ? atomic_load(&R.n_records) : SIZE_MAX;
+  const double tl_ests = ef_now();
   const double t_alg0 = ef_now();
-  if (sched_run(&cfg, gen, nest, est_task, &R)) return 1;
+  if (sched_run(&cfg, gen, n_hint, next_item, est_task, &R)) return 1;
   const double t_alg = ef_now() - t_alg0;
+  pthread_join(rth, NULL);
+  if (R.rc) return 1;
+  const size_t nest = atomic_load(&R.n_records);
+  if (!cfg.quiet) fprintf(stderr, "* INFO  Read %zu sequences.\n", nest);
   if (!cfg.quiet)
-    fprintf(stderr, "* INFO  timeline (s since start): genome read %.3f, small-exon index %.3f, ESTs read %.3f, dispatch order %.3f, workers done %.3f\n",
-            tl_genome - t0, tl_index - t0, tl_ests - t0, t_alg0 - t0, t_alg0 + t_alg - t0);
+    fprintf(stderr, "* INFO  timeline (s since start): genome read %.3f, small-exon index %.3f, first window / end of ests.txt %.3f, workers done %.3f\n",
+            tl_genome - t0, tl_index - t0, tl_ests - t0, t_alg0 + t_alg - t0);
 
   const double t_io1 = ef_now();
-  pthread_join(wth, NULL);
-  fclose(f_raw); fclose(f_megs); fclose(f_pmegs); fclose(f_info); fclose(f_pest); fclose(f_edges);
-  t_io += ef_now() - t_io1 + W.busy_s;
+  double wbusy = 0;
+  for (int k = 0; k < O_COUNT; ++k) { pthread_join(wth[k], NULL); fclose(R.f[k]); if (R.writer_busy[k] > wbusy) wbusy = R.writer_busy[k]; }
+  t_io += ef_now() - t_io1 + wbusy;
   fprintf(finfo, "end\t%ld\n", (long)time(NULL));
   fclose(finfo);
 

@@ -219,10 +219,10 @@ typedef struct worker {
   double gpu_wait, t_fibers, t_gather, t_submit;
 } worker;
 
-static _Atomic size_t g_next_item;
-static size_t g_n_items;
+static ef_next_fn g_next;            /* where items come from (main.c: the windows the FASTA reader has filled) */
+static void *g_next_user;
+static _Atomic int g_no_more;         /* the source has said -1 */
 static int g_nthreads = 1;
-static const uint32_t *g_order;       /* dispatch order (length-sorted windows), NULL = input order */
 static __thread fiber *tl_fiber;
 static __thread worker *tl_worker;
 static uint64_t g_batches, g_jobs, g_h2d, g_d2h, g_deferred, g_grows;
@@ -478,10 +478,11 @@ static bool run_group(worker *w, group *g) {
          * its fibers in one go would own the thousand longest ones (on mixed EST / mRNA inputs that is most of the
          * work of the run, fixed at t = 0).  Taking them in small bites while the other threads do the same spreads
          * the heavy ESTs evenly. */
-        if (started_now >= 64) break;
-        size_t idx = atomic_fetch_add(&g_next_item, 1);
-        if (idx >= g_n_items) break;
-        fiber_start(w, g, f, g_order ? g_order[idx] : idx);
+        if (started_now >= 64 || atomic_load_explicit(&g_no_more, memory_order_relaxed)) break;
+        size_t handle;
+        const int got = g_next(g_next_user, &handle);
+        if (got <= 0) { if (got < 0) atomic_store(&g_no_more, 1); break; }
+        fiber_start(w, g, f, handle);
         ++w->inflight; ++started_now;
       }
       if (f->state != F_RUNNABLE) break;
@@ -525,7 +526,11 @@ static void *worker_main(void *arg) {
   while (alive[0] || alive[1]) {
     for (int i = 0; i < 2; ++i)
       if (alive[i] || w->g[i].pending) alive[i] = run_group(w, &w->g[i]);
-    if (!alive[0] && !alive[1] && atomic_load_explicit(&g_next_item, memory_order_relaxed) < g_n_items) alive[0] = true;   /* nothing in flight but ESTs left */
+    if (!alive[0] && !alive[1] && !atomic_load(&g_no_more)) {      /* nothing in flight, but the reader may still deliver */
+      struct timespec ts = {0, 100 * 1000};
+      nanosleep(&ts, NULL);
+      alive[0] = true;
+    }
   }
   const double tw2 = ef_now();
   /* No tear-down: est-fact exits right after the last EST, and freeing pinned / device memory (two dozen streams,
@@ -540,8 +545,6 @@ static void *worker_main(void *arg) {
   pthread_mutex_unlock(&g_stat_mu);
   return NULL;
 }
-
-void sched_set_order(const uint32_t *order) { g_order = order; }
 
 void sched_bytes(uint64_t *h2d, uint64_t *d2h) { *h2d = g_h2d; *d2h = g_d2h; }
 
@@ -643,7 +646,7 @@ void sched_prepare(const ef_config *cfg, const ef_seq *gen) {
 
 void sched_engine_stats(pc_session_stats *sum, const char **mode) { if (sum) *sum = g_engine_stats; if (mode) *mode = g_engine_mode; }
 
-int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_fn fn, void *user) {
+int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_next_fn next, ef_task_fn fn, void *user) {
   const double ts0 = ef_now();
   if (!g_prep.started) sched_prepare(cfg, gen);
   pthread_join(g_prep.th, NULL);
@@ -658,8 +661,8 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_task_f
   }
   int per_group = g_prep.per_group;
   if ((size_t)per_group * 2 * (size_t)nthreads > n_items) per_group = (int)(n_items / (2 * (size_t)nthreads)) + 1;
-  atomic_store(&g_next_item, 0);
-  g_n_items = n_items;
+  g_next = next; g_next_user = user;
+  atomic_store(&g_no_more, 0);
   g_nthreads = nthreads;
   g_batches = g_jobs = g_h2d = g_d2h = g_deferred = g_grows = 0; g_gpu_wait = 0; g_t_fibers = g_t_gather = g_t_submit = g_t_init = g_t_fini = g_t_end_sum = g_t_end_min = 0;
   const double ts1 = ef_now();

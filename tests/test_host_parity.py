@@ -204,3 +204,13 @@ def test_client_fits_pintron_default_memory_limit(cpu_bin, cpu_daemon, tmp_path)
         assert U.md5s(str(d)) == {f: exp[f] for f in U.FILES}
     finally:
         srv.stop()
+
+
+def test_streaming_windows_and_back_pressure_keep_the_bytes(cpu_bin, tmp_path):
+    """ests.txt is read window by window while the workers run; the reader stays a bounded number of windows ahead of the
+    writers.  With 5-record windows and a look-ahead of 2 every mechanism is exercised all the time."""
+    env = dict(os.environ, EF_WINDOW="5", EF_WINDOW_AHEAD="2")
+    for case, extra in (("test-CPB2", ["--threads", "4", "--fibers", "3"]), ("test-AMBN", ["--threads", "2"]), ("edge-cases", [])):
+        d = tmp_path / case
+        d.mkdir()
+        U.check_case(cpu_bin, case, str(d), *extra, env=env)
