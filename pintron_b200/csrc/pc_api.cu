@@ -17,6 +17,7 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 static const bool g_prof = getenv("PC_PROFILE") != nullptr;
 #define PC_MULTI_STREAM_MAX ((size_t)1 << 18)        /* batches below this many jobs run their segments on side streams */
 static const bool g_serial = getenv("PC_SERIAL_SEGMENTS") != nullptr;      /* experiments: keep every batch on one stream */
+#define PC_POOL_MB_DEFAULT 320         /* scratch pool per stream (direction words, wavefront matrices); grows on demand */
 #define PC_DEVICE_ORDER_MIN ((size_t)1 << 16)      /* batches from this size up are ordered on the device (k_order.cu) */
 /* PC_CAPTURE=<file>: every batch handed to pc_submit is appended to <file> (bench.py replays the job stream of a real
  * est-fact run as its device-resident workload).  Record = u32 njobs, u64 arena_bytes, jobs, arena. */
@@ -118,6 +119,7 @@ struct DevBuf {
     g_base = nullptr; p = nullptr; cap = 0;
     if (cudaMalloc(&g_base, b16 + 2 * GUARD) != cudaSuccess) { g_base = nullptr; return fail(PC_E_NOMEM, "%s", "cudaMalloc (guard mode)"); }
     cudaMemset(g_base, 0xA5, b16 + 2 * GUARD);
+    cudaDeviceSynchronize();                          /* the fill runs on the legacy stream, which our non-blocking streams do not wait for */
     p = (uint8_t *)g_base + GUARD; cap = b16; g_bytes = b16;
     return 0;
   }
@@ -277,7 +279,8 @@ extern "C" pc_stream *pc_stream_create(pc_ctx *c) {
   }
   /* scratch pool and staging as ONE allocation made up front: cudaMalloc / cudaFree while other streams run
    * serialise the whole device.  Buffers that outgrow their share later get their own allocation. */
-  const size_t sizes[7] = {256ull << 20, 8u << 20, 8u << 20, sizeof(pc_job) << 16, (sizeof(int32_t) * PC_RES_INTS) << 16, 4u << 16, 8u << 14};
+  static const size_t pool_mb = getenv("PC_POOL_MB") && atol(getenv("PC_POOL_MB")) >= 16 ? (size_t)atol(getenv("PC_POOL_MB")) : PC_POOL_MB_DEFAULT;
+  const size_t sizes[7] = {pool_mb << 20, 8u << 20, 8u << 20, sizeof(pc_job) << 16, (sizeof(int32_t) * PC_RES_INTS) << 16, 4u << 16, 8u << 14};
   DevBuf *bufs[7] = {&st->pool, &st->arena, &st->var, &st->jobs, &st->res, &st->idx, &st->lcs_best};
   if (g_guard) {               /* no slab: every buffer on its own, exactly sized, between guard bands (only the pool is sized up front) */
     if (st->pool.reserve(sizes[0])) { pc_stream_destroy(st); return nullptr; }
@@ -499,7 +502,7 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
       if (tot >= 0x7fffffffull) return fail(PC_E_RANGE, "%s", "LCS batch too large for one launch");
       pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, d_prefix, (uint32_t)tot, max_l2, ss);
     } else if (op == PC_OP_GAP && cls < 3) {
-      pc_launch_gap_pairs(cls, B, (int)max_l1, ss, c->sm_count);
+      pc_launch_gap_pairs(cls, B, (int)max_l1, d_slow_count + sg, ss, c->sm_count);
     } else if (op == PC_OP_BORDERS && cls < 3) {
       pc_launch_borders_packed(cls, B, (int)std::min<uint32_t>(seg[sg].max_t, PC_BORDERS_FAST_MAX_T), ss, c->sm_count);
     } else if (op == PC_OP_BORDERS) {
@@ -518,6 +521,14 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
       pc_launch_dp((int)op, B, ss, c->sm_count);
     }
     st->op_launches[op] += tl_pc_launches - before;
+    if (g_guard) {                                       /* debugging mode: name the segment whose kernel faulted */
+      const cudaError_t ge = cudaStreamSynchronize(ss);
+      if (ge != cudaSuccess) {
+        static thread_local char msg[200];
+        snprintf(msg, sizeof msg, "PC_GUARD: kernel of op %u class %d (%d jobs, longest a %d, longest b %lld) faulted: %s", op, cls, B.n, max_l2, max_l1, cudaGetErrorString(ge));
+        return fail(PC_E_CUDA, "%s", msg);
+      }
+    }
     if (g_prof) g_op_launches[op] += 1;
     if (st->timers || g_prof) { cudaEventRecord(e1, ss); st->ev_pending.push_back({(int)op, {e0, e1}}); }
     i = j;

@@ -151,7 +151,7 @@ void pc_collect_status(const int32_t *d_res, int n, int code, uint32_t *d_list, 
 void pc_lcs_prefix(const pc_job *d_jobs, const uint32_t *d_order, int n, int lcs_tpb, int lcs_max_s2, uint32_t *d_prefix, cudaStream_t s);
 void pc_launch_borders_chunked(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count);
 void pc_launch_borders_packed(int cls, const PcDevBatch &B, int tcap, cudaStream_t s, int sm_count);
-void pc_launch_gap_pairs(int cls, const PcDevBatch &B, int max_m, cudaStream_t s, int sm_count);
+void pc_launch_gap_pairs(int cls, const PcDevBatch &B, int max_m, uint32_t *work, cudaStream_t s, int sm_count);
 void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count);
 int pc_lcs_blocks(long long l1, int l2);
 int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t *d_blk_prefix, uint32_t total_blocks, int max_l2,
