@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(128) k_seed(PcDevBatch B) {
 // diagonal i1-i2; one thread walks one diagonal, a block stages its slice of s1 in shared memory.  The
 // reference keeps the FIRST strictly longer run in (i1 outer, i2 inner) order = max len, then min i1, then
 // min i2: packed so that one 64-bit atomicMax per block picks it.
-#define LCS_TPB PC_LCS_TPB
+#define LCS_TPB 256                 /* threads (= diagonals) of one block of the locate pass */
+#define LCS_TILE PC_LCS_TPB          /* diagonals of one tile of the length pass (one warp, 32 per lane) */
 #define LCS_MAX_S2 PC_LCS_MAX_S2
 
 __device__ __forceinline__ unsigned long long lcs_key(int len, uint32_t i1, int i2) {
@@ -313,31 +314,199 @@ __device__ __forceinline__ void lcs_block_generic(const uint8_t *s1, long long l
   if ((threadIdx.x & 31) == 0 && key) atomicMax(best_w, key);
 }
 
-// One flat grid over the blocks of ALL jobs of the batch (blk_prefix[w] = first block of job w): a 2 Mbp genome scan
-// and hundreds of 23 x 23 jobs share a launch without the small jobs paying for the long one's grid.
-__global__ void __launch_bounds__(LCS_TPB) k_lcs(PcDevBatch B, unsigned long long *best, const uint32_t *blk_prefix) {
-  __shared__ int s_job;
-  if (threadIdx.x == 0) {
-    int lo = 0, hi = B.n - 1;                             // last job whose first block is <= blockIdx.x
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (blk_prefix[mid] <= blockIdx.x) lo = mid; else hi = mid - 1; }
-    s_job = lo;
+// ---- the scan in two passes ----------------------------------------------------------------------------------------
+// Pass 1 (k_lcs_len) only asks HOW LONG the longest common run of every tile is, with the DP transposed: a lane owns 32
+// consecutive diagonals as the 32 bits of a word, so one AND serves 32 cells.  The bytes of s1 are read as nine bit planes
+// (the eight bits of the byte + "is N"): for the genome they are built once per upload (pc_build_planes) and a lane just
+// loads its three words per plane; for strings in the arena the warp builds them with ballots.  For column i2 the cells
+// of the lane's diagonals are the plane bits shifted by i2, compared with the (uniform) byte s2[i2]; the 32-bit equality
+// words of all columns go to shared memory, and "runs of length >= k+1 ending here" = R_k[i2] & R_k[i2-1] is applied until
+// nothing is left: the number of rounds is the longest run.  Pass 2 (k_lcs_pick) lists the tiles that reach their job's
+// maximum; pass 3 (k_lcs_locate) runs the position-exact per-diagonal form above on those few tiles only.  The reference's
+// answer — first strictly longer run in (i1 outer, i2 inner) order — is max length, then min i1, then min i2, whatever
+// the order of evaluation, so the split changes nothing.  (One thread per diagonal spent ~360 instructions on ~20 cells.)
+constexpr int LCS_WPB = 4;                      // warps per block of the length pass
+constexpr int LCS_ROWS = LCS_TILE / 32 + 3;     // plane words a tile needs: 1024 diagonals + up to 63 more columns
+struct LcsWarpMem {
+  uint32_t planes[9][LCS_ROWS + 1];
+  uint32_t R[64][32];
+  uint32_t s2b[64];
+};
+
+__device__ __forceinline__ uint32_t range_mask(long long lo, long long hi, long long base) {   // bits b with lo <= base + b < hi
+  const long long a = lo - base, e = hi - base;
+  if (e <= 0 || a >= 32) return 0u;
+  const uint32_t m_hi = e >= 32 ? 0xffffffffu : ((1u << (int)e) - 1u);
+  const uint32_t m_lo = a <= 0 ? 0xffffffffu : (0xffffffffu << (int)a);
+  return m_hi & m_lo;
+}
+
+__global__ void __launch_bounds__(LCS_WPB * 32) k_lcs_len(PcDevBatch B, unsigned long long *best, const uint32_t *blk_prefix, uint32_t total_tiles,
+                                                          uint32_t *tile_len) {
+  __shared__ LcsWarpMem smem[LCS_WPB];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  LcsWarpMem &M = smem[wib];
+  const uint32_t gw = blockIdx.x * LCS_WPB + wib, nw = gridDim.x * LCS_WPB;
+  const uint32_t t0 = (uint32_t)(((unsigned long long)total_tiles * gw) / nw), t1 = (uint32_t)(((unsigned long long)total_tiles * (gw + 1)) / nw);
+  if (t0 >= t1) return;
+  int w;
+  {
+    int lo = 0, hi = B.n - 1;                             // last job whose first tile is <= t0 (every lane: same loads, broadcast)
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (blk_prefix[mid] <= t0) lo = mid; else hi = mid - 1; }
+    w = lo;
   }
-  __syncthreads();
-  const int w = s_job;
-  const uint32_t bx = blockIdx.x - blk_prefix[w];
-  const uint32_t ji = B.idx[w];
-  const pc_job *job = B.jobs + ji;
-  const uint8_t *s2 = B.arena + job->a_off;
-  const int l2 = (int)job->a_len;
-  const uint8_t *s1 = ((job->flags & PC_B_IN_GENOME) ? B.genome : B.arena) + job->b_off;
-  const long long l1 = job->b_len;
-  if (l2 > LCS_MAX_S2) return;                              // reported by k_lcs_finish
-  // diagonals d = i1 - i2 in [-(l2-1), l1-1]; this block owns LCS_TPB consecutive ones
-  const long long d0 = (long long)bx * LCS_TPB - (l2 - 1);
-  if (d0 > l1 - 1) return;
+  int cur = -1, l2 = 0;
+  const uint8_t *s1 = nullptr, *s2 = nullptr;
+  long long l1 = 0, goff = -1;                            // goff >= 0: s1 lies in the genome at this offset (planes precomputed)
+  uint32_t first = 0;
+  for (uint32_t t = t0; t < t1; ++t) {
+    while (w + 1 < B.n && blk_prefix[w + 1] <= t) ++w;
+    if (w != cur) {
+      cur = w;
+      const pc_job *job = B.jobs + B.idx[w];
+      s2 = B.arena + job->a_off; l2 = (int)job->a_len;
+      const bool ing = (job->flags & PC_B_IN_GENOME) != 0;
+      s1 = (ing ? B.genome : B.arena) + job->b_off; l1 = job->b_len;
+      goff = (ing && B.gplanes) ? (long long)job->b_off : -1;
+      first = blk_prefix[w];
+      __syncwarp();
+      if (l2 <= 64) for (int i = lane; i < l2; i += 32) M.s2b[i] = s2[i];
+      __syncwarp();
+    }
+    if (l2 > 64 || l2 <= 0) { if (lane == 0) tile_len[t] = 0xffffffffu; continue; }      // the locate pass handles these itself
+    const long long tile_d0 = (long long)(t - first) * LCS_TILE - (l2 - 1);                // first diagonal of the tile
+    if (tile_d0 > l1 - 1) { if (lane == 0) tile_len[t] = 0; continue; }
+    const long long p0 = tile_d0 + 32 * lane;                                              // s1 position of this lane's bit 0 at column 0
+    uint32_t X[9][3];
+    if (goff >= 0) {
+      const long long g0 = goff + p0;                                                      // absolute genome position (may be negative by < 64)
+      const long long wi = g0 >> 5;                                                        // arithmetic shift: floor
+      const int bit = (int)(g0 & 31);
+#pragma unroll
+      for (int p = 0; p < 9; ++p) {
+        const uint32_t *pl = B.gplanes + (size_t)p * B.gplane_words;
+        uint32_t W[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const long long x = wi + q; W[q] = (x >= 0 && x < (long long)B.gplane_words) ? pl[x] : 0u; }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) X[p][q] = __funnelshift_r(W[q], W[q + 1], bit);
+      }
+    } else {
+      __syncwarp();
+      for (int r = 0; r < LCS_ROWS; ++r) {                                                 // 32 positions per round, one ballot per plane
+        const long long pos = tile_d0 + 32 * r + lane;
+        const uint8_t c = (pos >= 0 && pos < l1) ? s1[pos] : 0;
+        uint32_t bal[9];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) bal[p] = __ballot_sync(0xffffffffu, (c >> p) & 1u);
+        bal[8] = __ballot_sync(0xffffffffu, pc_is_n(c));
+        if (lane < 9) {
+          uint32_t v = bal[0];
+#pragma unroll
+          for (int p = 1; p < 9; ++p) v = lane == p ? bal[p] : v;
+          M.planes[lane][r] = v;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < 9; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) X[p][q] = M.planes[p][lane + q];
+    }
+    uint32_t V[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) V[q] = range_mask(0, l1, p0 + 32 * q);                     // positions that exist in s1
+    // equality words of all columns
+    uint32_t any = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {                 // columns 0..31 read words 0 and 1 of the window, columns 32..63 words 1 and 2
+      const int i2_end = min(l2, 32 * (half + 1));
+      for (int i2 = 32 * half; i2 < i2_end; ++i2) {
+        const uint32_t sym = M.s2b[i2];
+        const int sh = i2 & 31;
+        uint32_t diff = 0;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) diff |= __funnelshift_r(X[p][half], X[p][half + 1], sh) ^ (0u - ((sym >> p) & 1u));
+        const uint32_t an = __funnelshift_r(X[8][half], X[8][half + 1], sh), av = __funnelshift_r(V[half], V[half + 1], sh);
+        const uint32_t e = (~diff | an | (pc_is_n((uint8_t)sym) ? 0xffffffffu : 0u)) & av;
+        M.R[i2][lane] = e;
+        any |= e;
+      }
+    }
+    // longest run: R_{k+1}[i2] = R_k[i2] & R_k[i2-1]
+    int len = any ? 1 : 0;
+    unsigned alive = __ballot_sync(0xffffffffu, any != 0);
+    for (int k = 1; alive && k < l2; ++k) {
+      uint32_t nz = 0, up = M.R[l2 - 1][lane];
+      for (int i2 = l2 - 1; i2 >= k; --i2) {
+        const uint32_t dn = M.R[i2 - 1][lane];
+        const uint32_t v = up & dn;
+        M.R[i2][lane] = v;
+        nz |= v;
+        up = dn;
+      }
+      if (nz) len = k + 1;
+      alive = __ballot_sync(0xffffffffu, nz != 0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if (lane == 0) {
+      tile_len[t] = (uint32_t)len;
+      if (len) atomicMax(best + w, (unsigned long long)len << 48);                           // positions come from the locate pass
+    }
+  }
+}
+
+// the tiles that reach their job's longest run (and the tiles the length pass left alone)
+__global__ void __launch_bounds__(256) k_lcs_pick(const unsigned long long *best, const uint32_t *blk_prefix, int n, uint32_t total_tiles,
+                                                  const uint32_t *tile_len, uint32_t *list, uint32_t *count) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total_tiles; t += gridDim.x * blockDim.x) {
+    const uint32_t tl = tile_len[t];
+    if (tl == 0) continue;
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (blk_prefix[mid] <= t) lo = mid; else hi = mid - 1; }
+    while (lo + 1 < n && blk_prefix[lo + 1] <= t) ++lo;
+    if (tl == 0xffffffffu || tl == (uint32_t)(best[lo] >> 48)) list[atomicAdd(count, 1u)] = t;
+  }
+}
+
+// position-exact pass over the listed tiles: LCS_TILE / LCS_TPB blocks of the per-diagonal form each
+__global__ void __launch_bounds__(LCS_TPB) k_lcs_locate(PcDevBatch B, unsigned long long *best, const uint32_t *blk_prefix, const uint32_t *list,
+                                                        const uint32_t *count) {
   extern __shared__ __align__(16) uint8_t sh[];
-  if (l2 <= 64) lcs_block_bits(s1, l1, s2, l2, d0, sh, best + w);
-  else lcs_block_generic(s1, l1, s2, l2, d0, sh, best + w);
+  constexpr int SUBS = LCS_TILE / LCS_TPB;
+  const uint32_t n_items = *count * SUBS;
+  for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const uint32_t t = list[it / SUBS], sub = it % SUBS;
+    int lo = 0, hi = B.n - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (blk_prefix[mid] <= t) lo = mid; else hi = mid - 1; }
+    while (lo + 1 < B.n && blk_prefix[lo + 1] <= t) ++lo;
+    const int w = lo;
+    const pc_job *job = B.jobs + B.idx[w];
+    const uint8_t *s2 = B.arena + job->a_off;
+    const int l2 = (int)job->a_len;
+    const uint8_t *s1 = ((job->flags & PC_B_IN_GENOME) ? B.genome : B.arena) + job->b_off;
+    const long long l1 = job->b_len;
+    const long long d0 = (long long)(t - blk_prefix[w]) * LCS_TILE + (long long)sub * LCS_TPB - (l2 - 1);
+    if (l2 <= LCS_MAX_S2 && l2 > 0 && d0 <= l1 - 1) {
+      if (l2 <= 64) lcs_block_bits(s1, l1, s2, l2, d0, sh, best + w);
+      else lcs_block_generic(s1, l1, s2, l2, d0, sh, best + w);
+    }
+    __syncthreads();
+  }
+}
+
+// nine bit planes of the genome (bit 0..7 of every byte, "is N"), built once per upload: plane p = words [p * nwords, (p + 1) * nwords)
+__global__ void __launch_bounds__(256) k_genome_planes(const uint8_t *g, uint32_t len, uint32_t nwords, uint32_t *planes) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t wd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wd < nwords; wd += (gridDim.x * blockDim.x) >> 5) {
+    const uint32_t pos = wd * 32 + lane;
+    const uint8_t c = pos < len ? g[pos] : 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) { const uint32_t b = __ballot_sync(0xffffffffu, (c >> p) & 1u); if (lane == p) planes[(size_t)p * nwords + wd] = b; }
+    const uint32_t bn = __ballot_sync(0xffffffffu, pc_is_n(c));
+    if (lane == 8) planes[(size_t)8 * nwords + wd] = bn;
+  }
 }
 
 __global__ void k_lcs_finish(PcDevBatch B, const unsigned long long *best) {
@@ -372,18 +541,46 @@ void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count) {
 // best: device array of B.n 64-bit slots (zeroed here); max_l1/max_l2 over the jobs of the batch
 int pc_lcs_blocks(long long l1, int l2) {                       // blocks one job needs (0 for an oversized s2: reported by the finish kernel)
   if (l2 > LCS_MAX_S2 || l2 <= 0 || l1 <= 0) return 0;
-  return (int)((l1 + l2 - 1 + LCS_TPB - 1) / LCS_TPB);
+  return (int)((l1 + l2 - 1 + LCS_TILE - 1) / LCS_TILE);
 }
 
-int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t *d_blk_prefix, uint32_t total_blocks, int max_l2,
+// best: B.n 64-bit slots; work: 2 * total_tiles + 4 uint32 (tile lengths, tile list, list counter); all zeroed / filled here
+int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t *d_blk_prefix, uint32_t total_tiles, int max_l2, uint32_t *work,
                   cudaStream_t s) {
   if (max_l2 > LCS_MAX_S2) max_l2 = LCS_MAX_S2;
   cudaMemsetAsync(best, 0, sizeof(unsigned long long) * B.n, s);
-  size_t sh = LCS_TPB + 2 * (size_t)max_l2 + 8;
-  if (sh < LCS_TPB + 64 + 8 + 4 * ((LCS_TPB + 64) / 32 + 2) + 72 + 16) sh = LCS_TPB + 64 + 8 + 4 * ((LCS_TPB + 64) / 32 + 2) + 72 + 16;
-  if (total_blocks > 0) { k_lcs<<<total_blocks, LCS_TPB, sh, s>>>(B, best, d_blk_prefix); PC_COUNT_LAUNCH(1); }
+  if (total_tiles > 0) {
+    uint32_t *tile_len = work, *list = work + total_tiles, *count = work + 2 * (size_t)total_tiles;
+    cudaMemsetAsync(count, 0, 16, s);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = pc_cached_occupancy((const void *)k_lcs_len, LCS_WPB * 32, 0);
+    const uint32_t need1 = (total_tiles + LCS_WPB - 1) / LCS_WPB;
+    const uint32_t grid1 = need1 < (uint32_t)(sms * per_sm) ? need1 : (uint32_t)(sms * per_sm);
+    k_lcs_len<<<grid1, LCS_WPB * 32, 0, s>>>(B, best, d_blk_prefix, total_tiles, tile_len);
+    const uint32_t need2 = (total_tiles + 255) / 256;
+    k_lcs_pick<<<need2 < (uint32_t)(sms * 8) ? need2 : (uint32_t)(sms * 8), 256, 0, s>>>(best, d_blk_prefix, B.n, total_tiles, tile_len, list, count);
+    size_t sh = LCS_TPB + 2 * (size_t)max_l2 + 8;
+    if (sh < LCS_TPB + 64 + 8 + 4 * ((LCS_TPB + 64) / 32 + 2) + 72 + 16) sh = LCS_TPB + 64 + 8 + 4 * ((LCS_TPB + 64) / 32 + 2) + 72 + 16;
+    const uint32_t need3 = total_tiles * (LCS_TILE / LCS_TPB);
+    const uint32_t cap3 = (uint32_t)(sms * pc_cached_occupancy((const void *)k_lcs_locate, LCS_TPB, sh));
+    k_lcs_locate<<<need3 < cap3 ? need3 : cap3, LCS_TPB, sh, s>>>(B, best, d_blk_prefix, list, count);
+    PC_COUNT_LAUNCH(3);
+  }
   k_lcs_finish<<<(B.n + 127) / 128, 128, 0, s>>>(B, best);
   PC_COUNT_LAUNCH(1);
+  return 0;
+}
+
+// bit planes of the genome for the LCS scan; planes: 9 * nwords uint32 (grown here), *nwords_out = words per plane
+int pc_build_planes(const uint8_t *d_genome, uint32_t len, PcGrowBuf &planes, uint32_t *nwords_out, cudaStream_t s) {
+  const uint32_t nwords = (len + 31) / 32 + 8;
+  if (planes.reserve(9ull * nwords * sizeof(uint32_t))) return PC_E_NOMEM;
+  const uint32_t blocks = (nwords * 32 + 255) / 256;
+  k_genome_planes<<<blocks < 4096 ? blocks : 4096, 256, 0, s>>>(d_genome, len, nwords, (uint32_t *)planes.p);
+  PC_COUNT_LAUNCH(1);
+  *nwords_out = nwords;
   return 0;
 }
 

@@ -95,6 +95,7 @@ struct pc_ctx {
   uint32_t ix_n = 0;
   int ix_word = 0;
   double depth_rate = 0.2;
+  const uint32_t *gplanes = nullptr; uint32_t gplane_words = 0;
   PcGrowBuf genome_buf;         /* the buffers behind d_genome / ix_*: kept (and grown) across pc_genome_upload calls */
   PcIndexBufs ix_bufs;
   cudaStream_t up = nullptr;    /* uploads and index builds run here, not on the legacy stream */
@@ -241,7 +242,7 @@ extern "C" void pc_ctx_destroy(pc_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   c->genome_buf.release();
-  for (PcGrowBuf *b : {&c->ix_bufs.keys_in, &c->ix_bufs.keys_out, &c->ix_bufs.pos_in, &c->ix_bufs.pos_out, &c->ix_bufs.tmp, &c->ix_bufs.bstart}) b->release();
+  for (PcGrowBuf *b : {&c->ix_bufs.keys_in, &c->ix_bufs.keys_out, &c->ix_bufs.pos_in, &c->ix_bufs.pos_out, &c->ix_bufs.tmp, &c->ix_bufs.bstart, &c->ix_bufs.planes}) b->release();
   if (c->up) cudaStreamDestroy(c->up);
   delete c;
 }
@@ -259,6 +260,9 @@ extern "C" int pc_genome_upload(pc_ctx *c, const char *genome, size_t len, int w
   c->depth_rate = depth_rate;
   int rc = pc_build_index(c->d_genome, c->genome_len, word_len, c->ix_bufs, &c->ix_keys, &c->ix_pos, &c->ix_n, &c->ix_bstart, &c->ix_shift, c->up);
   if (rc) return fail(rc, "%s", "pc_genome_upload: index build failed");
+  c->gplanes = nullptr;
+  if (pc_build_planes(c->d_genome, c->genome_len, c->ix_bufs.planes, &c->gplane_words, c->up)) return fail(PC_E_NOMEM, "%s", "pc_genome_upload: bit planes");
+  c->gplanes = (const uint32_t *)c->ix_bufs.planes.p;
   CU(cudaStreamSynchronize(c->up));
   return 0;
 }
@@ -445,6 +449,7 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
   B.jobs = d_jobs; B.res = d_res; B.var_out = d_var;
   B.pool = (uint8_t *)st->pool.p; B.pool_cap = st->pool.cap; B.pool_need = st->d_pool_need;
   B.slots = 1; B.max_warps = st->max_warps; B.n_dev = nullptr;
+  B.gplanes = c->gplanes; B.gplane_words = c->gplane_words;
   B.ix_keys = c->ix_keys; B.ix_pos = c->ix_pos; B.ix_bstart = c->ix_bstart; B.ix_shift = c->ix_shift; B.ix_n = c->ix_n; B.ix_word = c->ix_word; B.depth_rate = c->depth_rate;
   int nseg_live = 0;
   for (int sg = 0; sg < NSEG; ++sg) nseg_live += seg[sg].n != 0;
@@ -481,8 +486,10 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
       pc_launch_seed(B, ss, c->sm_count);
     } else if (op == PC_OP_LCS) {
       // [best slots | block prefix] in one device buffer; the prefix comes from the host copy of the jobs
-      const size_t best_b = (8ull * B.n + 255u) & ~(size_t)255u;
-      if (st->lcs_best.reserve(best_b + 4ull * (B.n + 1))) { if (e0) { st->ev_free.push_back(e0); st->ev_free.push_back(e1); } return PC_E_NOMEM; }
+      const size_t best_b = (8ull * B.n + 255u) & ~(size_t)255u, prefix_b = (4ull * (B.n + 1) + 255u) & ~(size_t)255u;
+      const uint64_t tiles_bound = on_device ? seg[sg].lcs_blocks : [&] { uint64_t z = 0; for (size_t q = i; q < j; ++q) { const pc_job &jb = h_jobs[order.p[q]]; z += (uint64_t)pc_lcs_blocks(jb.b_len, (int)jb.a_len); } return z; }();
+      if (tiles_bound >= 0x7fffffffull) return fail(PC_E_RANGE, "%s", "LCS batch too large for one launch");
+      if (st->lcs_best.reserve(best_b + prefix_b + 4ull * (2 * tiles_bound + 8))) { if (e0) { st->ev_free.push_back(e0); st->ev_free.push_back(e1); } return PC_E_NOMEM; }
       uint32_t *d_prefix = (uint32_t *)((uint8_t *)st->lcs_best.p + best_b);
       uint64_t tot = 0;
       if (on_device) {
@@ -500,7 +507,7 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
         CU(cudaMemcpyAsync(d_prefix, pl.p, 4ull * (B.n + 1), cudaMemcpyHostToDevice, ss));
       }
       if (tot >= 0x7fffffffull) return fail(PC_E_RANGE, "%s", "LCS batch too large for one launch");
-      pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, d_prefix, (uint32_t)tot, max_l2, ss);
+      pc_launch_lcs(B, (unsigned long long *)st->lcs_best.p, d_prefix, (uint32_t)tot, max_l2, (uint32_t *)((uint8_t *)st->lcs_best.p + best_b + prefix_b), ss);
     } else if (op == PC_OP_GAP && cls < 3) {
       pc_launch_gap_pairs(cls, B, (int)max_l1, d_slow_count + sg, ss, c->sm_count);
     } else if (op == PC_OP_BORDERS && cls < 3) {

@@ -31,12 +31,15 @@ struct PcDevBatch {
   uint32_t ix_n;
   int ix_word;
   double depth_rate;
+  /* nine bit planes of the genome (LCS scan), or nullptr */
+  const uint32_t *gplanes;
+  uint32_t gplane_words;
 };
 
 /* device-side job ordering (k_order.cu) */
 #define PC_ORDER_SEGS (PC_OP_COUNT * 4)
 #define PC_ORDER_BINS (PC_ORDER_SEGS * 64)
-#define PC_LCS_TPB 256
+#define PC_LCS_TPB 1024        /* diagonals per tile of the LCS scan (tile counts are computed with this on host and device) */
 #define PC_LCS_MAX_S2 4096
 struct PcSegStat { uint32_t n, max_a, max_b, max_t; unsigned long long lcs_blocks; };      /* max_t: widest BORDERS window */
 __host__ __device__ inline uint32_t pc_borders_window(const pc_job &j) {
@@ -154,7 +157,7 @@ void pc_launch_borders_packed(int cls, const PcDevBatch &B, int tcap, cudaStream
 void pc_launch_gap_pairs(int cls, const PcDevBatch &B, int max_m, uint32_t *work, cudaStream_t s, int sm_count);
 void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count);
 int pc_lcs_blocks(long long l1, int l2);
-int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t *d_blk_prefix, uint32_t total_blocks, int max_l2,
+int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t *d_blk_prefix, uint32_t total_blocks, int max_l2, uint32_t *work,
                   cudaStream_t s);
 /* device buffers of one genome index; they only grow, so a context that is reused for the next genome (the engine keeps
  * idle contexts) builds its index without a single cudaMalloc / cudaFree */
@@ -171,7 +174,8 @@ struct PcGrowBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
-struct PcIndexBufs { PcGrowBuf keys_in, keys_out, pos_in, pos_out, tmp, bstart; };
+struct PcIndexBufs { PcGrowBuf keys_in, keys_out, pos_in, pos_out, tmp, bstart, planes; };
+int pc_build_planes(const uint8_t *d_genome, uint32_t len, PcGrowBuf &planes, uint32_t *nwords_out, cudaStream_t s);
 int pc_build_index(const uint8_t *d_genome, uint32_t len, int word, PcIndexBufs &bufs, unsigned long long **keys, uint32_t **pos,
                    uint32_t *n_out, uint32_t **bstart, int *shift, cudaStream_t s);
 extern unsigned long long g_pc_launches;

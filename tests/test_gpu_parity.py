@@ -261,6 +261,9 @@ def test_lcs_bit_parallel_vs_port(cu, port):
                 s1[at:at + len(piece)] = piece
         if it % 5 == 0:
             s1 = bytearray(bytes(s1).lower()[: len(s1) // 2] + bytes(s1)[len(s1) // 2:])
+        if it % 7 == 3:                                       # bytes outside ACGTN / acgtn: the bit-plane form hands the block to the byte form
+            tgt = s1 if it % 2 else s2
+            tgt[r.randrange(len(tgt))] = r.choice(b"RY*#-x")
         b.add(PC_OP.LCS, bytes(s2), bytes(s1)); cases.append((bytes(s1), bytes(s2)))
     res, _ = cu.run(b)
     for (s1, s2), rr in zip(cases, res):
