@@ -202,6 +202,7 @@ typedef struct group {
   uint8_t *var; size_t var_cap, var_len;
   struct worker *w;
   uint64_t deferred, grows;   /* fibers put off to a later batch; lane re-allocations */
+  bool want_grow;             /* the last batch had to leave many fibers behind: take a larger slab before the next one */
 } group;
 
 typedef struct worker {
@@ -388,11 +389,22 @@ ef_aln aln_from_ops(ef_task *T, const uint8_t *ops, int n, const char *est, cons
 }
 
 /* ---- batching -------------------------------------------------------------------------------------------- */
+#define LANE_MAX_BYTES ((size_t)32 << 20)
 static void gather(group *g) {
   g->arena_len = 0; g->njobs = 0; g->var_len = 0;
+  /* Reads with thousands of candidate alignments (mRNAs) fill a lane with a handful of fibers; batches of a handful of
+   * fibers keep neither the engine nor the workers busy.  When a batch had to defer more than a quarter of the waiting
+   * fibers, the lane doubles (up to 32 MB per buffer) before the next batch is gathered. */
+  if (g->want_grow) {
+    g->want_grow = false;
+    if (g->arena_cap < LANE_MAX_BYTES && !getenv("EF_STAGING_KB"))
+      lane_grow(g, MIN2(g->arena_cap * 2, LANE_MAX_BYTES), MIN2(g->jobs_cap * 2, 1 << 20), MIN2(g->var_cap * 2, LANE_MAX_BYTES));
+  }
+  int waiting_now = 0, deferred_now = 0;
   for (int k = 0; k < g->nfibers; ++k) {
     fiber *f = &g->fibers[k];
     if (f->state != F_WAITING) continue;
+    ++waiting_now;
     /* Back-pressure instead of growth: the lane keeps the size it was given at start-up; a fiber whose requests do not
      * fit any more waits for the next batch.  Only a single fiber that is larger than an EMPTY lane makes the engine
      * move the lane to a larger slab. */
@@ -408,7 +420,7 @@ static void gather(group *g) {
     }
     if (g->njobs > 0 && (g->arena_len + f->need_a > g->arena_cap || g->var_len + f->need_v > g->var_cap || (size_t)g->njobs + (size_t)f->nreq > (size_t)g->jobs_cap)) {
       f->submitted = false;
-      ++g->deferred;
+      ++g->deferred; ++deferred_now;
       continue;
     }
     f->submitted = true;
@@ -444,6 +456,7 @@ static void gather(group *g) {
       }
     }
   }
+  if (deferred_now * 4 > waiting_now) g->want_grow = true;
   if (g->njobs == 0) return;
   if (g->arena_len >= 0xfff00000u || g->var_len >= 0xfff00000u) {
     fprintf(stderr, "* FATAL est-fact: one batch exceeds 4 GiB; lower --fibers\n");

@@ -18,6 +18,8 @@ CONFIGS = {
                read_len=(300, 800), err=0.01, seed=1003),
     "C4": dict(genome=2_000_000, genes=8, exons=40, exon_len=(25, 300), intron_len=(80, 60000), reads=1_000_000,
                read_len=(300, 800), err=0.01, seed=1004, mrna_frac=0.2, mrna_len=(1000, 6000)),
+    "C5": dict(genome=320_000, genes=1, exons=200, exon_len=(100, 600), intron_len=(80, 2000), reads=500_000,
+               read_len=(10_000, 100_000), err=0.005, seed=1005, long_exons=(4, 5000, 17000)),
     # reduced C4 / C5 shapes for parity tests (multi-gene locus with long 3' UTR exons and mRNAs; titin-like long exons)
     "C4mini": dict(genome=400_000, genes=3, exons=25, exon_len=(25, 300), intron_len=(80, 15000), reads=400,
                    read_len=(300, 800), err=0.01, seed=1104, mrna_frac=0.3, mrna_len=(1000, 5000), utr_len=(500, 3000)),
