@@ -132,7 +132,7 @@ static int connect_path(const char *path) {
   struct sockaddr_un a;
   memset(&a, 0, sizeof a);
   a.sun_family = AF_UNIX;
-  snprintf(a.sun_path, sizeof a.sun_path, "%s", path);
+  { const size_t n = strlen(path); memcpy(a.sun_path, path, n < sizeof a.sun_path - 1 ? n : sizeof a.sun_path - 1); }
   if (connect(s, (struct sockaddr *)&a, sizeof a) != 0) { close(s); return -1; }
   return s;
 }

@@ -11,6 +11,15 @@
  */
 #include "ef.h"
 
+/* strcmp(pt, pat) == 0 for the two-letter windows the splice-site scans compare at every alignment column (a libc call per
+ * column was 7 % of the host profile): pt = {c0, c1, NUL}, pat = a NUL-terminated dinucleotide */
+static inline bool eq2(const char *pt, const char *pat) {
+  if (pt[0] != pat[0]) return false;
+  if (pt[0] == 0) return true;
+  if (pt[1] != pat[1]) return false;
+  return pt[1] == 0 || pat[2] == 0;
+}
+
 /* ---- Burset frequencies (getBursetFrequency :376-556, pinned by reference test/refine-intron_test.c:148-922) -- */
 static const struct { char d[3], a[3]; int f; } BURSET[] = {
   {"AA","AG",1},{"AA","AT",1},{"AA","GT",1},{"AC","CC",1},{"AG","AC",1},{"AG","AG",5},{"AG","CT",2},{"AG","GC",1},
@@ -77,7 +86,7 @@ static void find_AG_after_on_the_right(const gapaln *A, int init, int *cut_on_al
     while (A->gen[index] == '-') ++index;
     pt[1] = A->gen[index];
     pt[2] = 0;
-    stop = strcmp(pt, "AG") == 0;
+    stop = eq2(pt, "AG");
   }
   if (!stop) return;
   int cg = 0, ce = 0;
@@ -102,7 +111,7 @@ static void find_ACCEPTOR_before_on_the_left(const gapaln *A, int init, int *cut
     while (index >= 0 && A->gen[index] == '-') --index;
     pt[0] = index < 0 ? 0 : A->gen[index];
     pt[2] = 0;
-    if (strcmp(pt, acc) == 0) stop = true;
+    if (eq2(pt, acc)) stop = true;
   }
   if (!stop) return;
   int cg = 0, ce = 0;
@@ -124,7 +133,7 @@ static void find_ACCEPTOR_after_on_the_left(const gapaln *A, int init, int *gen_
     ++index;
     pt[1] = A->gen[index];
     pt[2] = 0;
-    if (strcmp(pt, acc) == 0) stop = true;
+    if (eq2(pt, acc)) stop = true;
   }
   if (stop) *gen_sub = index - A->is_on_align - 1;
 }
@@ -139,7 +148,7 @@ static void find_AG_before_on_the_right(const gapaln *A, int init, int *gen_sub)
     --index;
     pt[0] = A->gen[index];
     pt[2] = 0;
-    if (strcmp(pt, "AG") == 0) stop = true;
+    if (eq2(pt, "AG")) stop = true;
   }
   if (stop) *gen_sub = A->ie_on_align - index - 1;
 }

@@ -118,7 +118,7 @@ void ar_free_all(ef_arena *a) {
 
 static void buf_reserve(ef_buf *b, size_t extra) {
   if (b->len + extra + 1 <= b->cap) return;
-  size_t cap = b->cap ? b->cap * 2 : 256;
+  size_t cap = b->cap ? b->cap * 2 : 2048;      /* one EST's records are a few KB per file: start there, not at 256 bytes */
   while (cap < b->len + extra + 1) cap *= 2;
   b->p = realloc(b->p, cap);
   if (!b->p) { fprintf(stderr, "* FATAL est-fact: out of memory\n"); exit(1); }
