@@ -14,8 +14,8 @@
 // the only traffic between lanes is two boundary values and the genome code, by shuffle.  Scores are kept with a
 // +0x4000 bias per half so that every add is a plain 32-bit add (either pipe) and every max is unsigned.
 //   stored per row:  YL = L-1, VL = L, VG = G, YR = R-1 (R on the job's last row: that folds the free end gap in)
-// Direction bytes go to the warp's scratch slot as [lane][column][8 rows] = one 8-byte store per job per step and
-// stay L2/L1-resident for the traceback, which lanes 0 and 1 of the group walk for the two jobs.
+// Direction bytes go to the warp's scratch slot as [step][lane] x 16 bytes (8 rows of job A, 8 rows of job B): one coalesced
+// 512-byte store per warp-step; the traceback is walked by the whole group, both jobs together, a run at a time.
 #include "pc_device.cuh"
 #include <cstdlib>
 #define PC_GAP_MINB_DEFAULT 4
@@ -378,8 +378,6 @@ static void launch_cls(int cls, const PcDevBatch &B, int max_m, uint32_t *work, 
 // work: a device counter, zero at launch (the segment's otherwise unused hand-over counter)
 void pc_launch_gap_pairs(int cls, const PcDevBatch &B, int max_m, uint32_t *work, cudaStream_t s, int sm_count) {
   static const int variant = getenv("PC_GAP_MINB") ? atoi(getenv("PC_GAP_MINB")) : PC_GAP_MINB_DEFAULT;      /* experiments */
-  if (variant == 3) launch_cls<3>(cls, B, max_m, work, s, sm_count);
-  else if (variant == 5) launch_cls<5>(cls, B, max_m, work, s, sm_count);
-  else if (variant == 6) launch_cls<6>(cls, B, max_m, work, s, sm_count);
+  if (variant == 3) launch_cls<3>(cls, B, max_m, work, s, sm_count);      /* 3 CTAs/SM: what the kernel ran at before the store layout changed */
   else launch_cls<4>(cls, B, max_m, work, s, sm_count);
 }

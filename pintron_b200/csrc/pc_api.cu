@@ -18,6 +18,7 @@ static const bool g_prof = getenv("PC_PROFILE") != nullptr;
 #define PC_MULTI_STREAM_MAX ((size_t)1 << 18)        /* batches below this many jobs run their segments on side streams */
 static const bool g_serial = getenv("PC_SERIAL_SEGMENTS") != nullptr;      /* experiments: keep every batch on one stream */
 #define PC_POOL_MB_DEFAULT 320         /* scratch pool per stream (direction words, wavefront matrices); grows on demand */
+#define PC_PARTS_HOST_ORDER_MAX ((size_t)1 << 14)   /* merged batches below this are keyed and ordered by the submitting thread: no mid-batch read-back */
 #define PC_DEVICE_ORDER_MIN ((size_t)1 << 16)      /* batches from this size up are ordered on the device (k_order.cu) */
 /* PC_CAPTURE=<file>: every batch handed to pc_submit is appended to <file> (bench.py replays the job stream of a real
  * est-fact run as its device-resident workload).  Record = u32 njobs, u64 arena_bytes, jobs, arena. */
@@ -549,8 +550,8 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
   return 0;
 }
 
-static int check_jobs(pc_stream *st, const pc_job *jobs, int njobs, size_t arena_bytes, size_t var_out_bytes) {
-  const size_t glen = st->ctx->genome_len;
+static int check_jobs(const pc_ctx *c, const pc_job *jobs, int njobs, size_t arena_bytes, size_t var_out_bytes) {
+  const size_t glen = c->genome_len;
   for (int i = 0; i < njobs; ++i) {
     const pc_job &j = jobs[i];
     if ((size_t)j.a_off + j.a_len > arena_bytes) return fail(PC_E_ARG, "%s", "pc_submit: job string a outside the arena");
@@ -575,7 +576,7 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
   if (njobs == 0) return 0;
   double tp = g_prof ? now_s() : 0;
   CU(cudaSetDevice(st->ctx->device));
-  int rc = (size_t)njobs >= PC_DEVICE_ORDER_MIN ? 0 : check_jobs(st, jobs, njobs, arena_bytes, var_out_bytes);   /* large batches: checked by the key kernel */
+  int rc = (size_t)njobs >= PC_DEVICE_ORDER_MIN ? 0 : check_jobs(st->ctx, jobs, njobs, arena_bytes, var_out_bytes);   /* large batches: checked by the key kernel */
   if (rc) return rc;
   if (g_capture) {
     std::lock_guard<std::mutex> lk(g_capture_mu);
@@ -614,7 +615,7 @@ extern "C" int pc_submit_device(pc_stream *st, const uint8_t *d_arena, size_t ar
   if (njobs == 0) return 0;
   CU(cudaSetDevice(st->ctx->device));
   /* no host copy of the jobs: validated, keyed and ordered on the device whatever the size (the engine's path) */
-  int rc = ((size_t)njobs >= PC_DEVICE_ORDER_MIN || !h_jobs) ? 0 : check_jobs(st, h_jobs, njobs, arena_bytes, var_out_bytes);
+  int rc = ((size_t)njobs >= PC_DEVICE_ORDER_MIN || !h_jobs) ? 0 : check_jobs(st->ctx, h_jobs, njobs, arena_bytes, var_out_bytes);
   if (rc) return rc;
   st->pend.merged.clear();
   rc = launch_selected(st, st->ctx, h_jobs, nullptr, (size_t)njobs, d_arena, d_jobs, d_res, d_var_out, arena_bytes, var_out_bytes, h_jobs == nullptr);
@@ -684,8 +685,21 @@ extern "C" int pc_submit_parts(pc_stream *st, pc_ctx *genome_ctx, const pc_part 
   tab[3 * np] = (uint32_t)nj;
   CU(cudaMemcpyAsync(st->d_parts.p, tab, 4 * (3 * np + 1), cudaMemcpyHostToDevice, st->s));
   pc_rebase_jobs((pc_job *)st->jobs.p, (int)nj, (const uint32_t *)st->d_parts.p, (int)np, st->s, c->sm_count);
-  int rc = launch_selected(st, c, nullptr, nullptr, nj, (const uint8_t *)st->arena.p, (const pc_job *)st->jobs.p, (int32_t *)st->res.p,
-                           (uint8_t *)st->var.p, na, nv, true);
+  // Small merged batches (a few lanes of a few hundred fibers: most of what the host sends, and all of it when a handful of
+  // long reads are the only ones left) are validated, keyed and ordered right here from the lanes' own job arrays: the
+  // device ordering path costs three launches, a read-back of the segment table and a synchronisation in mid-batch.
+  const pc_job *h_jobs = nullptr;
+  if (nj < PC_PARTS_HOST_ORDER_MAX) {
+    P.merged.resize(nj);
+    for (const Pending::Part &q : P.parts) {
+      memcpy(P.merged.data() + q.j_base, q.p.jobs, sizeof(pc_job) * (size_t)q.p.njobs);
+      const int bad = check_jobs(c, q.p.jobs, q.p.njobs, q.p.arena_bytes, q.p.var_out_bytes);       // offsets are still lane-relative here
+      if (bad) { P.parts.clear(); P.merged.clear(); cudaStreamSynchronize(st->s); return bad; }
+    }
+    h_jobs = P.merged.data();
+  }
+  int rc = launch_selected(st, c, h_jobs, nullptr, nj, (const uint8_t *)st->arena.p, (const pc_job *)st->jobs.p, (int32_t *)st->res.p,
+                           (uint8_t *)st->var.p, na, nv, h_jobs == nullptr);
   if (rc) { P.parts.clear(); return rc; }
   P.active = true; P.device_mode = true; P.jobs = nullptr; P.njobs = (int)nj; P.res = nullptr; P.var_out = nullptr;
   P.var_out_bytes = nv; P.d_arena = (const uint8_t *)st->arena.p; P.d_jobs = (const pc_job *)st->jobs.p;
@@ -719,7 +733,8 @@ extern "C" int pc_stream_sync(pc_stream *st) {
   // Jobs whose scratch did not fit their warp's pool slot are re-run with fewer warps (= larger slots: the launchers
   // give exactly max_warps warps a slot); the pool itself grows only when a single job needs more than all of it.
   const pc_job *h_jobs = P.jobs;
-  if (!P.parts.empty()) {           // merged batch: the host copy of the jobs is only put together now that it is needed
+  if (!P.parts.empty() && P.merged.size() == (size_t)P.njobs) h_jobs = P.merged.data();      // small merged batch: copy already there
+  else if (!P.parts.empty()) {      // merged batch: the host copy of the jobs is only put together now that it is needed
     P.merged.resize((size_t)P.njobs);     // (lengths, op and parameters only: the offsets stay un-rebased and are not read)
     for (const Pending::Part &q : P.parts) memcpy(P.merged.data() + q.j_base, q.p.jobs, sizeof(pc_job) * (size_t)q.p.njobs);
     h_jobs = P.merged.data();

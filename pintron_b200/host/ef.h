@@ -142,6 +142,10 @@ static inline ef_str S_(const char *p, int len) { ef_str s = {p, len < 0 ? 0 : l
 static inline ef_str SZ_(const char *p, int len) { ef_str s = {p, len < 0 ? 0 : len, false, 0, true}; return s; }   /* t[len] reads as NUL */
 int dp_push(int op, ef_str a, ef_str b, int p0, int p1, int p2, int out_cap);
 void dp_wait(void);
+/* body(T, k, user) for k = 0 .. n-1, as child fibers whose DP round trips overlap.  The iterations must touch disjoint data
+ * (they share T and its arena cooperatively: same thread); the caller continues when all of them have returned. */
+typedef void (*ef_par_fn)(ef_task *T, int k, void *user);
+void dp_parallel_for(ef_task *T, int n, ef_par_fn body, void *user);
 const int32_t *dp_res(int handle);
 const uint8_t *dp_var(int handle);
 
@@ -187,6 +191,7 @@ uint64_t ef_task_ticks(const ef_task *T);   /* ticks this task's code has run so
 enum { EF_PH_OTHER = 0, EF_PH_SEED, EF_PH_MEG, EF_PH_EMBED, EF_PH_CAND, EF_PH_FILTER, EF_PH_INTRON, EF_PH_REFINE, EF_PH_SMALLEX, EF_PH_OUTPUT, EF_PH_COUNT };
 int ef_phase(int ph);                       /* returns the previous phase */
 const double *sched_phase_seconds(void);
+const uint64_t *sched_phase_yields(uint64_t *max_per_est);   /* engine round trips (dp_wait) per phase; the longest chain of one EST */
 
 /* ---- scheduler entry ------------------------------------------------------------------------------------ */
 typedef struct ef_job_result {          /* per input EST, filled by the workers */

@@ -611,6 +611,15 @@ static void candidate_phases(ef_task *T, const ef_seq *est, ef_fzlist *cand, ef_
   }
 }
 
+typedef struct par_fz { const ef_seq *est; ef_fzlist *L; } par_fz;
+static void refine_introns_of(ef_task *T, int k, void *user) {
+  const par_fz *P = user;
+  ef_fz *z = P->L->v[k];
+  if (z->n == 0) return;
+  for (int i = 0; i + 1 < z->n; ++i) refine_intron(T, P->est, &z->f[i], &z->f[i + 1], i == 0);
+  if (z->n > 1 && z->f[0].es == z->f[1].es) fz_remove(z, 0);
+}
+
 ef_fzlist *est_factorizations(ef_task *T, const ef_seq *est, ef_meg *M, bool *timed_out) {
   const ef_config *cfg = T->cfg;
   const char *g = T->gen->seq;
@@ -670,12 +679,7 @@ ef_fzlist *est_factorizations(ef_task *T, const ef_seq *est, ef_meg *M, bool *ti
   if (cfg->max_number_of_factorizations != 0 && L->n > cfg->max_number_of_factorizations) L->n = 0;
   ef_phase(EF_PH_INTRON);
   /* splice-site refinement, intron by intron (the donor of intron k+1 is the acceptor refined by intron k) */
-  for (int k = 0; k < L->n; ++k) {
-    ef_fz *z = L->v[k];
-    if (z->n == 0) continue;
-    for (int i = 0; i + 1 < z->n; ++i) refine_intron(T, est, &z->f[i], &z->f[i + 1], i == 0);
-    if (z->n > 1 && z->f[0].es == z->f[1].es) fz_remove(z, 0);
-  }
+  { par_fz P = {est, L}; dp_parallel_for(T, L->n, refine_introns_of, &P); }      /* factorizations are independent of each other */
   for (int k = 0; k < L->n; ++k) {
     ef_fz *z = L->v[k];
     correct_tail(z, g, T->gen->len, est->orig, est->len);

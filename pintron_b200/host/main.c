@@ -351,6 +351,11 @@ int main(int argc, char **argv) {
     fprintf(stderr, "* INFO  per-EST code by phase (s):");
     for (int i = 0; i < EF_PH_COUNT; ++i) fprintf(stderr, " %s %.3f", nm[i], ph[i]);
     fprintf(stderr, "\n");
+    uint64_t ymax = 0;
+    const uint64_t *py = sched_phase_yields(&ymax);
+    fprintf(stderr, "* INFO  engine round trips by phase:");
+    for (int i = 0; i < EF_PH_COUNT; ++i) if (py[i]) fprintf(stderr, " %s %llu", nm[i], (unsigned long long)py[i]);
+    fprintf(stderr, "; longest chain of one EST: %llu\n", (unsigned long long)ymax);
   }
   uint64_t h2d, d2h;
   sched_bytes(&h2d, &d2h);

@@ -130,14 +130,18 @@ static bool analyze_small_exon(ef_task *T, const ef_seq *est, ef_fz *z, int c) {
   return true;
 }
 
-static void remove_false_small_exons(ef_task *T, const ef_seq *est, ef_fzlist *L) {
-  for (int k = 0; k < L->n; ++k) {
-    ef_fz *z = L->v[k];
-    /* after a removal the exon before the removed one is examined again against the same successor */
-    for (int c = 0; c < z->n;) {
-      if (analyze_small_exon(T, est, z, c)) --c; else ++c;
-    }
+typedef struct par_fz { const ef_seq *est; ef_fzlist *L; } par_fz;      /* loops over factorizations: each iteration touches its own only */
+static void false_small_exons_of(ef_task *T, int k, void *user) {
+  const par_fz *P = user;
+  ef_fz *z = P->L->v[k];
+  /* after a removal the exon before the removed one is examined again against the same successor */
+  for (int c = 0; c < z->n;) {
+    if (analyze_small_exon(T, P->est, z, c)) --c; else ++c;
   }
+}
+static void remove_false_small_exons(ef_task *T, const ef_seq *est, ef_fzlist *L) {
+  par_fz P = {est, L};
+  dp_parallel_for(T, L->n, false_small_exons_of, &P);
 }
 
 static bool canonical_intron(const char *g, size_t s, size_t e) {
@@ -348,29 +352,39 @@ static bool small_exon_between(ef_task *T, const ef_seq *est, ef_fz *z, int i) {
   return true;
 }
 
-static void search_new_small_exons(ef_task *T, const ef_seq *est, ef_fzlist *L) {
-  for (int k = 0; k < L->n; ++k) {
-    ef_fz *z = L->v[k];
-    if (z->n == 0) continue;
-    int first = 0;
-    if (z->f[0].es > LB_SMALL_EXON) {
-      const int before = z->n;
-      small_exon_at_prefix(T, est, z);
-      first = z->n - before;                /* the old first exon moved to index 1 when a new one was put in front */
-    }
-    for (int i = first; i + 1 < z->n;) {
-      if (small_exon_between(T, est, z, i)) i += 2; else ++i;     /* the inserted exon is not examined */
-    }
+static void new_small_exons_of(ef_task *T, int k, void *user) {
+  const par_fz *P = user;
+  const ef_seq *est = P->est;
+  ef_fz *z = P->L->v[k];
+  if (z->n == 0) return;
+  int first = 0;
+  if (z->f[0].es > LB_SMALL_EXON) {
+    const int before = z->n;
+    small_exon_at_prefix(T, est, z);
+    first = z->n - before;                /* the old first exon moved to index 1 when a new one was put in front */
   }
+  for (int i = first; i + 1 < z->n;) {
+    if (small_exon_between(T, est, z, i)) i += 2; else ++i;     /* the inserted exon is not examined */
+  }
+}
+static void search_new_small_exons(ef_task *T, const ef_seq *est, ef_fzlist *L) {
+  par_fz P = {est, L};
+  dp_parallel_for(T, L->n, new_small_exons_of, &P);
+}
+
+static void clean_one(ef_task *T, int k, void *user) {
+  const par_fz *P = user;
+  ef_fz *z = P->L->v[k];
+  clean_noisy_exons(T, z, T->gen->seq, P->est->orig);
+  clean_external_exons(T, z, T->gen->seq, P->est->orig);
 }
 
 /* clean_factorizations :909-946 — the noisy / external exon cleaning again, this time against the ORIGINAL EST bytes */
 static void clean_all(ef_task *T, const ef_seq *est, ef_fzlist *L) {
   ef_fzlist out = {0};
-  for (int k = 0; k < L->n; ++k) {
+  { par_fz P = {est, L}; dp_parallel_for(T, L->n, clean_one, &P); }      /* the cleaning is per factorization ... */
+  for (int k = 0; k < L->n; ++k) {                                       /* ... the containment test goes in list order */
     ef_fz *z = L->v[k];
-    clean_noisy_exons(T, z, T->gen->seq, est->orig);
-    clean_external_exons(T, z, T->gen->seq, est->orig);
     if (z->n == 0) continue;
     add_if_not_exists(T, z, &out);
   }

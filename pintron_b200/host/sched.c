@@ -167,7 +167,7 @@ void buf_ints(ef_buf *b, const char *open, const int *v, int n, char sep, const 
 void buf_free(ef_buf *b) { free(b->p); b->p = NULL; b->len = b->cap = 0; }
 
 /* ---- fibers ---------------------------------------------------------------------------------------- */
-enum { F_FREE = 0, F_RUNNABLE, F_WAITING, F_DONE };
+enum { F_FREE = 0, F_RUNNABLE, F_WAITING, F_DONE, F_JOINING };      /* JOINING: waits for the child fibers of dp_parallel_for */
 
 typedef struct ef_req { int op; ef_str a, b; int p0, p1, p2, out_cap; } ef_req;
 
@@ -186,6 +186,11 @@ typedef struct fiber {
   size_t need_a, need_v;    /* staging bytes of the pending requests (valid while need_valid) */
   bool need_valid;
   bool submitted;           /* its requests are part of the batch in flight (false: deferred to the next one) */
+  uint64_t yields;          /* round trips to the engine of the EST on this fiber */
+  /* child fibers (dp_parallel_for): a child runs one iteration of its parent's loop on the parent's task */
+  struct fiber *parent;
+  int pending_children;
+  ef_par_fn par_fn; void *par_user; int par_k; ef_task *par_T;
   struct group *grp;
 } fiber;
 
@@ -193,7 +198,9 @@ typedef struct group {
   ef_conn *conn;              /* the engine session of this thread's GPU */
   int lane_k;                 /* which of the session's lanes is ours */
   fiber *fibers;
-  int nfibers;
+  int nfibers;                /* slots that take ESTs; slots [nfibers, nslots) are child fibers, started by dp_parallel_for only */
+  int nslots;
+  bool rerun;                 /* a fiber behind the cursor of the current pass became runnable */
   bool pending;
   /* batch buffers = the lane's slab in the engine's pinned (shared) memory; refreshed by lane_refresh */
   uint8_t *arena; size_t arena_cap, arena_len;
@@ -235,6 +242,9 @@ static __thread int tl_phase;
 static __thread uint64_t tl_mark;
 static __thread uint64_t tl_phase_s[EF_PH_COUNT];      /* ticks */
 static double g_phase_s[EF_PH_COUNT];
+static __thread uint64_t tl_phase_yields[EF_PH_COUNT];      /* dp_wait round trips per phase */
+static uint64_t g_phase_yields[EF_PH_COUNT], g_max_yields;
+static __thread uint64_t tl_max_yields;
 static inline void phase_account(void) {
   const uint64_t t = ef_ticks();
   tl_phase_s[tl_phase] += t - tl_mark;
@@ -242,6 +252,7 @@ static inline void phase_account(void) {
 }
 int ef_phase(int ph) { phase_account(); const int old = tl_phase; tl_phase = ph; return old; }
 const double *sched_phase_seconds(void) { return g_phase_s; }
+const uint64_t *sched_phase_yields(uint64_t *max_per_est) { if (max_per_est) *max_per_est = g_max_yields; return g_phase_yields; }
 
 /* the group's view of its lane: pointers into the (shared, pinned) segment that holds the slab */
 static void lane_refresh(group *g) {
@@ -279,7 +290,45 @@ static void fiber_entry(void) {
   __builtin_unreachable();
 }
 
+static void fiber_prepare_stack(fiber *f, void (*entry)(void));
 static void fiber_start(worker *w, group *g, fiber *f, size_t index) {
+  fiber_prepare_stack(f, fiber_entry);
+  f->index = index;
+  f->yields = 0;
+  f->state = F_RUNNABLE;
+  f->nreq = 0;
+  f->has_results = false;
+  f->grp = g;
+  f->parent = NULL; f->pending_children = 0;
+  ar_reset(&f->task.ar);
+  f->task.cfg = w->cfg;
+  f->task.gen = w->gen;
+}
+
+/* ---- parallel loops over child fibers ----------------------------------------------------------------------------
+ * A read with many candidate factorizations refines them one after the other in the reference, and every refinement is a
+ * chain of dependent DP calls: on the device that is thousands of sequential round trips for ONE read (11 879 for the
+ * worst mRNA of the C4 sample) while the rest of the machine waits.  Iterations that touch disjoint data run here as
+ * child fibers of the same group, so their round trips overlap; the iteration bodies themselves are unchanged and the
+ * result does not depend on the interleaving.  Without a free child slot the iteration simply runs inline. */
+static void child_entry(void) {
+  fiber *f = tl_fiber;
+  worker *w = tl_worker;
+  tl_mark = ef_ticks();
+  f->par_fn(f->par_T, f->par_k, f->par_user);
+  phase_account();
+  fiber *p = f->parent;
+  if (--p->pending_children == 0 && p->state == F_JOINING) { p->state = F_RUNNABLE; p->grp->rerun = true; }
+  f->state = F_DONE;
+#if EF_FAST_SWITCH
+  ctx_switch(&f->sp, w->main_sp);
+#else
+  swapcontext(&f->ctx, &w->main_ctx);
+#endif
+  __builtin_unreachable();
+}
+
+static void fiber_prepare_stack(fiber *f, void (*entry)(void)) {
   if (!f->stack) {
     f->stack = mmap(NULL, FIBER_STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
     if (f->stack == MAP_FAILED) { perror("mmap fiber stack"); exit(1); }
@@ -288,8 +337,8 @@ static void fiber_start(worker *w, group *g, fiber *f, size_t index) {
 #if EF_FAST_SWITCH
   {
     uintptr_t *sp = (uintptr_t *)(((uintptr_t)f->stack + FIBER_STACK) & ~(uintptr_t)15);
-    *--sp = 0;                          /* the return address fiber_entry never uses (keeps the ABI stack alignment) */
-    *--sp = (uintptr_t)fiber_entry;     /* where the first switch "returns" to */
+    *--sp = 0;                          /* the return address the entry never uses (keeps the ABI stack alignment) */
+    *--sp = (uintptr_t)entry;           /* where the first switch "returns" to */
     for (int r = 0; r < 6; ++r) *--sp = 0;   /* rbp rbx r12 r13 r14 r15 */
     f->sp = sp;
   }
@@ -298,16 +347,41 @@ static void fiber_start(worker *w, group *g, fiber *f, size_t index) {
   f->ctx.uc_stack.ss_sp = f->stack;
   f->ctx.uc_stack.ss_size = FIBER_STACK;
   f->ctx.uc_link = NULL;
-  makecontext(&f->ctx, fiber_entry, 0);
+  makecontext(&f->ctx, entry, 0);
 #endif
-  f->index = index;
-  f->state = F_RUNNABLE;
-  f->nreq = 0;
-  f->has_results = false;
-  f->grp = g;
-  ar_reset(&f->task.ar);
-  f->task.cfg = w->cfg;
-  f->task.gen = w->gen;
+}
+
+void dp_parallel_for(ef_task *T, int n, ef_par_fn body, void *user) {
+  fiber *f = tl_fiber;
+  group *g = f->grp;
+  if (f->nreq && !f->has_results) dp_wait();                 /* nothing of the caller's may be in flight while it joins */
+  int next_slot = g->nfibers;
+  for (int k = 0; k < n; ++k) {
+    fiber *c = NULL;
+    if (n > 1)
+      for (; next_slot < g->nslots; ++next_slot)
+        if (g->fibers[next_slot].state == F_FREE) { c = &g->fibers[next_slot++]; break; }
+    if (!c) { body(T, k, user); continue; }                  /* no child slot left (or a single iteration): inline */
+    fiber_prepare_stack(c, child_entry);
+    c->index = f->index; c->yields = 0; c->nreq = 0; c->has_results = false; c->grp = g;
+    c->task.cfg = T->cfg; c->task.gen = T->gen;              /* dp_push looks at these; everything else goes through the parent's T */
+    c->parent = f; c->pending_children = 0; c->par_fn = body; c->par_user = user; c->par_k = k; c->par_T = T;
+    c->phase = tl_phase;
+    c->state = F_RUNNABLE;
+    ++f->pending_children;
+  }
+  if (f->pending_children == 0) return;
+  f->state = F_JOINING;
+  phase_account();
+  f->task.run_ticks += tl_mark - f->task.run_mark;
+  f->phase = tl_phase;
+#if EF_FAST_SWITCH
+  ctx_switch(&f->sp, tl_worker->main_sp);
+#else
+  swapcontext(&f->ctx, &tl_worker->main_ctx);
+#endif
+  tl_phase = f->phase; tl_mark = ef_ticks();
+  f->task.run_mark = tl_mark;
 }
 
 int dp_push(int op, ef_str a, ef_str b, int p0, int p1, int p2, int out_cap) {
@@ -331,6 +405,8 @@ void dp_wait(void) {
   f->state = F_WAITING;
   f->need_valid = false;
   phase_account();
+  ++tl_phase_yields[tl_phase];
+  if (++f->yields > tl_max_yields) tl_max_yields = f->yields;
   f->task.run_ticks += tl_mark - f->task.run_mark;
   f->phase = tl_phase;
 #if EF_FAST_SWITCH
@@ -401,7 +477,7 @@ static void gather(group *g) {
       lane_grow(g, MIN2(g->arena_cap * 2, LANE_MAX_BYTES), MIN2(g->jobs_cap * 2, 1 << 20), MIN2(g->var_cap * 2, LANE_MAX_BYTES));
   }
   int waiting_now = 0, deferred_now = 0;
-  for (int k = 0; k < g->nfibers; ++k) {
+  for (int k = 0; k < g->nslots; ++k) {
     fiber *f = &g->fibers[k];
     if (f->state != F_WAITING) continue;
     ++waiting_now;
@@ -476,14 +552,32 @@ static bool run_group(worker *w, group *g) {
     }
     w->gpu_wait += ef_now() - t0;
     g->pending = false;
-    for (int k = 0; k < g->nfibers; ++k)
+    for (int k = 0; k < g->nslots; ++k)
       if (g->fibers[k].state == F_WAITING && g->fibers[k].submitted) { g->fibers[k].state = F_RUNNABLE; g->fibers[k].has_results = true; }
   }
   bool any = false;
   int started_now = 0;
   const double tf0 = ef_now();
-  for (int k = 0; k < g->nfibers; ++k) {
+again:
+  g->rerun = false;
+  any = false;
+  for (int k = 0; k < g->nslots; ++k) {
     fiber *f = &g->fibers[k];
+    if (k >= g->nfibers) {                      /* child slots: run when runnable, never take a new EST */
+      if (f->state == F_RUNNABLE) {
+        tl_fiber = f;
+        tl_phase = f->phase;
+#if EF_FAST_SWITCH
+        ctx_switch(&w->main_sp, f->sp);
+#else
+        swapcontext(&w->main_ctx, &f->ctx);
+#endif
+        tl_fiber = NULL;
+      }
+      if (f->state == F_DONE) f->state = F_FREE;
+      if (f->state == F_WAITING) any = true;
+      continue;
+    }
     for (;;) {
       if (f->state == F_FREE || f->state == F_DONE) {
         if (f->state == F_DONE) { --w->inflight; f->state = F_FREE; }
@@ -510,6 +604,7 @@ static bool run_group(worker *w, group *g) {
     }
     if (f->state == F_WAITING) any = true;
   }
+  if (g->rerun) goto again;                     /* a parent whose last child just finished sits behind the cursor */
   const double tf1 = ef_now();
   w->t_fibers += tf1 - tf0;
   if (!any) return false;
@@ -554,7 +649,8 @@ static void *worker_main(void *arg) {
   g_t_fibers += w->t_fibers; g_t_gather += w->t_gather; g_t_submit += w->t_submit;
   g_t_init += tw1 - tw0; g_t_fini += ef_now() - tw2;
   g_t_end_sum += tw2; if (g_t_end_min == 0 || tw2 < g_t_end_min) g_t_end_min = tw2;
-  for (int i = 0; i < EF_PH_COUNT; ++i) g_phase_s[i] += ef_ticks_to_s(tl_phase_s[i]);
+  for (int i = 0; i < EF_PH_COUNT; ++i) { g_phase_s[i] += ef_ticks_to_s(tl_phase_s[i]); g_phase_yields[i] += tl_phase_yields[i]; }
+  if (tl_max_yields > g_max_yields) g_max_yields = tl_max_yields;
   pthread_mutex_unlock(&g_stat_mu);
   return NULL;
 }
@@ -649,7 +745,7 @@ void sched_prepare(const ef_config *cfg, const ef_seq *gen) {
   const size_t lim = va_limit();
   if (lim) {
     mallopt(M_ARENA_MAX, 2);
-    const size_t budget = lim / 3 / FIBER_STACK;               /* fibers in total */
+    const size_t budget = lim / 3 / FIBER_STACK * 2 / 3;       /* EST fibers in total (child fibers add half as many again) */
     if ((size_t)per_group * 2 * (size_t)nthreads > budget) per_group = (int)MAX2((size_t)8, budget / (2 * (size_t)nthreads));
   }
   g_prep.nthreads = nthreads; g_prep.per_group = per_group;
@@ -688,7 +784,8 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_next_f
       w->g[k].conn = g_prep.conns[i % nuse];
       w->g[k].lane_k = 2 * (i / nuse) + k;
       w->g[k].nfibers = per_group;
-      w->g[k].fibers = calloc((size_t)per_group, sizeof(fiber));
+      w->g[k].nslots = per_group + MAX2(32, per_group / 2);       /* child fibers of dp_parallel_for */
+      w->g[k].fibers = calloc((size_t)w->g[k].nslots, sizeof(fiber));
     }
     if (pthread_create(&w->th, NULL, worker_main, w)) { perror("pthread_create"); return 1; }
   }

@@ -22,7 +22,7 @@ open(os.path.join(work, "genomic.txt"), "wb").write(Synth(wl, reads=1).genome_fa
 open(os.path.join(work, "ests.txt"), "wb").write(ests_fasta_parallel(wl, reads, 0, reads, procs=max(1, (os.cpu_count() or 2) - 1)))
 print(f"probe: {wl} x {reads} reads in {work}, {os.cpu_count()} cores", flush=True)
 exe = os.path.join(ROOT, "pintron_b200", "bin", "est-fact")
-KEEP = ("scheduler:", "thread-seconds", "lane batches", "engine (", "per-EST code by phase", "@Timer Total", "@Timer IO", "device ms per op", "pc profile", "timeline")
+KEEP = ("scheduler:", "thread-seconds", "lane batches", "engine (", "per-EST code by phase", "@Timer Total", "@Timer IO", "device ms per op", "pc profile", "timeline", "round trips")
 
 
 def run(tag, args, env):
