@@ -50,8 +50,13 @@ enum pc_op {
 
 enum pc_flags {
   PC_B_IN_GENOME = 1u,  /* b_off/b_len index the genome uploaded with pc_genome_upload, not the arena */
-  PC_B_NUL_AFTER = 2u   /* BORDERS: the byte after t reads as NUL (the reference passes a NUL-terminated copy of t,
+  PC_B_NUL_AFTER = 2u,  /* BORDERS: the byte after t reads as NUL (the reference passes a NUL-terminated copy of t,
                            src/est-factorizations.c:1490), whatever follows it in the arena or the genome */
+  PC_KBAND_OK_ONLY = 4u /* KBAND: the caller reads only `ok`, as every call site of the reference does
+                           (src/est-factorizations.c:1876-1888, src/factorization-refinement.c:931).  When the distance is
+                           above k the reference's `edit` is the value of its band-restricted matrix, which only a banded
+                           sweep reproduces; with this flag res[2] then holds the true edit distance instead and the job
+                           never leaves the bit-parallel kernel */
 };
 
 enum pc_status {

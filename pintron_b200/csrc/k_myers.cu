@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(MY_TPB) k_myers(PcDevBatch B, uint32_t *slow_l
         else if (la == lb && d == 0) { res[0] = PC_OK; res[1] = 1; res[2] = 0; }                               // equal strings
         else if (k == 0) { res[0] = PC_OK; res[1] = 0; res[2] = 1; }
         else if (2ull * k + 1ull >= (unsigned long long)n || d <= k) { res[0] = PC_OK; res[1] = d <= k; res[2] = (int32_t)d; }   // full matrix, or inside the band: exact
+        else if (job->flags & PC_KBAND_OK_ONLY) { res[0] = PC_OK; res[1] = 0; res[2] = (int32_t)d; }             // not ok; the caller does not read `edit`
         else slow = true;                                                                                      // band-restricted value wanted
       }
     }

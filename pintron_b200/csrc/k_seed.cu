@@ -527,9 +527,14 @@ __global__ void k_lcs_finish(PcDevBatch B, const unsigned long long *best) {
 
 }  // namespace
 
-void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count) {
+void pc_launch_seed(const PcDevBatch &B, int max_len, cudaStream_t s, int sm_count) {
   const int ctas = (B.n + 3) / 4;
   int grid = ctas < sm_count * 8 ? ctas : sm_count * 8;
+  // a warp needs about 40 B of scratch per read position plus its candidate lists: as many warps as get a slot of that size
+  // (a segment of 6 kbp mRNAs launched at full occupancy had every job come back for a re-run)
+  const unsigned long long need = 56ull * (unsigned long long)(max_len > 0 ? max_len : 1) + 16384ull;
+  const unsigned long long fit = B.pool_cap / need;
+  if (fit < (unsigned long long)grid * 4ull) grid = (int)(fit / 4ull > 0 ? fit / 4ull : 1);
   if (B.max_warps > 0 && grid > (B.max_warps + 3) / 4) grid = (B.max_warps + 3) / 4;
   if (grid < 1) grid = 1;
   PcDevBatch C = B;

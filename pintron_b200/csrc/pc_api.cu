@@ -484,7 +484,7 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
     if (st->timers || g_prof) { e0 = get_event(st); e1 = get_event(st); cudaEventRecord(e0, ss); }
     const unsigned long long before = tl_pc_launches;
     if (op == PC_OP_SEED) {
-      pc_launch_seed(B, ss, c->sm_count);
+      pc_launch_seed(B, max_l2, ss, c->sm_count);
     } else if (op == PC_OP_LCS) {
       // [best slots | block prefix] in one device buffer; the prefix comes from the host copy of the jobs
       const size_t best_b = (8ull * B.n + 255u) & ~(size_t)255u, prefix_b = (4ull * (B.n + 1) + 255u) & ~(size_t)255u;

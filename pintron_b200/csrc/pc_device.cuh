@@ -67,6 +67,7 @@ __host__ __device__ inline int pc_job_class(const pc_job &j) {
     const uint32_t m = j.a_len < j.b_len ? j.a_len : j.b_len;
     return m <= 64 ? 0 : (m <= 128 ? 1 : (m <= 320 ? 2 : 3));
   }
+  if (j.op == PC_OP_SEED) return j.a_len <= 1024 ? 0 : (j.a_len <= 3072 ? 1 : 2);      /* scratch per warp grows with the read: long reads get larger slots */
   return 0;
 }
 /* cost class inside a segment, 0..63, larger = heavier (packed kernels: by the number of column steps, finely) */
@@ -155,7 +156,7 @@ void pc_lcs_prefix(const pc_job *d_jobs, const uint32_t *d_order, int n, int lcs
 void pc_launch_borders_chunked(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count);
 void pc_launch_borders_packed(int cls, const PcDevBatch &B, int tcap, cudaStream_t s, int sm_count);
 void pc_launch_gap_pairs(int cls, const PcDevBatch &B, int max_m, uint32_t *work, cudaStream_t s, int sm_count);
-void pc_launch_seed(const PcDevBatch &B, cudaStream_t s, int sm_count);
+void pc_launch_seed(const PcDevBatch &B, int max_len, cudaStream_t s, int sm_count);
 int pc_lcs_blocks(long long l1, int l2);
 int pc_launch_lcs(const PcDevBatch &B, unsigned long long *best, const uint32_t *d_blk_prefix, uint32_t total_blocks, int max_l2, uint32_t *work,
                   cudaStream_t s);

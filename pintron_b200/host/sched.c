@@ -513,6 +513,7 @@ static void gather(group *g) {
       if (r->a.len) memcpy(g->arena + g->arena_len, r->a.p, (size_t)r->a.len);
       g->arena_len += (size_t)r->a.len;
       if (r->b.nul_after) j->flags |= PC_B_NUL_AFTER;
+      if (r->op == PC_OP_KBAND) j->flags |= PC_KBAND_OK_ONLY;      /* clean_noisy_exons reads the boolean only, like the reference's call sites */
       if (r->b.in_genome) { j->flags |= PC_B_IN_GENOME; j->b_off = (uint32_t)r->b.gen_off; j->b_len = (uint32_t)r->b.len; }
       else {
         j->b_off = (uint32_t)g->arena_len; j->b_len = (uint32_t)r->b.len;

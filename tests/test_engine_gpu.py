@@ -227,3 +227,46 @@ def test_guard_bands_stay_intact(tmp_path):
     for case in ("test-AMBN", "test-CPB2", "test_gtf7"):
         d = tmp_path / case; d.mkdir()
         U.check_case(U.GPU_BIN, case, d, "--quiet", "--threads", "6", "--engine", "inproc", env=env)
+
+
+def test_kband_ok_only_flag_and_seed_size_classes(cu):
+    """PC_KBAND_OK_ONLY (what the est-fact host sets: the reference's call sites read the boolean only): same `ok` as the exact
+    form on every job, and identical (ok, edit) whenever ok.  SEED jobs of 300 nt to 7 kbp in one batch (three size classes,
+    scratch slots sized by the longest read of a class) == the port's vertex sets."""
+    import random
+    port = Port()
+    rnd = random.Random(4711)
+    g = Gen(4711)
+    b1, b2, cases = Batch(), Batch(), []
+    for it in range(3000):
+        ln = rnd.choice([20, 60, 64, 65, 100, 130, 200, 300, 320, 400])
+        a = g.rs(ln)
+        c = g.mutate(a, rnd.choice([0.0, 0.02, 0.05, 0.1, 0.3])) or b"A"
+        k = rnd.randint(0, 12)
+        b1.add(PC_OP.KBAND, a, c, p0=k)
+        b2.add(PC_OP.KBAND, a, c, p0=k)
+        cases.append((a, c, k))
+    b2.jobs = [(op, flags | 4, *rest) for (op, flags, *rest) in b2.jobs]
+    r1, _ = cu.run(b1)
+    r2, _ = cu.run(b2)
+    assert (r1[:, 0] == 0).all() and (r2[:, 0] == 0).all()
+    assert (r1[:, 1] == r2[:, 1]).all()
+    okm = r1[:, 1] != 0
+    assert (r1[okm, 2] == r2[okm, 2]).all()
+    for (a, c, k), r in list(zip(cases, r2))[:400]:
+        assert bool(r[1]) == port.kband(a, c, k)[0]
+    genome = g.genome(60000)
+    cu.genome_upload(genome, 15, 0.2)
+    b = Batch()
+    ests = []
+    for ln in (300, 800, 1024, 1025, 2000, 3072, 3073, 5000, 7000, 400, 6000):
+        off = rnd.randint(0, len(genome) - ln - 1)
+        e = g.mutate(genome[off:off + ln], 0.01)
+        ests.append(e)
+        b.add(PC_OP.SEED, e, p0=15, out_cap=8192)
+    res, var = cu.run(b)
+    _, jobs = b.arrays()
+    for e, r, j in zip(ests, res, jobs):
+        assert r[0] == 0, (len(e), list(r))
+        tri = var[j["out_off"]:j["out_off"] + 12 * r[1]].view(np.int32).reshape(-1, 3)
+        assert [tuple(map(int, x)) for x in tri] == port.seed(genome, e, 15, 0.2), len(e)
