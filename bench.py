@@ -162,6 +162,22 @@ class RefShards:
         assert all(r == 0 for r in rcs), rcs
         return time.perf_counter() - t0
 
+    def cells(self):
+        """DP cells the reference computes on these ESTs, per routine: one pass of oracle/_ref/est-fact-cells (the same
+        unmodified sources with counting interposers, oracle/ref_cells.c) over the shards; None when it is not built."""
+        exe = os.path.join(ROOT, "oracle", "_ref", "est-fact-cells")
+        if not os.path.exists(exe):
+            return None
+        procs = [subprocess.Popen([exe], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for d in self.dirs]
+        if any(p.wait() != 0 for p in procs):
+            return None
+        tot = {}
+        for d in self.dirs:
+            for k, v in json.load(open(os.path.join(d, "cells.json"))).items():
+                t = tot.setdefault(k, {"cells": 0, "calls": 0})
+                t["cells"] += v["cells"]; t["calls"] += v["calls"]
+        return tot
+
     def md5s(self):
         """md5 of the shard outputs concatenated in shard order (== the single run: ESTs are independent)."""
         out = {}
@@ -517,7 +533,7 @@ def main():
 
     if rank == 0:
         # ---- parity + CPU baseline: the reference on a bounded sample with every host core, its bytes against ours -------
-        cpu = parity = None
+        cpu = parity = cells_basis = None
         if not args.no_cpu_baseline:
             _log("reference on the host cores (cpu_baseline) and byte parity on the same ESTs")
             sh = RefShards(args.workload, args.ref_reads_per_core)
@@ -535,6 +551,30 @@ def main():
                 bad = [f for f in FILES if ours[f] != ref[f]]
                 parity = {"status": "identical" if not bad else "MISMATCH", "ests": sh.n, "files": FILES, "differing": bad,
                           "how": "md5 of our five output files (client of est-factd) == md5 of the reference's shard outputs concatenated"}
+                ref_cells = sh.cells()
+                if ref_cells:
+                    # the same ESTs through our host: the jobs it issues, counted with the same formulas
+                    cap = os.path.join(pd, "jobs.capture")
+                    est_fact(pd, "inproc", ("--no-aux-outputs",), env=dict(os.environ, PC_CAPTURE=cap))
+                    pa, pj, _, _ = replay.merge(cap)
+                    oc = replay.algorithmic_cells(pa, synth.genome, pj)
+                    oj = {nm: int((pj["op"] == i).sum()) for i, nm in enumerate(OP_NAMES)}
+                    oc["AFFIX"] = sum(oc.get(k, 0) for k in ("AFFIX", "SUFCUT", "PRECUT"))
+                    oj["AFFIX"] = sum(oj.get(k, 0) for k in ("AFFIX", "SUFCUT", "PRECUT"))
+                    cells_basis = {"ests": sh.n, "per_routine": {}, "how": "reference: oracle/_ref/est-fact-cells = the unmodified sources with counting "
+                                   "interposers on compute_alignment, K_band_edit_distance, edit_distance, compute_edit_distance, edit_distance_matrix, "
+                                   "compute_gap_alignment (oracle/ref_cells.c); ours: the captured job stream of est-fact on the same ESTs; AFFIX = "
+                                   "edit_distance_matrix callers (longest affix + prefix / suffix cuts); LCS is a static function in the reference "
+                                   "and is not counted"}
+                    for k, rv in ref_cells.items():
+                        ratio = oc.get(k, 0) / rv["cells"] if rv["cells"] else None
+                        cells_basis["per_routine"][k] = {"reference_cells": rv["cells"], "reference_calls": rv["calls"], "our_cells": oc.get(k, 0),
+                                                          "our_jobs": oj.get(k, 0), "ours_over_reference": ratio}
+                        for kk in ((k,) if k != "AFFIX" else ("AFFIX", "SUFCUT", "PRECUT")):
+                            if ratio and kk in per_kernel and "gcups" in per_kernel[kk]:
+                                per_kernel[kk]["gcups_reference_basis"] = per_kernel[kk]["gcups"] / ratio
+                    if roof.get("gcups") and cells_basis["per_routine"].get(dom, {}).get("ours_over_reference"):
+                        roof["gcups_reference_basis"] = roof["gcups"] / cells_basis["per_routine"][dom]["ours_over_reference"]
                 shutil.rmtree(pd, ignore_errors=True)
             sh.close()
         extra = {}
@@ -550,8 +590,10 @@ def main():
                            "lane_batches_per_step": n_records, "launches_per_step": launches_dev // args.steps, "jobs_per_op": jobs_per_op},
             "kernels": {"what": "the same jobs as ONE merged batch, per-op CUDA-event timers (single stream)", "ms_per_step": sum(ms_merged) / len(ms_merged),
                         "ests_per_sec": args.reads / (sum(ms_merged) / len(ms_merged) * 1e-3), "per_kernel": per_kernel,
-                        "gcups_basis": "cells of the jobs OUR host issues, counted with the reference's formulas (SURVEY.md §8(d)); the host issues some "
-                                       "DP calls speculatively (all four splice-shift variants), so EDIT counts more cells than the reference would compute"},
+                        "cells_basis": cells_basis,
+                        "gcups_basis": "gcups: cells of the jobs OUR host issues, counted with the reference's formulas (SURVEY.md §8(d)); the host issues some "
+                                       "DP calls speculatively (all four splice-shift variants), so EDIT counts more cells than the reference would compute; gcups_reference_basis: the same time, only the cells the "
+                                       "reference itself computes on these ESTs (cells_basis, measured on the parity sample)"},
             "roofline": roof, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e, "unit": "ESTs/s", "ms_per_step": ms_step_e2e,
                     "h2d_bytes_per_step": e2e_info.get("h2d"), "d2h_bytes_per_step": e2e_info.get("d2h"),

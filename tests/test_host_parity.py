@@ -214,3 +214,21 @@ def test_streaming_windows_and_back_pressure_keep_the_bytes(cpu_bin, tmp_path):
         d = tmp_path / case
         d.mkdir()
         U.check_case(cpu_bin, case, str(d), *extra, env=env)
+
+
+def test_counting_reference_is_the_reference(tmp_path):
+    """oracle/_ref/est-fact-cells (the reference sources as a PIC library + the counting interposers of oracle/ref_cells.c)
+    writes the reference's bytes and counts cells for every routine bench.py divides GCUPS from."""
+    exe = os.path.join(U.ROOT, "oracle", "_ref", "est-fact-cells")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/est-fact-cells not built (make -C oracle ref)")
+    import json
+    U.unpack("test-CPB2", str(tmp_path))
+    subprocess.run([exe], cwd=tmp_path, check=True, capture_output=True, timeout=600)
+    exp = json.load(open(os.path.join(U.GOLD, "test-CPB2", "expected.json")))
+    got = U.md5s(str(tmp_path))
+    assert all(got[f] == exp[f] for f in exp if f in got)
+    cells = json.load(open(tmp_path / "cells.json"))
+    assert set(cells) == {"ALIGN", "KBAND", "EDIT", "BORDERS", "GAP", "AFFIX"}
+    assert all(v["calls"] > 0 and v["cells"] > 0 for v in cells.values()), cells
+    assert cells["GAP"]["cells"] % 3 == 0
