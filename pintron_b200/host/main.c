@@ -19,7 +19,8 @@ typedef struct est_item {
   ef_seq fwd, rc;
   bool has_rc;
   ef_buf out[6];                  /* raw, processed-ests, megs, processed-megs, meg-edges, processed-megs-info */
-  _Atomic int done;               /* set by the worker when every buffer above is final */
+  _Atomic uint32_t done;          /* set by the worker when every buffer above is final (futex word) */
+  _Atomic uint32_t waited;        /* a writer sleeps on `done` */
   _Atomic int written;            /* writers that are through with this item (the last one frees its strings) */
 } est_item;
 enum { O_RAW = 0, O_PEST, O_MEGS, O_PMEGS, O_EDGES, O_INFO, O_COUNT };
@@ -34,6 +35,18 @@ enum { O_RAW = 0, O_PEST, O_MEGS, O_PMEGS, O_EDGES, O_INFO, O_COUNT };
 #define WIN_BYTES ((size_t)48 << 20)
 #define WIN_AHEAD 10
 #define MAX_WINDOWS ((size_t)1 << 22)
+/* Sleeping instead of polling (six writers polling every 100 us cost a good part of a core per process — eight processes
+ * of them on a 32-core box): a futex wait on a 32-bit word that changes whenever the condition may have become true;
+ * the 50 ms time-out is a safety net only. */
+#include <linux/futex.h>
+#include <sys/syscall.h>
+static void word_wait(_Atomic uint32_t *w, uint32_t seen) {
+  const struct timespec to = {0, 50000000};
+  syscall(SYS_futex, (uint32_t *)w, FUTEX_WAIT_PRIVATE, seen, &to, NULL, 0);
+}
+static void word_wake(_Atomic uint32_t *w) { syscall(SYS_futex, (uint32_t *)w, FUTEX_WAKE_PRIVATE, INT32_MAX, NULL, NULL, 0); }
+static void seq_bump(_Atomic uint32_t *w) { atomic_fetch_add(w, 1); word_wake(w); }
+
 typedef struct window {
   uint32_t n;
   est_item *items;
@@ -51,6 +64,8 @@ typedef struct run_ctx {
   _Atomic size_t n_written[O_COUNT];
   _Atomic int eof;
   _Atomic size_t n_records;
+  _Atomic uint32_t ready_seq;    /* bumped when a window becomes ready and at end of input */
+  _Atomic uint32_t written_seq;  /* bumped when a writer finishes a window */
   FILE *f[O_COUNT];
   double writer_busy[O_COUNT];
   int rc;
@@ -147,7 +162,8 @@ static void est_task(ef_task *T, size_t handle, void *user) {
   run_ctx *R = user;
   est_item *it = &R->win[handle >> WIN_BITS]->items[handle & (((size_t)1 << WIN_BITS) - 1)];
   est_task_body(T, R, it);
-  atomic_store_explicit(&it->done, 1, memory_order_release);
+  atomic_store(&it->done, 1);
+  if (atomic_load(&it->waited)) word_wake(&it->done);
 }
 
 static void est_task_body(ef_task *T, run_ctx *R, est_item *it) {
@@ -191,12 +207,13 @@ static void close_window(run_ctx *R, window *W) {
   R->win[w] = W;
   atomic_fetch_add(&R->n_records, W->n);
   atomic_store_explicit(&R->n_ready, w + 1, memory_order_release);
+  seq_bump(&R->ready_seq);
 }
 
 static void *reader_main(void *arg) {
   run_ctx *R = arg;
   ef_fasta *fa = ef_fasta_open("ests.txt");
-  if (!fa) { fprintf(stderr, "* FATAL File ests.txt not found! Terminating\n"); R->rc = 1; atomic_store(&R->eof, 1); return NULL; }
+  if (!fa) { fprintf(stderr, "* FATAL File ests.txt not found! Terminating\n"); R->rc = 1; atomic_store(&R->eof, 1); seq_bump(&R->ready_seq); return NULL; }
   window *W = NULL;
   size_t bytes = 0, cap = 0;
   ef_seq e;
@@ -216,16 +233,18 @@ static void *reader_main(void *arg) {
       W = NULL;
       /* stay at most WIN_AHEAD windows in front of the slowest writer */
       for (;;) {
+        const uint32_t seen = atomic_load(&R->written_seq);
         size_t slowest = (size_t)-1;
         for (int k = 0; k < O_COUNT; ++k) { const size_t v = atomic_load(&R->n_written[k]); if (v < slowest) slowest = v; }
         if (atomic_load(&R->n_ready) < slowest + win_ahead) break;
-        usleep(200);
+        word_wait(&R->written_seq, seen);
       }
     }
   }
   if (W) close_window(R, W);
   ef_fasta_close(fa);
   atomic_store(&R->eof, 1);
+  seq_bump(&R->ready_seq);
   return NULL;
 }
 
@@ -240,14 +259,20 @@ static void *writer_main(void *arg) {
   run_ctx *R = ((writer_arg *)arg)->R;
   const int k = ((writer_arg *)arg)->k;
   for (size_t w = 0;; ++w) {
-    while (w >= atomic_load_explicit(&R->n_ready, memory_order_acquire)) {
+    for (;;) {
+      const uint32_t seen = atomic_load(&R->ready_seq);
+      if (w < atomic_load_explicit(&R->n_ready, memory_order_acquire)) break;
       if (atomic_load(&R->eof) && w >= atomic_load(&R->n_ready)) return NULL;
-      usleep(200);
+      word_wait(&R->ready_seq, seen);
     }
     window *W = R->win[w];
     for (uint32_t i = 0; i < W->n; ++i) {
       est_item *it = &W->items[i];
-      while (!atomic_load_explicit(&it->done, memory_order_acquire)) usleep(100);
+      while (!atomic_load_explicit(&it->done, memory_order_acquire)) {
+        atomic_store(&it->waited, 1);
+        if (atomic_load(&it->done)) break;
+        word_wait(&it->done, 0);
+      }
       const double t0 = ef_now();
       ef_buf *b = &it->out[k];
       if (b->len) fwrite_unlocked(b->p, 1, b->len, R->f[k]);
@@ -257,6 +282,7 @@ static void *writer_main(void *arg) {
     }
     if (atomic_fetch_add(&W->writers_done, 1) == O_COUNT - 1) { free(W->items); W->items = NULL; }   /* the struct itself stays: late next_item calls read n */
     atomic_store(&R->n_written[k], w + 1);
+    seq_bump(&R->written_seq);
   }
 }
 
@@ -311,7 +337,11 @@ int main(int argc, char **argv) {
   if (pthread_create(&rth, NULL, reader_main, &R)) { perror("pthread_create"); return 1; }
   for (int k = 0; k < O_COUNT; ++k) { wa[k].R = &R; wa[k].k = k; if (pthread_create(&wth[k], NULL, writer_main, &wa[k])) { perror("pthread_create"); return 1; } }
   /* short inputs are known in full before the first window closes: they get fewer threads and fibers (sched_run) */
-  while (!atomic_load(&R.eof) && atomic_load(&R.n_ready) == 0) usleep(100);
+  for (;;) {
+    const uint32_t seen = atomic_load(&R.ready_seq);
+    if (atomic_load(&R.eof) || atomic_load(&R.n_ready) != 0) break;
+    word_wait(&R.ready_seq, seen);
+  }
   const size_t n_hint = atomic_load(&R.eof) ? atomic_load(&R.n_records) : SIZE_MAX;
   const double tl_ests = ef_now();
   const double t_alg0 = ef_now();
