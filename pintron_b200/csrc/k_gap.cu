@@ -18,6 +18,7 @@
 // 512-byte store per warp-step; the traceback is walked by the whole group, both jobs together, a run at a time.
 #include "pc_device.cuh"
 #include <cstdlib>
+#include <type_traits>
 #define PC_GAP_MINB_DEFAULT 4
 
 namespace {
@@ -273,14 +274,19 @@ __global__ void __launch_bounds__(128, MINB) k_gap_pairs(PcDevBatch B, int mcap,
     for (int r = 0; r < ROWS; ++r) { YL[r] = BIAS2 - ONE2; VL[r] = BIAS2; VG[r] = BIAS2; YR[r] = BIAS2 - subv[r]; }   // column 0: all planes 0
     uint32_t inYL = BIAS2 - ONE2, inYR = BIAS2 - ONE2, gcur = 0;
     uint32_t fL = BIAS2, fG = BIAS2, fR = BIAS2;          // packed final cells (n, m) of the two jobs
-    for (int s = 1; s <= steps; ++s) {
+    // One step of the wavefront.  `guarded` steps test whether the lane is inside its matrix; the steady state needs no
+    // test, and runs two steps a round with the L and G values of a row ping-ponging between two register sets (written in
+    // place they cost 16 register moves a step: the old value of a cell is still read after the new one exists).
+    uint32_t VL2[ROWS], VG2[ROWS];
+    const int capSA = k == laneA ? A.m + k : -1, capSB = k == laneB ? Bj.m + k : -1;     // the step in which this lane computes cell (n, m)
+    auto step = [&](auto guarded, const int s, const uint32_t (&VLi)[ROWS], const uint32_t (&VGi)[ROWS], uint32_t (&VLo)[ROWS], uint32_t (&VGo)[ROWS]) {
       const int j = s - k;
       const uint32_t dL0 = inYL, dR0 = inYR;              // (row 8k, column j-1)
       inYL = __shfl_up_sync(0xffffffffu, YL[ROWS - 1], 1, LANES);
       inYR = __shfl_up_sync(0xffffffffu, YR[ROWS - 1], 1, LANES);
       gcur = __shfl_up_sync(0xffffffffu, gcur, 1, LANES);
       if (k == 0) { inYL = BIAS2 - ONE2; inYR = BIAS2 - ONE2; gcur = codes[min(s, mmax)]; }
-      if (j >= 1 && j <= mmax && live && fits) {
+      if (!decltype(guarded)::value || (j >= 1 && j <= mmax && live && fits)) {
         const uint32_t g2 = __vminu2(gcur, TWO2);
         uint32_t dL = dL0, dR = dR0, upL = inYL, upR = inYR;
         uint32_t wa0 = 0, wa1 = 0, wb0 = 0, wb1 = 0;
@@ -295,11 +301,11 @@ __global__ void __launch_bounds__(128, MINB) k_gap_pairs(PcDevBatch B, int mcap,
           if (!pl) bits_a |= 1u; if (!ph) bits_b |= 1u;
           v = pc_vibmax_u16x2(v, YL[r], ph, pl);
           if (!pl) bits_a |= 2u; if (!ph) bits_b |= 2u;
-          const uint32_t llf = VL[r];
-          dL = YL[r]; VL[r] = v; YL[r] = v - ONE2; upL = YL[r];
+          const uint32_t llf = VLi[r];
+          dL = YL[r]; VLo[r] = v; YL[r] = v - ONE2; upL = YL[r];
           // G plane: stay in the gap, or enter it from L
-          const uint32_t glf = VG[r];
-          VG[r] = pc_vibmax_u16x2(glf, llf, ph, pl);
+          const uint32_t glf = VGi[r];
+          VGo[r] = pc_vibmax_u16x2(glf, llf, ph, pl);
           if (!pl) bits_a |= 4u; if (!ph) bits_b |= 4u;
           // R plane: diagonal, left (free on the job's last row), jump from G, up
           v = pc_vibmax_u16x2(dR + c2m, YR[r], ph, pl);
@@ -314,17 +320,30 @@ __global__ void __launch_bounds__(128, MINB) k_gap_pairs(PcDevBatch B, int mcap,
         }
         if (!(dbg & 2)) dirW[(size_t)s * 32 + lane] = make_uint4(wa0, wa1, wb0, wb1);
         else if ((wa0 ^ wb0 ^ wa1 ^ wb1) == 0x12345678u) fL = 0;
-        const bool capA = j == A.m && k == laneA, capB = j == Bj.m && k == laneB;
+        const bool capA = s == capSA, capB = s == capSB;
         if (capA | capB) {                                  // once per job: pick the row holding (n, m)
 #pragma unroll
           for (int r = 0; r < ROWS; ++r) {
             const uint32_t vr = YR[r] + subv[r];
-            if (capA && r == rowA) { fL = (fL & 0xffff0000u) | (VL[r] & 0xffffu); fG = (fG & 0xffff0000u) | (VG[r] & 0xffffu); fR = (fR & 0xffff0000u) | (vr & 0xffffu); }
-            if (capB && r == rowB) { fL = (fL & 0xffffu) | (VL[r] & 0xffff0000u); fG = (fG & 0xffffu) | (VG[r] & 0xffff0000u); fR = (fR & 0xffffu) | (vr & 0xffff0000u); }
+            if (capA && r == rowA) { fL = (fL & 0xffff0000u) | (VLo[r] & 0xffffu); fG = (fG & 0xffff0000u) | (VGo[r] & 0xffffu); fR = (fR & 0xffff0000u) | (vr & 0xffffu); }
+            if (capB && r == rowB) { fL = (fL & 0xffffu) | (VLo[r] & 0xffff0000u); fG = (fG & 0xffffu) | (VGo[r] & 0xffff0000u); fR = (fR & 0xffffu) | (vr & 0xffff0000u); }
           }
         }
       }
+    };
+    // lead-in (lanes joining the wavefront), steady state (every lane of the warp inside its matrix: no guard, two steps a
+    // round), lead-out
+    int s_hi = live ? mmax : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s_hi = min(s_hi, __shfl_xor_sync(0xffffffffu, s_hi, o));
+    if (steps == 0 || (dbg & 8)) s_hi = 0;
+    int s = 1;
+    for (; s <= steps && s < LANES; ++s) step(std::true_type{}, s, VL, VG, VL, VG);
+    for (; s + 1 <= s_hi; s += 2) {
+      step(std::false_type{}, s, VL, VG, VL2, VG2);
+      step(std::false_type{}, s + 1, VL2, VG2, VL, VG);
     }
+    for (; s <= steps; ++s) step(std::true_type{}, s, VL, VG, VL, VG);
     __syncwarp();
     // final cells to the tracing lanes (group lane 0 walks job A, group lane 1 job B)
     const int base = grp * LANES;
@@ -361,7 +380,7 @@ void launch_pairs(const PcDevBatch &B, int mcap, uint32_t *work, cudaStream_t s,
   if (grid < 1) grid = 1;
   PcDevBatch C = B;
   C.slots = (B.max_warps > 0 && B.max_warps < grid * 4) ? B.max_warps : grid * 4;
-  static const int dbg = getenv("PC_GAP_DBG") ? atoi(getenv("PC_GAP_DBG")) : 0;      /* timing experiments only: 1 = no traceback, 2 = no direction stores, 4 = no sweep */
+  static const int dbg = getenv("PC_GAP_DBG") ? atoi(getenv("PC_GAP_DBG")) : 0;      /* timing experiments only: 1 = no traceback, 2 = no direction stores, 4 = no sweep, 8 = guarded steps only */
   k_gap_pairs<LANES, MINB><<<grid, 128, sh, s>>>(C, mcap, work, dbg);
   PC_COUNT_LAUNCH(1);
 }

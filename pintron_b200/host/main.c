@@ -135,17 +135,19 @@ static bool compute_est_fact(ef_task *T, const run_ctx *R, est_item *it, const e
     timed_out = timed_out || ef_timeout_expired(T);
     const double t_comp1 = ef_now();
     const bool got = L && L->n > 0;
+    size_t meg_at = 0, meg_len = 0;
     if ((!timed_out || got) && R->cfg->aux_outputs) {
       buf_printf(&it->it_megs, "\n\n***********\n\n");
+      meg_at = it->it_megs.len;
       write_est_record(&it->it_megs, e);
       meg_write(&it->it_megs, M);
+      meg_len = it->it_megs.len - meg_at;
     }
     if (got) {
       if (R->cfg->aux_outputs) {
         buf_printf(&it->it_edges, ">%s\n", e->id);
         meg_write_edges(&it->it_edges, M);
-        write_est_record(&it->it_pmegs, e);
-        meg_write(&it->it_pmegs, M);
+        buf_write(&it->it_pmegs, it->it_megs.p + meg_at, meg_len);      /* processed-megs.txt: the same record and graph, formatted once */
       }
       buf_printf(&it->it_info, "%llu %llu %zu\n", (unsigned long long)((t_meg1 - t_meg0) * 1e6), (unsigned long long)((t_comp1 - t_meg1) * 1e6), (size_t)L->n);
       write_factorizations(&it->it_raw, R, e, L, polya, polyad);

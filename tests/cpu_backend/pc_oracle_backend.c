@@ -28,7 +28,7 @@ unsigned po_prefix_cut(const char *s1, int l1, const char *s2, int l2, int *c1, 
 void po_lcs(const char *s1, long l1, const char *s2, long l2, long *occ1, long *occ2, long *len);
 long po_seed(const char *T, long G, const char *P, long n, int mfl, double rate, int *out, long cap);
 
-struct pc_ctx { char *genome; size_t len; int word; double rate; };
+struct pc_ctx { char *genome; size_t len; int word; double rate; uint64_t ghash; };
 struct pc_stream { pc_ctx *ctx; };
 static unsigned long long g_jobs;
 
@@ -42,6 +42,9 @@ int pc_genome_upload(pc_ctx *c, const char *genome, size_t len, int word_len, do
   memset(c->genome, 0, len + 16);
   memcpy(c->genome, genome, len);
   c->len = len; c->word = word_len; c->rate = depth_rate;
+  uint64_t h = 1469598103934665603ull ^ (uint64_t)word_len ^ (uint64_t)(depth_rate * 1e6);
+  for (size_t i = 0; i < len; ++i) h = (h ^ (uint8_t)genome[i]) * 1099511628211ull;
+  c->ghash = h;
   return 0;
 }
 pc_stream *pc_stream_create(pc_ctx *c) { pc_stream *s = calloc(1, sizeof *s); s->ctx = c; return s; }
@@ -51,6 +54,89 @@ void pc_host_free(void *p) { free(p); }
 int pc_stream_sync(pc_stream *s) { (void)s; return 0; }
 uint64_t pc_launch_count(void) { return g_jobs; }
 void pc_debug_dump(void) {}
+
+/* ---- optional memo of job results (developer tool: PC_ORACLE_MEMO=<file>) ---------------------------------------------
+ * The oracle is orders of magnitude slower than the device, so a profile of the HOST code over this backend is all
+ * waiting.  With a memo file a second run answers every job from the table (key = hash of the job's parameters and
+ * input bytes) and the host code runs at its own speed; the output bytes are checked as always. */
+typedef struct memo_ent { uint64_t k0, k1; int32_t res[PC_RES_INTS]; uint32_t var_len; uint8_t *var; } memo_ent;
+static struct { memo_ent *tab; size_t cap, n; pthread_mutex_t mu; const char *path; int loaded; size_t hits, misses; } g_memo = {.mu = PTHREAD_MUTEX_INITIALIZER};
+static void memo_insert_locked(const memo_ent *e) {
+  if ((g_memo.n + 1) * 2 > g_memo.cap) {
+    const size_t ncap = g_memo.cap ? g_memo.cap * 2 : (size_t)1 << 16;
+    memo_ent *nt = calloc(ncap, sizeof *nt);
+    for (size_t i = 0; i < g_memo.cap; ++i) if (g_memo.tab[i].k0 | g_memo.tab[i].k1) { size_t h = g_memo.tab[i].k0 & (ncap - 1); while (nt[h].k0 | nt[h].k1) h = (h + 1) & (ncap - 1); nt[h] = g_memo.tab[i]; }
+    free(g_memo.tab); g_memo.tab = nt; g_memo.cap = ncap;
+  }
+  size_t h = e->k0 & (g_memo.cap - 1);
+  while (g_memo.tab[h].k0 | g_memo.tab[h].k1) { if (g_memo.tab[h].k0 == e->k0 && g_memo.tab[h].k1 == e->k1) return; h = (h + 1) & (g_memo.cap - 1); }
+  g_memo.tab[h] = *e; ++g_memo.n;
+}
+static void memo_save(void) {
+  if (!g_memo.path || !g_memo.misses) return;
+  FILE *f = fopen(g_memo.path, "wb");
+  if (!f) return;
+  for (size_t i = 0; i < g_memo.cap; ++i) {
+    const memo_ent *e = &g_memo.tab[i];
+    if (!(e->k0 | e->k1)) continue;
+    fwrite(&e->k0, 8, 1, f); fwrite(&e->k1, 8, 1, f); fwrite(e->res, sizeof e->res, 1, f); fwrite(&e->var_len, 4, 1, f);
+    if (e->var_len) fwrite(e->var, 1, e->var_len, f);
+  }
+  fclose(f);
+  fprintf(stderr, "oracle backend memo: %zu entries saved (%zu hits, %zu misses)\n", g_memo.n, g_memo.hits, g_memo.misses);
+}
+static void memo_load_locked(void) {
+  g_memo.loaded = 1;
+  g_memo.path = getenv("PC_ORACLE_MEMO");
+  if (!g_memo.path) return;
+  atexit(memo_save);
+  FILE *f = fopen(g_memo.path, "rb");
+  if (!f) return;
+  memo_ent e;
+  while (fread(&e.k0, 8, 1, f) == 1 && fread(&e.k1, 8, 1, f) == 1 && fread(e.res, sizeof e.res, 1, f) == 1 && fread(&e.var_len, 4, 1, f) == 1) {
+    e.var = e.var_len ? malloc(e.var_len) : NULL;
+    if (e.var_len && fread(e.var, 1, e.var_len, f) != e.var_len) break;
+    memo_insert_locked(&e);
+  }
+  fclose(f);
+}
+static uint64_t mix(uint64_t h, const void *p, size_t n, uint64_t mul) {
+  const uint8_t *b = p;
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, b + i, 8); h = (h ^ w) * mul; h ^= h >> 29; }
+  for (; i < n; ++i) h = (h ^ b[i]) * mul;
+  return h ^ (h >> 31);
+}
+static void memo_key(const pc_ctx *c, const pc_job *j, const char *a, const char *b, uint64_t *k0, uint64_t *k1) {
+  const uint32_t hdr[8] = {j->op, j->a_len, j->b_len, (uint32_t)j->p0, (uint32_t)j->p1, (uint32_t)j->p2, j->out_cap, j->flags & ~(uint32_t)PC_B_IN_GENOME};
+  uint64_t x = mix(0x9E3779B97F4A7C15ull, hdr, sizeof hdr, 0xff51afd7ed558ccdull), y = mix(0xc4ceb9fe1a85ec53ull, hdr, sizeof hdr, 0x9fb21c651e98df25ull);
+  x = mix(x, a, j->a_len, 0xff51afd7ed558ccdull); y = mix(y, a, j->a_len, 0x9fb21c651e98df25ull);
+  if (j->op != PC_OP_SEED) { x = mix(x, b, j->b_len, 0xff51afd7ed558ccdull); y = mix(y, b, j->b_len, 0x9fb21c651e98df25ull); }
+  else { x ^= c->ghash; y += c->ghash * 0x9E3779B97F4A7C15ull; }        /* the genome, word length and depth rate of the session */
+  *k0 = x | 1; *k1 = y;
+}
+static int memo_get(uint64_t k0, uint64_t k1, int32_t *res, uint8_t *var) {
+  int hit = 0;
+  pthread_mutex_lock(&g_memo.mu);
+  if (!g_memo.loaded) memo_load_locked();
+  if (g_memo.cap) {
+    size_t h = k0 & (g_memo.cap - 1);
+    while (g_memo.tab[h].k0 | g_memo.tab[h].k1) {
+      if (g_memo.tab[h].k0 == k0 && g_memo.tab[h].k1 == k1) { memcpy(res, g_memo.tab[h].res, sizeof g_memo.tab[h].res); if (g_memo.tab[h].var_len) memcpy(var, g_memo.tab[h].var, g_memo.tab[h].var_len); hit = 1; break; }
+      h = (h + 1) & (g_memo.cap - 1);
+    }
+  }
+  if (hit) ++g_memo.hits; else ++g_memo.misses;
+  pthread_mutex_unlock(&g_memo.mu);
+  return hit;
+}
+static void memo_put(uint64_t k0, uint64_t k1, const int32_t *res, const uint8_t *var, uint32_t var_len) {
+  memo_ent e; e.k0 = k0; e.k1 = k1; memcpy(e.res, res, sizeof e.res); e.var_len = var_len; e.var = var_len ? malloc(var_len) : NULL;
+  if (var_len) memcpy(e.var, var, var_len);
+  pthread_mutex_lock(&g_memo.mu);
+  memo_insert_locked(&e);
+  pthread_mutex_unlock(&g_memo.mu);
+}
 
 int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes, const pc_job *jobs, int njobs, int32_t *res,
               uint8_t *var_out, size_t var_out_bytes) {
@@ -64,6 +150,13 @@ int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes, const pc_
     const char *b = (j->flags & PC_B_IN_GENOME) ? c->genome + j->b_off : (const char *)arena + j->b_off;
     const int la = (int)j->a_len, lb = (int)j->b_len;
     ++g_jobs;
+    static int memo_on = -1;
+    if (memo_on < 0) memo_on = getenv("PC_ORACLE_MEMO") != NULL;
+    uint64_t k0 = 0, k1 = 0;
+    if (memo_on) {
+      memo_key(c, j, a, b, &k0, &k1);
+      if (memo_get(k0, k1, r, var_out + j->out_off)) continue;
+    }
     switch (j->op) {
       case PC_OP_ALIGN: {
         if ((uint32_t)(la + lb) > j->out_cap) { r[0] = PC_E_OUTCAP; break; }
@@ -96,6 +189,12 @@ int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes, const pc_
         break;
       }
       default: r[0] = PC_E_ARG;
+    }
+    if (memo_on) {
+      uint32_t vl = 0;
+      if (r[0] == 0 && (j->op == PC_OP_ALIGN || j->op == PC_OP_GAP)) vl = (uint32_t)(la + lb);
+      if (r[0] == 0 && j->op == PC_OP_SEED) vl = (uint32_t)r[1] * 12u;
+      memo_put(k0, k1, r, var_out + j->out_off, vl);
     }
   }
   return 0;

@@ -1,5 +1,5 @@
 /* ef_prof.c — tiny sampling profiler for the est-fact host code (developer tool, linked only into the -DEF_GPROF build).
- * SIGPROF every 1 ms of process CPU time; records the interrupted PC when it lies in the program's text, else the first
+ * SIGPROF every EF_PROF_US microseconds (default 1000) of process CPU time; records the interrupted PC when it lies in the program's text, else the first
  * stack word that does (the caller in our code of the libc routine that was running).  Dumped at exit as "addr count kind". */
 #define _GNU_SOURCE
 #include <signal.h>
@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
+#include <time.h>
 #include <ucontext.h>
 extern char __executable_start, etext;
 #define NS (1 << 16)
@@ -45,7 +46,17 @@ __attribute__((constructor)) static void start(void) {
   struct sigaction sa; memset(&sa, 0, sizeof sa);
   sa.sa_sigaction = on_prof; sa.sa_flags = SA_SIGINFO | SA_RESTART;
   sigaction(SIGPROF, &sa, NULL);
-  struct itimerval it = {{0, 1000}, {0, 1000}};
-  setitimer(ITIMER_PROF, &it, NULL);
+  const char *ov = getenv("EF_PROF_US");
+  const long us = ov && atol(ov) > 0 ? atol(ov) : 1000;
+  timer_t t;
+  struct sigevent ev; memset(&ev, 0, sizeof ev);
+  ev.sigev_notify = SIGEV_SIGNAL; ev.sigev_signo = SIGPROF;
+  if (timer_create(CLOCK_PROCESS_CPUTIME_ID, &ev, &t) == 0) {          /* high-resolution; ITIMER_PROF is tick-bound */
+    struct itimerspec its = {{us / 1000000, (us % 1000000) * 1000}, {us / 1000000, (us % 1000000) * 1000}};
+    timer_settime(t, 0, &its, NULL);
+  } else {
+    struct itimerval it = {{0, us}, {0, us}};
+    setitimer(ITIMER_PROF, &it, NULL);
+  }
   atexit(dump);
 }
