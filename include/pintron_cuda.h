@@ -25,6 +25,10 @@
  *   PC_OP_PRECUT    compute_best_prefix_cut     src/compute-alignments.c:290  ed, cut1, cut2
  *   PC_OP_LCS       find_longest_common_factor_dp  src/factorization-refinement.c:255  len, occ1, occ2
  *   PC_OP_SEED      build_vertex_set            src/max-emb-graph.c:217       count        (+(p,t,l) int32 triples)
+ *     with p1 = PC_SEED_BUILD_MEG the job goes on, on the device, through the rest of build_meg
+ *     (src/compute-est-fact.c:90-152): build_edge_set (src/max-emb-graph.c:649), simplify_meg,
+ *     transitive_reduction, compact_short_edges and is_too_complex (src/meg-simplification.c:314,518,258,89);
+ *     the result is the finished graph (struct pc_meg_cfg / "MEG record" below), count = its size in 12-byte units
  *
  * Alignment ops: one byte per alignment column, left to right: 0 = EST char over genome char,
  * 1 = EST char over '-', 2 = '-' over genome char (the reference's EST_alignment / GEN_alignment rows,
@@ -75,10 +79,29 @@ typedef struct pc_job {
   uint32_t a_off, a_len;  /* EST-side string (ALIGN/GAP/AFFIX/SEED: the EST; BORDERS: p; LCS: s2; else s1) */
   uint32_t b_off, b_len;  /* genome-side string (BORDERS: t; LCS: s1 = the long one; unused for SEED) */
   int32_t  p0, p1, p2;    /* KBAND: p0 = upper bound k.  BORDERS: p0 = max_errs, p1 = min_p_cut, p2 = max_p_cut.
-                             SEED: p0 = min factor length in force (config + inc_pairing_len). */
+                             SEED: p0 = min factor length in force (config + inc_pairing_len); p1 = 0 (vertex set only) or
+                             PC_SEED_BUILD_MEG (b = one struct pc_meg_cfg in the arena). */
   uint32_t out_off;       /* byte offset of this job's variable output inside var_out (4-aligned for SEED) */
-  uint32_t out_cap;       /* ALIGN/GAP: bytes (>= a_len + b_len); SEED: capacity in (p,t,l) triples */
+  uint32_t out_cap;       /* ALIGN/GAP: bytes (>= a_len + b_len); SEED: capacity in (p,t,l) triples (= 12-byte units) */
 } pc_job;
+
+/* ---- PC_OP_SEED with p1 = PC_SEED_BUILD_MEG: the whole Maximal Embedding Graph on the device -------------------
+ * b (in the arena, any alignment) = the options build_meg reads (src/options.ggo; include/configuration.h).
+ * MEG record written at out_off (int32 words; PC_E_OUTCAP + needed 12-byte units in res[1] when it does not fit):
+ *   [0] nv   vertices, in the order the reference's lists hold them (V[0] = source, V[i+1] = pairings at p = i in list
+ *            order, V[|P|+1] = sink) = the numbering of megs.txt (src/io-meg.c:147-190)
+ *   [1] ne   edges            [2] 1 = "too complex": build again with p0 + 1 (src/compute-est-fact.c:131-146)      [3] 0
+ *   then nv x (p, t, l)  (source: INT32_MIN, INT32_MIN, 200; sink: INT32_MAX - 200, INT32_MAX - 200, 200),
+ *   then nv adjacency counts, then the ne adjacency targets (vertex numbers), list by list in list order. */
+#define PC_SEED_BUILD_MEG 1
+typedef struct pc_meg_cfg {
+  int32_t min_intron_length, max_intron_length;          /* --min-intron-length, --max-intron-length (0 = unlimited) */
+  uint32_t max_pairings_in_MEG;                          /* --max-pairings-in-CMEG */
+  uint32_t flags;                                        /* 1 = transitive reduction, 2 = short-edge compaction */
+  double max_prefix_discarded_rate, max_suffix_discarded_rate, max_freq_shortest_pairing;
+} pc_meg_cfg;
+#define PC_MEG_TRANS_RED 1u
+#define PC_MEG_SHORT_EDGE_COMP 2u
 
 /* ---- context / errors ---------------------------------------------------------------------------- */
 const char *pc_last_error(void);                 /* thread-local message of the last failing call */

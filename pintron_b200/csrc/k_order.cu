@@ -20,6 +20,8 @@ __device__ __forceinline__ bool job_valid(const pc_job &j, size_t arena_bytes, s
   if (j.op != PC_OP_SEED) {
     const size_t lim = (j.flags & PC_B_IN_GENOME) ? genome_len : arena_bytes;
     if ((size_t)j.b_off + j.b_len > lim) return false;
+  } else if (j.p1 == PC_SEED_BUILD_MEG) {            /* b = the MEG options, in the arena */
+    if ((j.flags & PC_B_IN_GENOME) || j.b_len != sizeof(pc_meg_cfg) || (size_t)j.b_off + j.b_len > arena_bytes || j.p0 < 1) return false;
   }
   if (j.op == PC_OP_ALIGN || j.op == PC_OP_GAP) { if ((size_t)j.out_off + j.out_cap > var_bytes) return false; }
   else if (j.op == PC_OP_SEED) { if ((j.out_off & 3u) || (size_t)j.out_off + 12ull * j.out_cap > var_bytes) return false; }

@@ -7,6 +7,7 @@
 // never occur in a genome), and every hit is re-verified by the byte-wise extension, so hash collisions cost
 // time, never correctness.
 #include "pc_device.cuh"
+#include "meg_core.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <climits>
 
@@ -75,9 +76,12 @@ __device__ int warp_exscan(int *v, int n, int lane) {
 struct TL { int t, l; };
 
 #define SEED_TILE 2048      /* EST bytes staged in shared memory per warp (longer ESTs are read through L1) */
-__device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane, uint8_t *tile) {
+// Returns the number of triples, written to the job's output region — or, for a PC_SEED_BUILD_MEG job, to the warp's scratch
+// slot (*tri_out); -1 when the job is already answered (status written).
+__device__ int seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane, uint8_t *tile, int32_t **tri_out) {
   const uint32_t ji = B.idx[w];
   const pc_job *job = B.jobs + ji;
+  const bool meg = job->p1 == PC_SEED_BUILD_MEG;
   int32_t *res = B.res + (size_t)ji * PC_RES_INTS;
   const uint8_t *P = B.arena + job->a_off;
   const int n = (int)job->a_len, mfl = job->p0, word = B.ix_word;
@@ -89,12 +93,13 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane, uin
   const uint8_t *T = B.genome;
   const uint32_t G = B.genome_len;
   int32_t *out = (int32_t *)(B.var_out + job->out_off);
-  if (mfl < word) { if (lane == 0) res[0] = PC_E_ARG; return; }
+  *tri_out = out;
+  if (mfl < word) { if (lane == 0) res[0] = PC_E_ARG; return -1; }
   const int np = n - word + 1;               // positions that can start a word
-  if (np <= 0 || G < (uint32_t)word) { if (lane == 0) { res[0] = PC_OK; res[1] = 0; } return; }
+  if (np <= 0 || G < (uint32_t)word) { if (!meg && lane == 0) { res[0] = PC_OK; res[1] = 0; } return meg ? 0 : -1; }
   // per-position arrays: bucket start, bucket end, D / offsets, counts
   int *arr = (int *)pc_pool_alloc(B, wp, 10ull * np * sizeof(int), lane);
-  if (!arr) { if (lane == 0) res[0] = PC_E_POOL; return; }
+  if (!arr) { if (lane == 0) res[0] = PC_E_POOL; return -1; }
   int *b_lo = arr, *b_hi = arr + np, *offs = arr + 2 * np, *cnt = arr + 3 * np, *thr_a = arr + 4 * np, *ncand = arr + 5 * np;
   TL *first2 = (TL *)(arr + 6 * np);           // the first two candidates of every position: S2 rarely has to extend again
   // S1: bucket, D(p), number of candidates >= mfl
@@ -124,7 +129,7 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane, uin
   TL *cand = nullptr; uint8_t *keep = nullptr;
   if (total > 0) {
     cand = (TL *)pc_pool_alloc(B, wp, (unsigned long long)total * (sizeof(TL) + 1), lane);
-    if (!cand) { if (lane == 0) res[0] = PC_E_POOL; return; }
+    if (!cand) { if (lane == 0) res[0] = PC_E_POOL; return -1; }
     keep = (uint8_t *)(cand + total);
   }
   // S2: emit candidates >= thr (ascending t), filter A in place
@@ -173,7 +178,11 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane, uin
   __syncwarp();
   const int n_out = warp_exscan(outc, np, lane);
   __syncwarp();
-  if ((uint32_t)n_out > job->out_cap) { if (lane == 0) { res[0] = PC_E_OUTCAP; res[1] = n_out; } return; }
+  if (meg) {
+    out = (int32_t *)pc_pool_alloc(B, wp, 12ull * (unsigned long long)n_out + 4ull, lane);
+    if (!out) { if (lane == 0) res[0] = PC_E_POOL; return -1; }
+    *tri_out = out;
+  } else if ((uint32_t)n_out > job->out_cap) { if (lane == 0) { res[0] = PC_E_OUTCAP; res[1] = n_out; } return -1; }
   for (int p = lane; p < np; p += 32) {
     const TL *v = cand + offs[p];
     const uint8_t *kp = keep + offs[p];
@@ -181,7 +190,52 @@ __device__ void seed_one(const PcDevBatch &B, WarpPool &wp, int w, int lane, uin
     for (int x = 0; x < cnt[p]; ++x)
       if (kp[x]) { out[3 * o] = p; out[3 * o + 1] = v[x].t; out[3 * o + 2] = v[x].l; ++o; }
   }
-  if (lane == 0) { res[0] = PC_OK; res[1] = n_out; }
+  if (!meg && lane == 0) { res[0] = PC_OK; res[1] = n_out; }
+  return n_out;
+}
+
+// ---- the rest of build_meg on the vertex set just found (PC_SEED_BUILD_MEG; meg_core.h) -----------------------------
+// The triples move to the bottom of the warp's scratch slot (everything else in it is dead by now) and the graph is carved
+// out of what follows.  Edge rules, list orders and the simplification passes are sequential and order-dependent (the bytes
+// of megs.txt follow the list orders): one lane walks them; graphs are a few dozen vertices, and the other warps of the SM
+// run meanwhile.
+__device__ void meg_one(const PcDevBatch &B, WarpPool &wp, int w, int lane, int32_t *tri, int ntri) {
+  const uint32_t ji = B.idx[w];
+  const pc_job *job = B.jobs + ji;
+  int32_t *res = B.res + (size_t)ji * PC_RES_INTS;
+  int32_t *base = (int32_t *)wp.base;
+  const int nw = 3 * ntri;
+  __syncwarp();
+  if (tri != base)
+    for (int r0 = 0; r0 < nw; r0 += 32) {              // downwards, a whole round read before it is written
+      const int i = r0 + lane;
+      const int32_t v = i < nw ? tri[i] : 0;
+      __syncwarp();
+      if (i < nw) base[i] = v;
+      __syncwarp();
+    }
+  __syncwarp();
+  if (lane == 0) {
+    const unsigned long long tri_bytes = (12ull * (unsigned long long)ntri + 255ull) & ~255ull;
+    pc_meg_cfg cfg;
+    const uint8_t *cb = B.arena + job->b_off;
+    for (int i = 0; i < (int)sizeof(pc_meg_cfg); ++i) ((uint8_t *)&cfg)[i] = cb[i];
+    mg_graph g;
+    g.err = MG_E_SCRATCH;
+    int retry = 0;
+    if (tri_bytes + 1024ull <= wp.size) {
+      mg_init(&g, (int *)(wp.base + tri_bytes), (long long)((wp.size - tri_bytes) / 4ull), base, ntri);
+      if (!g.err) retry = mg_build(&g, (int)job->a_len, job->p0, &cfg);
+    }
+    if (g.err == MG_E_SCRATCH) { atomicMax(B.pool_need, 2ull * wp.size + 4096ull); res[0] = PC_E_POOL; }
+    else if (g.err) res[0] = PC_E_RANGE;                  // a cyclic graph: cannot happen (edges ascend in p); the host reports it
+    else {
+      const long long units = (mg_record_words(&g) + 2) / 3;
+      if (units > (long long)job->out_cap) { res[0] = PC_E_OUTCAP; res[1] = (int32_t)units; }
+      else { mg_write_record(&g, retry, (int32_t *)(B.var_out + job->out_off)); res[0] = PC_OK; res[1] = (int32_t)units; }
+    }
+  }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(128) k_seed(PcDevBatch B) {
@@ -192,7 +246,9 @@ __global__ void __launch_bounds__(128) k_seed(PcDevBatch B) {
   WarpPool wp = pc_warp_pool(B, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < B.n; w += nwarps) {
     wp.used = 0;
-    seed_one(B, wp, w, lane, tiles[threadIdx.x >> 5]);
+    int32_t *tri = nullptr;
+    const int ntri = seed_one(B, wp, w, lane, tiles[threadIdx.x >> 5], &tri);
+    if (ntri >= 0 && B.jobs[B.idx[w]].p1 == PC_SEED_BUILD_MEG) meg_one(B, wp, w, lane, tri, ntri);
     __syncwarp();
   }
 }

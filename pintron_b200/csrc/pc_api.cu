@@ -558,6 +558,9 @@ static int check_jobs(const pc_ctx *c, const pc_job *jobs, int njobs, size_t are
     if (j.op != PC_OP_SEED) {
       const size_t lim = (j.flags & PC_B_IN_GENOME) ? glen : arena_bytes;
       if ((size_t)j.b_off + j.b_len > lim) return fail(PC_E_ARG, "%s", "pc_submit: job string b out of range");
+    } else if (j.p1 == PC_SEED_BUILD_MEG) {
+      if ((j.flags & PC_B_IN_GENOME) || j.b_len != sizeof(pc_meg_cfg) || (size_t)j.b_off + j.b_len > arena_bytes || j.p0 < 1)
+        return fail(PC_E_ARG, "%s", "pc_submit: PC_SEED_BUILD_MEG wants one struct pc_meg_cfg as string b (in the arena) and p0 >= 1");
     }
     if (j.op == PC_OP_ALIGN || j.op == PC_OP_GAP) {
       if ((size_t)j.out_off + j.out_cap > var_out_bytes) return fail(PC_E_ARG, "%s", "pc_submit: ops region outside var_out");

@@ -94,9 +94,9 @@ typedef struct ef_pairing ef_pairing;
 typedef struct ef_plist { ef_pairing **v; int n, cap; } ef_plist;      /* ordered list of pairing pointers */
 struct ef_pairing {
   int p, t, l;
-  int id;
-  ef_plist adjs, incs;
-  bool visited, dead;
+  int id;                       /* position in list order = the vertex number of megs.txt */
+  ef_plist adjs;
+  bool visited;
   void *memo;                   /* embeddings already enumerated from this vertex */
 };
 #define SRC_START INT_MIN
@@ -104,8 +104,9 @@ struct ef_pairing {
 #define SENTINEL_LEN 200
 
 typedef struct ef_meg {
-  int n;                        /* |P| + 2 slots: V[0] = source, V[i+1] = pairings at p = i, V[n-1] = sink */
-  ef_plist *V;
+  int n;                        /* |P| + 2: the reference's list slots (V[0] = source, V[i+1] = pairings at p = i, V[n-1] = sink) */
+  ef_pairing **flat; int nflat; /* the vertices in list order: V[0], V[1], ... concatenated (as the device returns them) */
+  size_t np, ne;                /* pairings (source and sink included) and edges */
 } ef_meg;
 
 typedef struct ef_factor { int es, ee, gs, ge; } ef_factor;        /* EST_start, EST_end, GEN_start, GEN_end */
@@ -124,8 +125,6 @@ typedef struct ef_task {
   uint64_t run_ticks, run_mark, t_start;
 } ef_task;
 
-void pl_push(ef_task *T, ef_plist *l, ef_pairing *x);
-bool pl_remove_first(ef_plist *l, ef_pairing *x);
 ef_fz *fz_new(ef_task *T, int cap);
 void fz_push(ef_task *T, ef_fz *z, ef_factor f);
 void fz_insert(ef_task *T, ef_fz *z, int at, ef_factor f);

@@ -627,18 +627,17 @@ ef_fzlist *est_factorizations(ef_task *T, const ef_seq *est, ef_meg *M, bool *ti
   *timed_out = false;
   ef_fzlist *L = ar_alloc(&T->ar, sizeof *L);
   unsigned tick = 0;
-  for (int i = 0; i < M->n; ++i)
-    for (int k = 0; k < M->V[i].n; ++k) {
-      ef_pairing *root = M->V[i].v[k];
-      if (root->visited) continue;
-      emblist *E = subtree_embeddings(T, root, &tick);
-      if (!E) { *timed_out = true; return NULL; }
-      ef_fzlist cand = {0};
-      for (int x = 0; x < E->n; ++x) fzl_push(T, &cand, factorization_of(T, E->v[x]));
-      ef_phase(EF_PH_CAND);
-      candidate_phases(T, est, &cand, L);
-      ef_phase(EF_PH_EMBED);
-    }
+  for (int vi = 0; vi < M->nflat; ++vi) {
+    ef_pairing *root = M->flat[vi];
+    if (root->visited) continue;
+    emblist *E = subtree_embeddings(T, root, &tick);
+    if (!E) { *timed_out = true; return NULL; }
+    ef_fzlist cand = {0};
+    for (int x = 0; x < E->n; ++x) fzl_push(T, &cand, factorization_of(T, E->v[x]));
+    ef_phase(EF_PH_CAND);
+    candidate_phases(T, est, &cand, L);
+    ef_phase(EF_PH_EMBED);
+  }
   ef_phase(EF_PH_FILTER);
   /* FILTER 1: coverage on P relative to the best one */
   double *cov = ar_alloc(&T->ar, sizeof(double) * (size_t)(L->n + 1)), maxc = 0.0;

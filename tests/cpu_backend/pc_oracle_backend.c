@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include "../../pintron_b200/csrc/meg_core.h"      /* the MEG core the device runs (PC_SEED_BUILD_MEG), compiled for the host */
 
 int po_align(const char *est, int n, const char *gen, int m, uint8_t *ops, int *ops_len);
 unsigned po_edit(const char *s1, int l1, const char *s2, int l2);
@@ -111,8 +112,8 @@ static void memo_key(const pc_ctx *c, const pc_job *j, const char *a, const char
   const uint32_t hdr[8] = {j->op, j->a_len, j->b_len, (uint32_t)j->p0, (uint32_t)j->p1, (uint32_t)j->p2, j->out_cap, j->flags & ~(uint32_t)PC_B_IN_GENOME};
   uint64_t x = mix(0x9E3779B97F4A7C15ull, hdr, sizeof hdr, 0xff51afd7ed558ccdull), y = mix(0xc4ceb9fe1a85ec53ull, hdr, sizeof hdr, 0x9fb21c651e98df25ull);
   x = mix(x, a, j->a_len, 0xff51afd7ed558ccdull); y = mix(y, a, j->a_len, 0x9fb21c651e98df25ull);
-  if (j->op != PC_OP_SEED) { x = mix(x, b, j->b_len, 0xff51afd7ed558ccdull); y = mix(y, b, j->b_len, 0x9fb21c651e98df25ull); }
-  else { x ^= c->ghash; y += c->ghash * 0x9E3779B97F4A7C15ull; }        /* the genome, word length and depth rate of the session */
+  if (j->op != PC_OP_SEED || j->p1 == PC_SEED_BUILD_MEG) { x = mix(x, b, j->b_len, 0xff51afd7ed558ccdull); y = mix(y, b, j->b_len, 0x9fb21c651e98df25ull); }
+  if (j->op == PC_OP_SEED) { x ^= c->ghash; y += c->ghash * 0x9E3779B97F4A7C15ull; }        /* the genome, word length and depth rate of the session */
   *k0 = x | 1; *k1 = y;
 }
 static int memo_get(uint64_t k0, uint64_t k1, int32_t *res, uint8_t *var) {
@@ -184,6 +185,31 @@ int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes, const pc_
       case PC_OP_LCS: { long o1, o2, ln; po_lcs(b, lb, a, la, &o1, &o2, &ln); r[1] = (int32_t)ln; r[2] = (int32_t)o1; r[3] = (int32_t)o2; break; }
       case PC_OP_SEED: {
         int *out = (int *)(var_out + j->out_off);
+        if (j->p1 == PC_SEED_BUILD_MEG) {
+          if (lb != (int)sizeof(pc_meg_cfg)) { r[0] = PC_E_ARG; break; }
+          pc_meg_cfg cfg; memcpy(&cfg, b, sizeof cfg);
+          long cap = 1024, n;
+          int *tri = malloc(sizeof(int) * 3 * (size_t)cap);
+          while ((n = po_seed(c->genome, (long)c->len, a, la, j->p0, c->rate, tri, cap)) < 0) { cap = -n + 16; tri = realloc(tri, sizeof(int) * 3 * (size_t)cap); }
+          long long nints = 1 << 16;
+          for (;;) {
+            int *mem = malloc(sizeof(int) * (size_t)nints);
+            mg_graph g;
+            mg_init(&g, mem, nints, tri, (int)n);
+            const int retry = g.err ? 0 : mg_build(&g, la, j->p0, &cfg);
+            if (g.err == MG_E_SCRATCH) { free(mem); nints *= 2; continue; }
+            if (g.err) r[0] = PC_E_RANGE;
+            else {
+              const long long units = (mg_record_words(&g) + 2) / 3;
+              if (units > (long long)j->out_cap) { r[0] = PC_E_OUTCAP; r[1] = (int32_t)units; }
+              else { mg_write_record(&g, retry, out); r[1] = (int32_t)units; }
+            }
+            free(mem);
+            break;
+          }
+          free(tri);
+          break;
+        }
         long n = po_seed(c->genome, (long)c->len, a, la, j->p0, c->rate, out, (long)j->out_cap);
         if (n < 0) { r[0] = PC_E_OUTCAP; r[1] = (int32_t)-n; } else r[1] = (int32_t)n;
         break;

@@ -423,3 +423,66 @@ def test_packed_borders_vs_port(cu, port):
         out = (ctypes.c_int * 4)()
         ok = bool(port.lib.po_borders(p, len(p), lo, hi, t, lt, ctypes.c_uint(me), out))
         assert bool(r[1]) == ok and list(r[2:6]) == list(out), (p, t, lt, me, lo, hi, list(r), ok, list(out))
+
+
+def _meg_shim():
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "tests"), "_build/libmeg_host.so"], check=True)
+    L = C.CDLL(os.path.join(root, "tests", "_build", "libmeg_host.so"))
+    L.meg_host_record.restype = C.c_longlong
+    L.meg_host_record.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
+    return L
+
+
+def _meg_cfg(min_intron=60, max_intron=0, max_pairings=80, flags=3, pre=0.6, suf=0.6, freq=0.4):
+    import struct
+    return struct.pack("<iiIIddd", min_intron, max_intron, max_pairings, flags, pre, suf, freq)
+
+
+def test_meg_on_device_vs_host_core(cu, port):
+    """PC_OP_SEED with PC_SEED_BUILD_MEG: the graph the GPU returns (vertices in list order, ordered adjacency lists, the
+    "too complex" flag) equals the record of the same core compiled for the host on the oracle's triples, for spliced ESTs
+    over a genome with repeats, every combination of the two simplification switches, several pairing lengths and option
+    values; an output region that is too small reports the needed size."""
+    L = _meg_shim()
+    g = Gen(977)
+    genome = g.genome(30000, n_repeats=12)
+    cu.genome_upload(genome, 15, 0.2)
+    b, chk = Batch(), []
+    for it in range(400):
+        r = g.rnd
+        parts, pos = [], r.randint(0, 4000)
+        for _ in range(r.randint(1, 14)):            # spliced EST: exons of 15..160 nt, introns of 3..2500 nt (short ones feed the compaction)
+            ln = r.randint(15, 160)
+            parts.append(genome[pos:pos + ln])
+            pos += ln + r.choice([r.randint(1, 3), r.randint(4, 70), r.randint(70, 2500)])
+            if pos >= len(genome) - 200:
+                break
+        e = g.mutate(b"".join(parts), r.choice([0, 0.01, 0.03]), alpha="ACGT") or b"ACGT"
+        cfg = _meg_cfg(min_intron=r.choice([60, 0, 200]), max_intron=r.choice([0, 0, 1500]), max_pairings=r.choice([80, 0, 5]), flags=it % 4,
+                       pre=r.choice([0.6, 0.1, 1.0]), suf=r.choice([0.6, 0.1, 1.0]), freq=r.choice([0.4, 0.05]))
+        mfl = (15, 15, 16, 19)[it % 4]
+        cap = 8 if it % 50 == 7 else 4096
+        b.add(PC_OP.SEED, e, b=cfg, p0=mfl, p1=1, out_cap=cap); chk.append((e, cfg, mfl, cap))
+    res, var = cu.run(b)
+    _, jobs = b.arrays()
+    sizes, retries, small = [], 0, 0
+    for r, j, (e, cfg, mfl, cap) in zip(res, jobs, chk):
+        tri = np.array(port.seed(genome, e, mfl, 0.2), dtype=np.int32).reshape(-1, 3)
+        out = np.zeros(1 << 18, dtype=np.int32)
+        tri_c = np.ascontiguousarray(tri)
+        words = L.meg_host_record(tri_c.ctypes.data, len(tri), len(e), mfl, cfg, out.ctypes.data, len(out))
+        assert words > 0
+        units = (words + 2) // 3
+        if units > cap:
+            assert r[0] == -2 and r[1] == units      # PC_E_OUTCAP + the needed 12-byte units
+            small += 1
+            continue
+        assert r[0] == 0 and r[1] == units, (list(r), units)
+        got = var[j["out_off"]:j["out_off"] + 4 * words].view(np.int32)
+        assert got.tolist() == out[:words].tolist()
+        sizes.append(int(out[0])); retries += int(out[2])
+    assert max(sizes) >= 12 and small >= 1           # real graphs, and the too-small region happened
