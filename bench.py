@@ -112,6 +112,14 @@ def _log(msg):
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
+def fresh_run_dir(d):
+    """Each whole-program step starts as pintron.py's STEP 2 does: a directory that holds genomic.txt and ests.txt only
+    (leftovers of the previous step would make the program pay for truncating hundreds of MB of page cache)."""
+    for f in os.listdir(d):
+        if f not in ("genomic.txt", "ests.txt"):
+            os.remove(os.path.join(d, f))
+
+
 def md5_files(d):
     return {f: hashlib.md5(open(os.path.join(d, f), "rb").read()).hexdigest() for f in FILES}
 
@@ -146,6 +154,8 @@ class RefShards:
 
     def step(self, timeout=None):
         """One pass over all shards; seconds, or None when `timeout` expired first (the processes are killed)."""
+        for d in self.dirs:
+            fresh_run_dir(d)
         t0 = time.perf_counter()
         procs = [subprocess.Popen([self.exe], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for d in self.dirs]
         rcs = []
@@ -218,10 +228,12 @@ def run_reference(args, rank):
 
 def host_threads(world_gpus_on_box):
     """est-fact worker threads per GPU: this GPU's share of the host cores (cores // GPUs of the BOX, whatever N is, so
-    that the N = 1 run of a scaling series uses what one GPU gets at N = 8), minus room for the engine and the writer."""
+    that the N = 1 run of a scaling series uses what one GPU gets at N = 8), the engine's submission loop and the writers float over the same cores)."""
     cores = os.cpu_count() or 1
     share = max(1, cores // max(1, world_gpus_on_box))
-    return share - 2 if share >= 8 else (share - 1 if share >= 6 else share)       # 16 cores / 1 GPU -> 14; 32 cores / 8 GPUs -> 4
+    # measured on the 16-core box (tools/e2e_probe.py): 16 workers beat 14 by ~2 % although the engine's submission loop and the
+    # writers then share cores with them
+    return share - 1 if 6 <= share < 8 else share       # 16 cores / 1 GPU -> 16; 32 cores / 8 GPUs -> 4
 
 
 def main():
@@ -306,6 +318,7 @@ def main():
     def est_fact(cwd, form, extra=(), env=None, timeout=None):
         """One run of the shipped program; returns (seconds, info parsed from its log)."""
         cmd = [exe, "--threads", str(threads), "--devices", str(local), "--engine", form, *extra]
+        fresh_run_dir(cwd)
         t0 = time.perf_counter()
         p = subprocess.run(cmd, cwd=cwd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env_srv if form == "daemon" else (env or os.environ), timeout=timeout)
         sec = time.perf_counter() - t0

@@ -15,6 +15,10 @@ thread_local unsigned long long tl_pc_launches = 0;
 #include <chrono>
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const bool g_prof = getenv("PC_PROFILE") != nullptr;
+static const bool g_prof_host = g_prof || getenv("PC_PROFILE_HOST") != nullptr;      /* only the host-side phase clock: side streams stay on */
+/* how many side streams a small batch forks over (launch_selected): every (op, class) kernel of such a batch is bound by the
+ * latency of its longest job, so the batch takes the longest chain on one stream, not the sum.  PC_SIDE_STREAMS=1..8. */
+static const int g_side_streams = [] { const char *v = getenv("PC_SIDE_STREAMS"); const int n = v ? atoi(v) : 0; return n >= 1 && n <= 8 ? n : 8; }();
 #define PC_MULTI_STREAM_MAX ((size_t)1 << 18)        /* batches below this many jobs run their segments on side streams */
 static const bool g_serial = getenv("PC_SERIAL_SEGMENTS") != nullptr;      /* experiments: keep every batch on one stream */
 #define PC_POOL_MB_DEFAULT 320         /* scratch pool per stream (direction words, wavefront matrices); grows on demand */
@@ -32,6 +36,7 @@ static unsigned long long g_op_slow[PC_OP_COUNT];
 static double g_op_ms[PC_OP_COUNT]; static unsigned long long g_op_launches[PC_OP_COUNT], g_retry_rounds, g_retry_jobs, g_pool_grows;
 extern "C" void pc_debug_dump(void) {
   if (g_capture) fflush(g_capture);
+  if (g_prof_host && !g_prof) fprintf(stderr, "[pc profile] host: check %.3f reserve %.3f h2d %.3f sort %.3f launch %.3f d2h %.3f sync %.3f s\n", g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5], g_t[6]);
   if (!g_prof) return;
   static const char *nm[PC_OP_COUNT] = {"ALIGN", "KBAND", "EDIT", "BORDERS", "GAP", "AFFIX", "SUFCUT", "PRECUT", "LCS", "SEED"};
   fprintf(stderr, "[pc profile] host: check %.3f reserve %.3f h2d %.3f sort %.3f launch %.3f d2h %.3f sync %.3f s\n", g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5], g_t[6]);
@@ -45,7 +50,7 @@ extern "C" void pc_debug_dump(void) {
           g_dev_grows, g_host_allocs, g_host_alloc_bytes / 1048576.0, g_host_alloc_s);
 }
 struct ProfDump { ~ProfDump() { if (g_prof) fprintf(stderr, "[pc profile] check %.3f reserve %.3f h2d %.3f sort %.3f launch %.3f d2h %.3f sync %.3f s\n", g_t[0], g_t[1], g_t[2], g_t[3], g_t[4], g_t[5], g_t[6]); } } g_prof_dump;
-#define PROF(slot, t0) do { if (g_prof) { double t1_ = now_s(); g_t[slot] += t1_ - (t0); (t0) = t1_; } } while (0)
+#define PROF(slot, t0) do { if (g_prof_host) { double t1_ = now_s(); g_t[slot] += t1_ - (t0); (t0) = t1_; } } while (0)
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char *fmt, const char *detail = "") {
@@ -208,9 +213,9 @@ struct pc_stream {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   /* side streams: the (op, class) segments of a SMALL batch are independent and each kernel is latency-bound (a grid
    * of a few dozen CTAs waiting for its longest job), so they run side by side instead of one after the other */
-  static constexpr int NSIDE = 4;
-  cudaStream_t side[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int NSIDE = 8;
+  cudaStream_t side[NSIDE] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;
   std::vector<cudaEvent_t> ev_free;
 };
@@ -381,7 +386,7 @@ static cudaEvent_t get_event(pc_stream *st) {
 static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const uint32_t *sel, size_t nsel, const uint8_t *d_arena,
                            const pc_job *d_jobs, int32_t *d_res, uint8_t *d_var, size_t arena_bytes, size_t var_bytes,
                            bool force_device_order = false) {
-  double tp = g_prof ? now_s() : 0;
+  double tp = g_prof_host ? now_s() : 0;
   constexpr int NSEG = PC_ORDER_SEGS, NB = PC_ORDER_BINS;
   struct Seg { uint32_t n, max_a, max_b, max_t; unsigned long long lcs_blocks; } seg[NSEG];
   memset(seg, 0, sizeof seg);
@@ -457,7 +462,7 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
   // small batch, several segments, no per-op timing wanted, not a retry round: fork over the side streams, each with
   // its own quarter of the scratch pool
   const bool multi = nseg_live > 1 && nsel < PC_MULTI_STREAM_MAX && !(st->timers || g_prof) && st->max_warps == 0 && !g_serial;
-  constexpr int NS = pc_stream::NSIDE;
+  const int NS = g_side_streams;
   if (multi) CU(cudaEventRecord(st->ev_fork, st->s));
   unsigned used_side = 0;
   int next_side = 0;
@@ -577,7 +582,7 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
   if (!st || njobs < 0 || (njobs && (!jobs || !res))) return fail(PC_E_ARG, "%s", "pc_submit: bad argument");
   if (st->pend.active) return fail(PC_E_ARG, "%s", "pc_submit: previous batch not synced");
   if (njobs == 0) return 0;
-  double tp = g_prof ? now_s() : 0;
+  double tp = g_prof_host ? now_s() : 0;
   CU(cudaSetDevice(st->ctx->device));
   int rc = (size_t)njobs >= PC_DEVICE_ORDER_MIN ? 0 : check_jobs(st->ctx, jobs, njobs, arena_bytes, var_out_bytes);   /* large batches: checked by the key kernel */
   if (rc) return rc;
@@ -604,7 +609,7 @@ extern "C" int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes
   P.active = true; P.device_mode = false; P.jobs = jobs; P.njobs = njobs; P.res = res; P.var_out = var_out;
   P.var_out_bytes = var_out_bytes; P.d_arena = (const uint8_t *)st->arena.p; P.d_jobs = (const pc_job *)st->jobs.p;
   P.d_res = (int32_t *)st->res.p; P.d_var = (uint8_t *)st->var.p; P.parts.clear(); P.ctx = st->ctx;
-  if (g_prof) tp = now_s();
+  if (g_prof_host) tp = now_s();
   CU(cudaMemcpyAsync(res, st->res.p, sizeof(int32_t) * PC_RES_INTS * (size_t)njobs, cudaMemcpyDeviceToHost, st->s));
   if (var_out_bytes) CU(cudaMemcpyAsync(var_out, st->var.p, var_out_bytes, cudaMemcpyDeviceToHost, st->s));
   PROF(5, tp);
@@ -713,7 +718,7 @@ extern "C" int pc_submit_parts(pc_stream *st, pc_ctx *genome_ctx, const pc_part 
 extern "C" int pc_stream_sync(pc_stream *st) {
   if (!st) return fail(PC_E_ARG, "%s", "pc_stream_sync: null stream");
   CU(cudaSetDevice(st->ctx->device));
-  double tp = g_prof ? now_s() : 0;
+  double tp = g_prof_host ? now_s() : 0;
   CU(cudaStreamSynchronize(st->s));
   PROF(6, tp);
   if (g_prof) drain_events(st);

@@ -399,6 +399,7 @@ extern "C" int pc_engine_close(pc_engine *e, uint32_t session, pc_session_stats 
     }
     g->sessions.erase(S->id);
     if (stats) *stats = S->stats;
+    if (getenv("PC_PROFILE") || getenv("PC_PROFILE_HOST")) pc_debug_dump();      /* cumulative phase clock of the submission loops */
     if (g->idle_ctx.size() < 8) { g->idle_ctx.push_back(S->ctx); S->ctx = nullptr; }
   }
   pc_ctx_destroy(S->ctx);

@@ -223,13 +223,16 @@ static void *reader_main(void *arg) {
   size_t win_ahead = WIN_AHEAD;
   { const char *ov = getenv("EF_WINDOW"); if (ov && atol(ov) > 0 && atol(ov) < (1 << WIN_BITS)) win_records = (uint32_t)atol(ov); }     /* tests: tiny windows */
   { const char *ov = getenv("EF_WINDOW_AHEAD"); if (ov && atol(ov) > 0) win_ahead = (size_t)atol(ov); }
+  /* the first windows are short (1/8, 1/4, 1/2 of a window), so that the workers start a few ms after the process does */
+  uint32_t win_now = win_records >= 8 * 256 ? win_records / 8 : win_records;
   while (ef_fasta_next(fa, &e)) {
     if (!W) { W = calloc(1, sizeof *W); cap = 0; bytes = 0; }
     if (W->n == cap) { cap = cap ? cap * 2 : 256; W->items = realloc(W->items, cap * sizeof(est_item)); }
     memset(&W->items[W->n], 0, sizeof(est_item));
     W->items[W->n++].fwd = e;       /* strand / reverse-complement / polyA masking happen in est_task, on the worker threads */
     bytes += (size_t)e.len;
-    if (W->n >= win_records || bytes >= WIN_BYTES) {
+    if (W->n >= win_now || bytes >= WIN_BYTES) {
+      if (win_now < win_records) win_now *= 2;
       if (atomic_load(&R->n_ready) + 1 >= MAX_WINDOWS) { fprintf(stderr, "* FATAL est-fact: too many input windows\n"); exit(1); }
       close_window(R, W);
       W = NULL;
@@ -359,8 +362,16 @@ int main(int argc, char **argv) {
 
   const double t_io1 = ef_now();
   double wbusy = 0;
-  for (int k = 0; k < O_COUNT; ++k) { pthread_join(wth[k], NULL); fclose(R.f[k]); if (R.writer_busy[k] > wbusy) wbusy = R.writer_busy[k]; }
+  double tl_join[O_COUNT], tl_close[O_COUNT];
+  for (int k = 0; k < O_COUNT; ++k) { pthread_join(wth[k], NULL); tl_join[k] = ef_now(); fclose(R.f[k]); tl_close[k] = ef_now(); if (R.writer_busy[k] > wbusy) wbusy = R.writer_busy[k]; }
   t_io += ef_now() - t_io1 + wbusy;
+  if (!cfg.quiet) {
+    fprintf(stderr, "* INFO  tail (s after workers done), writer joined / file closed:");
+    for (int k = 0; k < O_COUNT; ++k) fprintf(stderr, " %.3f/%.3f", tl_join[k] - t_io1, tl_close[k] - t_io1);
+    fprintf(stderr, "; writer busy (s):");
+    for (int k = 0; k < O_COUNT; ++k) fprintf(stderr, " %.3f", R.writer_busy[k]);
+    fprintf(stderr, "\n");
+  }
   fprintf(finfo, "end\t%ld\n", (long)time(NULL));
   fclose(finfo);
 

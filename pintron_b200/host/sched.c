@@ -210,6 +210,7 @@ typedef struct group {
   struct worker *w;
   uint64_t deferred, grows;   /* fibers put off to a later batch; lane re-allocations */
   bool want_grow;             /* the last batch had to leave many fibers behind: take a larger slab before the next one */
+  void *stacks;               /* nslots x FIBER_STACK, one mapping (fiber_prepare_stack) */
 } group;
 
 typedef struct worker {
@@ -274,6 +275,30 @@ static void lane_grow(group *g, size_t arena_cap, int jobs_cap, size_t var_cap) 
   lane_refresh(g);
 }
 
+#define EF_STACK_CANARY 0x5ca1ab1e0ddba11ull
+static inline void fiber_check_stack(const fiber *f) {
+  if (f->stack && *(const uint64_t *)f->stack != EF_STACK_CANARY) {
+    fprintf(stderr, "* FATAL est-fact: a fiber overran its %u KB stack\n", FIBER_STACK >> 10);
+    abort();
+  }
+}
+#define EF_PF_FAR 8
+#define EF_PF_NEAR 3
+static inline void fiber_prefetch(const group *g, const fiber *n) {
+  if (n->state != F_RUNNABLE || !n->sp) return;
+  if (n->has_results && n->submitted && n->nreq) {                         /* its results: DMA-written lines of the lane, in no cache */
+    const char *r = (const char *)&g->res[(size_t)n->base * PC_RES_INTS];
+    const size_t bytes = MIN2((size_t)n->nreq * PC_RES_INTS * sizeof(int32_t), (size_t)512);
+    for (size_t o = 0; o < bytes; o += 64) __builtin_prefetch(r + o);
+  }
+  const char *sp = (const char *)n->sp;
+  for (int i = 0; i < 16; ++i) __builtin_prefetch(sp + 64 * i, 1);       /* the frames it resumes into (dp_wait and its callers) */
+  __builtin_prefetch(&n->task, 1);
+  __builtin_prefetch((const char *)&n->task + 64, 1);
+  if (n->reqs) __builtin_prefetch(n->reqs);
+  if (n->task.ar.cur) __builtin_prefetch(n->task.ar.cur, 1);
+}
+
 static void fiber_entry(void) {
   fiber *f = tl_fiber;
   worker *w = tl_worker;
@@ -290,9 +315,9 @@ static void fiber_entry(void) {
   __builtin_unreachable();
 }
 
-static void fiber_prepare_stack(fiber *f, void (*entry)(void));
+static void fiber_prepare_stack(group *g, fiber *f, void (*entry)(void));
 static void fiber_start(worker *w, group *g, fiber *f, size_t index) {
-  fiber_prepare_stack(f, fiber_entry);
+  fiber_prepare_stack(g, f, fiber_entry);
   f->index = index;
   f->yields = 0;
   f->state = F_RUNNABLE;
@@ -328,11 +353,19 @@ static void child_entry(void) {
   __builtin_unreachable();
 }
 
-static void fiber_prepare_stack(fiber *f, void (*entry)(void)) {
+static void fiber_prepare_stack(group *g, fiber *f, void (*entry)(void)) {
   if (!f->stack) {
-    f->stack = mmap(NULL, FIBER_STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
-    if (f->stack == MAP_FAILED) { perror("mmap fiber stack"); exit(1); }
-    mprotect(f->stack, 4096, PROT_NONE);
+    /* The stacks of a group are slices of ONE mapping (pages appear as they are touched).  One mmap + one mprotect per
+     * fiber meant ~10^5 VMAs per process: every one of those calls takes the process-wide mmap lock while sixteen
+     * workers ramp up, and the kernel walks them all again at exit.  Overflow is caught by a canary word at the low end
+     * of each slice, checked whenever the fiber hands control back (fiber_check_stack). */
+    if (!g->stacks) {
+      g->stacks = mmap(NULL, (size_t)g->nslots * FIBER_STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+      if (g->stacks == MAP_FAILED) { perror("mmap fiber stacks"); exit(1); }
+      madvise(g->stacks, (size_t)g->nslots * FIBER_STACK, MADV_NOHUGEPAGE);      /* a 2 MB page per touched stack would be zeroed in full */
+    }
+    f->stack = (char *)g->stacks + (size_t)(f - g->fibers) * FIBER_STACK;
+    *(uint64_t *)f->stack = EF_STACK_CANARY;
   }
 #if EF_FAST_SWITCH
   {
@@ -362,7 +395,7 @@ void dp_parallel_for(ef_task *T, int n, ef_par_fn body, void *user) {
       for (; next_slot < g->nslots; ++next_slot)
         if (g->fibers[next_slot].state == F_FREE) { c = &g->fibers[next_slot++]; break; }
     if (!c) { body(T, k, user); continue; }                  /* no child slot left (or a single iteration): inline */
-    fiber_prepare_stack(c, child_entry);
+    fiber_prepare_stack(g, c, child_entry);
     c->index = f->index; c->yields = 0; c->nreq = 0; c->has_results = false; c->grp = g;
     c->task.cfg = T->cfg; c->task.gen = T->gen;              /* dp_push looks at these; everything else goes through the parent's T */
     c->parent = f; c->pending_children = 0; c->par_fn = body; c->par_user = user; c->par_k = k; c->par_T = T;
@@ -564,6 +597,10 @@ again:
   any = false;
   for (int k = 0; k < g->nslots; ++k) {
     fiber *f = &g->fibers[k];
+    /* A thousand suspended ESTs per group do not fit the caches: by the time a fiber runs again its stack top, its task
+     * and its request list have been evicted.  Ask for them a few fibers ahead (the slots are visited in order). */
+    if (k + EF_PF_FAR < g->nslots) __builtin_prefetch(&g->fibers[k + EF_PF_FAR].sp);
+    if (k + EF_PF_NEAR < g->nslots) fiber_prefetch(g, &g->fibers[k + EF_PF_NEAR]);
     if (k >= g->nfibers) {                      /* child slots: run when runnable, never take a new EST */
       if (f->state == F_RUNNABLE) {
         tl_fiber = f;
@@ -574,6 +611,7 @@ again:
         swapcontext(&w->main_ctx, &f->ctx);
 #endif
         tl_fiber = NULL;
+        fiber_check_stack(f);
       }
       if (f->state == F_DONE) f->state = F_FREE;
       if (f->state == F_WAITING) any = true;
@@ -601,6 +639,7 @@ again:
       swapcontext(&w->main_ctx, &f->ctx);
 #endif
       tl_fiber = NULL;
+      fiber_check_stack(f);
       if (f->state == F_WAITING) break;       /* F_DONE: loop to pick the next item */
     }
     if (f->state == F_WAITING) any = true;
@@ -736,13 +775,13 @@ void sched_prepare(const ef_config *cfg, const ef_seq *gen) {
   mallopt(M_TRIM_THRESHOLD, 1 << 30);
   memset(&g_prep, 0, sizeof g_prep);
   g_prep.cfg = cfg; g_prep.gen = gen;
-  /* defaults from measurements on a 16-core B200 host: all cores but two (the engine's submission threads and the output
-   * writer need them), 1024 ESTs in flight per group */
+  /* defaults from measurements on a 16-core B200 host (tools/e2e_probe.py, profiles/r2_summary.md): one worker per core (the
+   * engine's submission loop and the writers float over the same cores: 16 workers beat 14), 768 ESTs in flight per group */
   const int ncpu = (int)sysconf(_SC_NPROCESSORS_ONLN);
-  int nthreads = cfg->threads > 0 ? cfg->threads : (ncpu > 4 ? ncpu - 2 : ncpu);
+  int nthreads = cfg->threads > 0 ? cfg->threads : ncpu;
   if (nthreads < 1) nthreads = 1;
   if (nthreads > PCE_MAX_SESSION_LANES / 2) nthreads = PCE_MAX_SESSION_LANES / 2;
-  int per_group = cfg->fibers > 0 ? cfg->fibers : 1024;
+  int per_group = cfg->fibers > 0 ? cfg->fibers : 768;       /* measured (C3, 16 and 4 threads): fewer leave the threads waiting for the engine, more outgrow the caches */
   const size_t lim = va_limit();
   if (lim) {
     mallopt(M_ARENA_MAX, 2);

@@ -22,10 +22,18 @@ open(os.path.join(work, "genomic.txt"), "wb").write(Synth(wl, reads=1).genome_fa
 open(os.path.join(work, "ests.txt"), "wb").write(ests_fasta_parallel(wl, reads, 0, reads, procs=max(1, (os.cpu_count() or 2) - 1)))
 print(f"probe: {wl} x {reads} reads in {work}, {os.cpu_count()} cores", flush=True)
 exe = os.path.join(ROOT, "pintron_b200", "bin", "est-fact")
-KEEP = ("scheduler:", "thread-seconds", "lane batches", "engine (", "per-EST code by phase", "@Timer Total", "@Timer IO", "device ms per op", "pc profile", "timeline", "round trips")
+variants = sys.argv[5].split(";") if len(sys.argv) > 5 else [""]      # extra est-fact flags, one set per variant; "ENV=val" words go to the environment
+KEEP = ("scheduler:", "tail (", "thread-seconds", "lane batches", "engine (", "per-EST code by phase", "@Timer Total", "@Timer IO", "device ms per op", "pc profile", "timeline", "round trips")
 
 
 def run(tag, args, env):
+    for f in os.listdir(work):                       # a fresh run directory, as pintron.py's STEP 2 has: only the two inputs
+        if f not in ("genomic.txt", "ests.txt"):
+            os.remove(os.path.join(work, f))
+    env = dict(env or os.environ)
+    for a in [a for a in args if "=" in a and not a.startswith("-")]:
+        env[a.split("=", 1)[0]] = a.split("=", 1)[1]
+    args = [a for a in args if not ("=" in a and not a.startswith("-"))]
     t0 = time.perf_counter()
     p = subprocess.run([exe, *args], cwd=work, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     dt = time.perf_counter() - t0
@@ -47,11 +55,13 @@ for th in threads:
         srv = U.Server(os.path.join(ROOT, "pintron_b200", "bin", "est-factd"), srv_dir)
         print(f"est-factd up in {time.perf_counter() - t0:.3f} s", flush=True)
         try:
-            for rep in range(3):
-                md5[("daemon", th, rep)] = run(f"est-factd threads={th or 'default'} run {rep}", ["--engine", "daemon", *targs], srv.env)
+            for var in variants:
+                for rep in range(int(os.environ.get("PROBE_REPS", "3"))):
+                    md5[("daemon", th, var, rep)] = run(f"est-factd threads={th or 'default'} [{var}] run {rep}", ["--engine", "daemon", *targs, *var.split()], srv.env)
             if os.environ.get("PROBE_PROFILE"):
                 run(f"est-factd threads={th or 'default'} PC_PROFILE", ["--engine", "daemon", *targs], dict(srv.env, PC_PROFILE="1"))
         finally:
             srv.stop()
-        print("   server log tail: " + " | ".join(srv.text().splitlines()[-4:])[:900], flush=True)
+        nl = 30 if os.environ.get("PROBE_PROFILE") or os.environ.get("PC_PROFILE_HOST") else 4
+        print("   server log tail: " + "\n      ".join(l[:700] for l in srv.text().splitlines()[-nl:]), flush=True)
 print("md5s identical across runs:", len(set(map(tuple, md5.values()))) == 1, flush=True)
