@@ -9,13 +9,13 @@ scaling; ESTs shard across ranks with no data-path collective, genome index repl
 
   value   device-resident leg.  One step = EVERY device batch the shipped est-fact really issues for R ESTs of this rank
           — the engine's merged lane batches exactly as it formed them in a real run (PC_CAPTURE, pintron_b200/replay.py),
-          all inputs already in HBM — submitted one after the other through pc_submit_device + pc_stream_sync, timed
-          with CUDA events on the library's stream, L2 flushed between steps.  Launch overheads of the real batching are
+          all inputs already in HBM — submitted in order through pc_submit_device + pc_stream_sync over two pc_streams taken
+          in turn (the engine's two submission loops), timed with CUDA events, L2 flushed between steps.  Launch overheads of the real batching are
           inside; host control flow and copies are not.
   e2e     the shipped est-fact PROGRAM on E ESTs per GPU exactly as pintron.py calls it (genomic.txt / ests.txt in the
           working directory, no arguments beyond execution knobs): process start, FASTA parsing, engine session (genome
           upload + index build), all host control flow, every H2D / D2H copy through pinned lanes, six output files;
-          wall clock of the process.  The GPU server est-factd is resident, as deployed (started before the warm-up);
+          wall clock of the process; every step starts in a directory that holds only the two inputs.  The GPU server est-factd is resident, as deployed (started before the warm-up);
           `e2e_cold` is one run with the engine inside the process (CUDA context creation inside the timed region).
           This is the number to hold against `--impl reference`.
   kernels the same jobs as ONE merged batch with per-op CUDA-event timers: GCUPS and INT-ALU fractions per kernel
@@ -394,11 +394,24 @@ def main():
         oa += (len(arena) + 32 + 15) & ~15; oj += len(jobs); ov += (var_bytes + 32 + 15) & ~15
     torch.cuda.synchronize()
 
+    # two pc_streams taken in turn, as the engine's two submission loops do (pc_engine.cu): batch k+1 is formed and enqueued
+    # while batch k runs; a stream is synchronised before it takes its next batch and at the end of the step
+    st2 = L.pc_stream_create(cu.ctx)
+    assert st2, L.pc_last_error()
+    sts = [cu.st, st2]
+
     def step_batches():
-        for a, ab, j, n, r, v, vb, hj, _keep in plan:
-            rc = L.pc_submit_device(cu.st, a, ab, j, hj, n, r, v, vb)
+        busy = [False, False]
+        for k, (a, ab, j, n, r, v, vb, hj, _keep) in enumerate(plan):
+            q = k & 1
+            if busy[q]:
+                assert L.pc_stream_sync(sts[q]) == 0, L.pc_last_error()
+            rc = L.pc_submit_device(sts[q], a, ab, j, hj, n, r, v, vb)
             assert rc == 0, L.pc_last_error()
-            assert L.pc_stream_sync(cu.st) == 0, L.pc_last_error()
+            busy[q] = True
+        for q in (0, 1):
+            if busy[q]:
+                assert L.pc_stream_sync(sts[q]) == 0, L.pc_last_error()
 
     # the same jobs as ONE batch (kernel-level leg)
     md_arena = torch.zeros(len(m_arena) + 16, dtype=torch.uint8, device="cuda")
@@ -598,7 +611,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": config_of(args.workload),
             "value_what": f"device-resident leg: the {len(batches)} device batches est-fact's engine really formed for {args.reads} ESTs per GPU "
-                          f"({n_jobs} jobs, {n_records} lane batches merged by the engine), inputs in HBM, pc_submit_device + pc_stream_sync per batch",
+                          f"({n_jobs} jobs, {n_records} lane batches merged by the engine), inputs in HBM, pc_submit_device + pc_stream_sync per batch over two pc_streams taken in turn (the engine's two submission loops)",
             "device_leg": {"ests_per_gpu_per_step": args.reads, "jobs_per_step": n_jobs, "device_batches_per_step": len(batches),
                            "lane_batches_per_step": n_records, "launches_per_step": launches_dev // args.steps, "jobs_per_op": jobs_per_op},
             "kernels": {"what": "the same jobs as ONE merged batch, per-op CUDA-event timers (single stream)", "ms_per_step": sum(ms_merged) / len(ms_merged),
@@ -639,6 +652,7 @@ def main():
         shutil.rmtree(srv_dir, ignore_errors=True)
     if world > 1:
         dist.destroy_process_group()
+    L.pc_stream_destroy(st2)
     cu.close()
 
 

@@ -164,7 +164,11 @@ void *pc_stream_cuda_stream(pc_stream *st);    /* the cudaStream_t, for callers 
 /* INT32 ALU micro-benchmark: lane-operations per second of independent add/min chains (the roofline
  * denominator for the DP kernels; SURVEY.md §8(d) asks for a measured figure). */
 double pc_measure_int_peak(pc_ctx *ctx);
-void pc_debug_dump(void);                     /* prints library-side timings to stderr when PC_PROFILE is set */
+void pc_debug_dump(void);                     /* prints library-side timings to stderr when PC_PROFILE (or PC_PROFILE_HOST: phase clock only) is set */
+/* How a submitting thread waits for its stream: 0 = the driver's spinning cudaStreamSynchronize (lowest latency, one core per
+ * submission loop), 1 = sleep on a cudaEventBlockingSync event (measured: 0.3-0.5 ms later per wake-up; nothing turns it on by default).
+ * PC_SYNC=spin|block in the environment wins over this call.  PC_SIDE_STREAMS=1..8: side streams a small batch forks over. */
+void pc_set_blocking_sync(int on);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,13 @@ struct ProfDump { ~ProfDump() { if (g_prof) fprintf(stderr, "[pc profile] check 
 #define PROF(slot, t0) do { if (g_prof_host) { double t1_ = now_s(); g_t[slot] += t1_ - (t0); (t0) = t1_; } } while (0)
 static thread_local char g_err[512] = "";
 
+/* How the submitting thread waits for its stream.  The driver's default spins: lowest latency, one core per submission loop.
+ * PC_SYNC=block / pc_set_blocking_sync(1) make it sleep on a blocking event instead — measured slower everywhere we tried
+ * (the wake-up costs 0.3-0.5 ms per batch), kept as a knob for boxes with fewer cores than GPUs. */
+static const int g_sync_env = [] { const char *v = getenv("PC_SYNC"); return !v ? -1 : (strcmp(v, "block") == 0 ? 1 : (strcmp(v, "spin") == 0 ? 0 : -1)); }();
+static int g_block_sync = g_sync_env > 0;
+extern "C" void pc_set_blocking_sync(int on) { if (g_sync_env < 0) g_block_sync = on != 0; }
+
 static int fail(int code, const char *fmt, const char *detail = "") {
   snprintf(g_err, sizeof g_err, fmt, detail);
   return code;
@@ -195,6 +202,7 @@ struct Pending {          // what pc_stream_sync needs to re-run jobs that ran o
 struct pc_stream {
   pc_ctx *ctx = nullptr;
   cudaStream_t s = nullptr;
+  cudaEvent_t ev_block = nullptr;           /* cudaEventBlockingSync: stream_wait() sleeps on it when g_block_sync is on */
   DevBuf arena, jobs, idx, res, var, pool, lcs_best;
   void *slab = nullptr;
   unsigned long long *d_pool_need = nullptr, *h_pool_need = nullptr;   /* device counter + pinned mirror */
@@ -302,7 +310,8 @@ extern "C" pc_stream *pc_stream_create(pc_ctx *c) {
     for (int i = 0; i < 7; ++i) bufs[i]->carve(cur, sizes[i]);
   }
   if (st->pin_idx.reserve(1u << 16) || st->pin_lcs.reserve(1u << 14)) { pc_stream_destroy(st); return nullptr; }
-  bool ok = cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  bool ok = cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&st->ev_block, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; k < pc_stream::NSIDE && ok; ++k)
     ok = cudaStreamCreateWithFlags(&st->side[k], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&st->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { fail(PC_E_CUDA, "%s", "pc_stream_create: side streams"); pc_stream_destroy(st); return nullptr; }
@@ -323,6 +332,7 @@ extern "C" void pc_stream_destroy(pc_stream *st) {
   for (auto &e : st->ev_pending) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
   for (auto e : st->ev_free) cudaEventDestroy(e);
   if (st->ev_fork) cudaEventDestroy(st->ev_fork);
+  if (st->ev_block) cudaEventDestroy(st->ev_block);
   for (int k = 0; k < pc_stream::NSIDE; ++k) { if (st->ev_join[k]) cudaEventDestroy(st->ev_join[k]); if (st->side[k]) cudaStreamDestroy(st->side[k]); }
   cudaStreamDestroy(st->s);
   delete st;
@@ -374,6 +384,14 @@ extern "C" int pc_stream_op_time(pc_stream *st, int op, double *ms, uint64_t *la
   return 0;
 }
 
+static cudaError_t stream_wait(pc_stream *st) {
+  if (g_block_sync && st->ev_block) {
+    const cudaError_t e = cudaEventRecord(st->ev_block, st->s);
+    return e != cudaSuccess ? e : cudaEventSynchronize(st->ev_block);
+  }
+  return cudaStreamSynchronize(st->s);
+}
+
 static cudaEvent_t get_event(pc_stream *st) {
   if (!st->ev_free.empty()) { cudaEvent_t e = st->ev_free.back(); st->ev_free.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -413,7 +431,7 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
     uint32_t *h_invalid = st->pin_seg.p + NSEG * (sizeof(PcSegStat) / 4);
     CU(cudaMemcpyAsync(h_seg, d_seg, sizeof(PcSegStat) * NSEG, cudaMemcpyDeviceToHost, st->s));
     CU(cudaMemcpyAsync(h_invalid, d_work + 3 * NB + 1, 4, cudaMemcpyDeviceToHost, st->s));
-    CU(cudaStreamSynchronize(st->s));
+    CU(stream_wait(st));
     if (*h_invalid) return fail(PC_E_ARG, "%s", "pc_submit: a job references bytes outside its buffers (or has an unknown op)");
     for (int sg = 0; sg < NSEG; ++sg) { seg[sg].n = h_seg[sg].n; seg[sg].max_a = h_seg[sg].max_a; seg[sg].max_b = h_seg[sg].max_b; seg[sg].max_t = h_seg[sg].max_t; seg[sg].lcs_blocks = h_seg[sg].lcs_blocks; }
     PROF(3, tp);
@@ -719,7 +737,7 @@ extern "C" int pc_stream_sync(pc_stream *st) {
   if (!st) return fail(PC_E_ARG, "%s", "pc_stream_sync: null stream");
   CU(cudaSetDevice(st->ctx->device));
   double tp = g_prof_host ? now_s() : 0;
-  CU(cudaStreamSynchronize(st->s));
+  CU(stream_wait(st));
   PROF(6, tp);
   if (g_prof) drain_events(st);
   if (g_prof && st->last_slow_count) {

@@ -244,7 +244,16 @@ extern "C" pc_engine *pc_engine_create(const int *devices, int ndev, size_t segm
   pc_engine *e = new pc_engine();
   const char *env = getenv("PC_ENGINE_SEGMENT_MB");
   if (segment_bytes == 0) segment_bytes = (env && atol(env) > 0 ? (size_t)atol(env) : 384) << 20;
-  int nthreads = 1;          // one submission loop keeps a B200 fed (side streams overlap the kernels of a batch); measured: more only split the batches
+  // The submission loops wait with the driver's spinning synchronize.  Sleeping on a blocking event instead (PC_SYNC=block,
+  // pc_set_blocking_sync) was measured on the 16-core box and under a 4-core budget (taskset, the share of one GPU of an 8-GPU
+  // box): 1.1-1.4 ms per batch instead of 0.5-0.8, whole program 20-30 % slower in both settings (profiles/r2_summary.md).
+  // Submission loops per GPU.  A batch is latency-bound (copies in, ~20 small kernels, copies out: 0.5-0.8 ms whatever its
+  // size), so a second loop that forms the next batch while the first one waits for its stream cuts the queueing time of a
+  // lane: measured on the 16-core box 111-114 k -> 119-120 k ESTs/s; three or four loops only split the batches further
+  // (110-118 k).  Each loop spins on a core while it waits, so with fewer than 8 cores per GPU one loop is better (4-core
+  // budget: 48 k vs 43-46 k ESTs/s).  PC_ENGINE_THREADS overrides.
+  const long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+  int nthreads = ncpu > 0 && ncpu / ndev >= 8 ? 2 : 1;
   if (const char *t = getenv("PC_ENGINE_THREADS")) if (atoi(t) >= 1 && atoi(t) <= 8) nthreads = atoi(t);
   for (int i = 0; i < ndev; ++i) {
     Gpu *g = new Gpu();

@@ -358,7 +358,7 @@ static void fiber_prepare_stack(group *g, fiber *f, void (*entry)(void)) {
     /* The stacks of a group are slices of ONE mapping (pages appear as they are touched).  One mmap + one mprotect per
      * fiber meant ~10^5 VMAs per process: every one of those calls takes the process-wide mmap lock while sixteen
      * workers ramp up, and the kernel walks them all again at exit.  Overflow is caught by a canary word at the low end
-     * of each slice, checked whenever the fiber hands control back (fiber_check_stack). */
+     * of each slice, checked when the fiber's EST is done (fiber_check_stack). */
     if (!g->stacks) {
       g->stacks = mmap(NULL, (size_t)g->nslots * FIBER_STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
       if (g->stacks == MAP_FAILED) { perror("mmap fiber stacks"); exit(1); }
@@ -611,9 +611,8 @@ again:
         swapcontext(&w->main_ctx, &f->ctx);
 #endif
         tl_fiber = NULL;
-        fiber_check_stack(f);
       }
-      if (f->state == F_DONE) f->state = F_FREE;
+      if (f->state == F_DONE) { fiber_check_stack(f); f->state = F_FREE; }
       if (f->state == F_WAITING) any = true;
       continue;
     }
@@ -639,7 +638,7 @@ again:
       swapcontext(&w->main_ctx, &f->ctx);
 #endif
       tl_fiber = NULL;
-      fiber_check_stack(f);
+      if (f->state == F_DONE) fiber_check_stack(f);       /* once per EST: the canary's line is in no cache */
       if (f->state == F_WAITING) break;       /* F_DONE: loop to pick the next item */
     }
     if (f->state == F_WAITING) any = true;

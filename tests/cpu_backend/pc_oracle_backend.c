@@ -55,6 +55,7 @@ void pc_host_free(void *p) { free(p); }
 int pc_stream_sync(pc_stream *s) { (void)s; return 0; }
 uint64_t pc_launch_count(void) { return g_jobs; }
 void pc_debug_dump(void) {}
+void pc_set_blocking_sync(int on) { (void)on; }
 
 /* ---- optional memo of job results (developer tool: PC_ORACLE_MEMO=<file>) ---------------------------------------------
  * The oracle is orders of magnitude slower than the device, so a profile of the HOST code over this backend is all
