@@ -80,7 +80,8 @@ typedef struct pc_job {
   uint32_t b_off, b_len;  /* genome-side string (BORDERS: t; LCS: s1 = the long one; unused for SEED) */
   int32_t  p0, p1, p2;    /* KBAND: p0 = upper bound k.  BORDERS: p0 = max_errs, p1 = min_p_cut, p2 = max_p_cut.
                              SEED: p0 = min factor length in force (config + inc_pairing_len); p1 = 0 (vertex set only) or
-                             PC_SEED_BUILD_MEG (b = one struct pc_meg_cfg in the arena). */
+                             PC_SEED_BUILD_MEG (b = one struct pc_meg_cfg in the arena; p2 = largest vertex set built on the
+                             device, 0 = any). */
   uint32_t out_off;       /* byte offset of this job's variable output inside var_out (4-aligned for SEED) */
   uint32_t out_cap;       /* ALIGN/GAP: bytes (>= a_len + b_len); SEED: capacity in (p,t,l) triples (= 12-byte units) */
 } pc_job;
@@ -94,6 +95,11 @@ typedef struct pc_job {
  *   then nv x (p, t, l)  (source: INT32_MIN, INT32_MIN, 200; sink: INT32_MAX - 200, INT32_MAX - 200, 200),
  *   then nv adjacency counts, then the ne adjacency targets (vertex numbers), list by list in list order. */
 #define PC_SEED_BUILD_MEG 1
+/* p2 > 0 on such a job: build the graph on the device only when the vertex set has at most p2 pairings; for a larger one
+ * the job answers res[3] = PC_SEED_VERTEX_SET_ONLY, res[1] = the number of (p, t, l) triples, written at out_off
+ * (PC_E_OUTCAP + that number when they do not fit), and the caller builds the graph from them (one sequential walk per
+ * graph: quadratic in the vertices, milliseconds for one GPU lane on an mRNA, microseconds on a host core). */
+#define PC_SEED_VERTEX_SET_ONLY 1
 typedef struct pc_meg_cfg {
   int32_t min_intron_length, max_intron_length;          /* --min-intron-length, --max-intron-length (0 = unlimited) */
   uint32_t max_pairings_in_MEG;                          /* --max-pairings-in-CMEG */

@@ -215,7 +215,22 @@ __device__ void meg_one(const PcDevBatch &B, WarpPool &wp, int w, int lane, int3
       __syncwarp();
     }
   __syncwarp();
+  // Large vertex sets (mRNAs of several kbp: hundreds of pairings, build_edge_set alone is quadratic) would keep this one
+  // lane — and the batch that waits for it — busy for tens of milliseconds; a host core does the same walk in well under
+  // one.  Above the caller's limit (p2 > 0) the job answers with the vertex set only (res[3] = 1): the whole warp copies
+  // the triples out and the caller runs the very same meg_core.h on them.
+  if (job->p2 > 0 && ntri > job->p2) {
+    if ((uint32_t)ntri > job->out_cap) { if (lane == 0) { res[0] = PC_E_OUTCAP; res[1] = ntri; } }
+    else {
+      int32_t *out = (int32_t *)(B.var_out + job->out_off);
+      for (int i = lane; i < nw; i += 32) out[i] = base[i];
+      if (lane == 0) { res[0] = PC_OK; res[1] = ntri; res[3] = PC_SEED_VERTEX_SET_ONLY; }
+    }
+    __syncwarp();
+    return;
+  }
   if (lane == 0) {
+    res[3] = 0;
     const unsigned long long tri_bytes = (12ull * (unsigned long long)ntri + 255ull) & ~255ull;
     pc_meg_cfg cfg;
     const uint8_t *cb = B.arena + job->b_off;

@@ -1,12 +1,15 @@
 /* meg.c — the Maximal Embedding Graph of one EST.  The graph is BUILT ON THE DEVICE: one PC_OP_SEED job with
  * PC_SEED_BUILD_MEG runs build_vertex_set, build_edge_set, simplify_meg, transitive_reduction, compact_short_edges and
  * is_too_complex (reference src/compute-est-fact.c:90-152, src/max-emb-graph.c:217-672, src/meg-simplification.c:52-632;
- * ours: csrc/k_seed.cu + csrc/meg_core.h).  What is left here: asking for it (and again with a longer pairing length while
+ * ours: csrc/k_seed.cu + csrc/meg_core.h).  Vertex sets above EF_MEG_DEVICE_MAX pairings (mRNAs of several kbp) come back
+ * as they are and the same meg_core.h walks them here: the walk is sequential and quadratic, one GPU lane needs tens of
+ * milliseconds for what a host core does in well under one, and the whole batch would wait for it.  What is left here: asking for it (and again with a longer pairing length while
  * the device says "too complex"), turning the returned record into the pointer graph the embedding enumeration walks, and
  * the text of megs.txt / processed-megs.txt / meg-edges.txt (src/io-meg.c:147-190, src/max-emb-graph.c:677-707).
  */
 #include "ef.h"
 #include <pthread.h>
+#include "../csrc/meg_core.h"      /* the MEG core of the device, plain C: the host runs it on the vertex sets the device hands back */
 
 void meg_stats(const ef_meg *M, size_t *pairings, size_t *edges) { *pairings = M->np; *edges = M->ne; }
 
@@ -34,6 +37,31 @@ static const pc_meg_cfg *meg_cfg(const ef_config *c) {
 /* One device job per attempt: vertex set, edges, simplification, transitive reduction, compaction and the complexity test
  * all run on the GPU (PC_OP_SEED with PC_SEED_BUILD_MEG; csrc/k_seed.cu + csrc/meg_core.h); what comes back is the
  * finished graph in list order.  The "too complex" retry (compute-est-fact.c:131-146) asks again with a longer pairing. */
+#define EF_MEG_DEVICE_MAX_DEFAULT 32      /* measured: C3 does not care (16 .. 64 .. all on the device within noise), C4 prefers the low end (24: 4.3 k reads/s, 64: 3.6 k, all on the device: 0.28 k) */
+static int meg_device_max(void) {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("EF_MEG_DEVICE_MAX"); v = e && atoi(e) >= 0 ? atoi(e) : EF_MEG_DEVICE_MAX_DEFAULT; }      /* 0 = always on the device */
+  return v;
+}
+
+/* the device's MEG record (include/pintron_cuda.h) from a vertex set, on this core; caller frees */
+static int32_t *meg_record_on_host(const int32_t *tri, int ntri, int est_len, int l, const pc_meg_cfg *mc) {
+  for (long long nints = (1 << 15) + 256ll * ntri;; nints *= 2) {
+    int *mem = malloc(sizeof(int) * (size_t)nints);
+    if (!mem) { fprintf(stderr, "* FATAL est-fact: out of memory\n"); exit(1); }
+    mg_graph g;
+    mg_init(&g, mem, nints, tri, ntri);
+    const int retry = g.err ? 0 : mg_build(&g, est_len, l, mc);
+    if (g.err == MG_E_SCRATCH) { free(mem); continue; }
+    if (g.err) { fprintf(stderr, "* FATAL est-fact: cyclic embedding graph\n"); exit(1); }
+    int32_t *rec = malloc(sizeof(int32_t) * (size_t)(mg_record_words(&g) + 4));
+    if (!rec) { fprintf(stderr, "* FATAL est-fact: out of memory\n"); exit(1); }
+    mg_write_record(&g, retry, rec);
+    free(mem);
+    return rec;
+  }
+}
+
 ef_meg *meg_build(ef_task *T, const ef_seq *est, unsigned *inc) {
   const ef_config *c = T->cfg;
   const pc_meg_cfg *mc = meg_cfg(c);
@@ -41,12 +69,18 @@ ef_meg *meg_build(ef_task *T, const ef_seq *est, unsigned *inc) {
   int cap = 256;       /* 12-byte units; the kernel reports the needed count when this is too small */
   for (;;) {
     const int l = (int)(c->min_factor_len + *inc);
-    const int h = dp_push(PC_OP_SEED, S_(est->seq, est->len), S_((const char *)mc, (int)sizeof *mc), l, PC_SEED_BUILD_MEG, 0, cap);
+    const int h = dp_push(PC_OP_SEED, S_(est->seq, est->len), S_((const char *)mc, (int)sizeof *mc), l, PC_SEED_BUILD_MEG, meg_device_max(), cap);
     dp_wait();
     const int32_t *r = dp_res(h);
     if (r[0] == PC_E_OUTCAP) { cap = r[1] + 16; continue; }
     const int32_t *rec = (const int32_t *)dp_var(h);
-    if (rec[2]) { ++*inc; continue; }
+    int32_t *own = NULL;
+    if (r[3] == PC_SEED_VERTEX_SET_ONLY) {
+      ef_phase(EF_PH_MEG);
+      rec = own = meg_record_on_host(rec, r[1], est->len, l, mc);
+      ef_phase(EF_PH_SEED);
+    }
+    if (rec[2]) { ++*inc; free(own); continue; }
     ef_phase(EF_PH_MEG);
     const int nv = rec[0], ne = rec[1];
     const int32_t *ptl = rec + 4, *cnt = ptl + 3 * nv, *adj = cnt + nv;
@@ -63,6 +97,7 @@ ef_meg *meg_build(ef_task *T, const ef_seq *est, unsigned *inc) {
       for (int k = 0; k < cnt[x]; ++k) *E++ = &P[*adj++];
       M->flat[x] = q;
     }
+    free(own);
     ef_phase(ph_);
     return M;
   }

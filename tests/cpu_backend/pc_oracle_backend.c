@@ -192,6 +192,12 @@ int pc_submit(pc_stream *st, const uint8_t *arena, size_t arena_bytes, const pc_
           long cap = 1024, n;
           int *tri = malloc(sizeof(int) * 3 * (size_t)cap);
           while ((n = po_seed(c->genome, (long)c->len, a, la, j->p0, c->rate, tri, cap)) < 0) { cap = -n + 16; tri = realloc(tri, sizeof(int) * 3 * (size_t)cap); }
+          if (j->p2 > 0 && n > (long)j->p2) {                  /* the device's rule: a large vertex set goes back as it is */
+            if (n > (long)j->out_cap) { r[0] = PC_E_OUTCAP; r[1] = (int32_t)n; }
+            else { memcpy(out, tri, sizeof(int) * 3 * (size_t)n); r[1] = (int32_t)n; r[3] = PC_SEED_VERTEX_SET_ONLY; }
+            free(tri);
+            break;
+          }
           long long nints = 1 << 16;
           for (;;) {
             int *mem = malloc(sizeof(int) * (size_t)nints);

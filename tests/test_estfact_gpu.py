@@ -66,6 +66,17 @@ def test_scheduling_and_sharding_do_not_change_bytes(gpu_bin, tmp_path):
         assert cat[f] == open(whole / f, "rb").read(), f
 
 
+@pytest.mark.parametrize("limit", ["0", "1", "12"])
+def test_meg_built_on_either_side_gives_the_same_bytes(gpu_bin, limit, tmp_path):
+    """EF_MEG_DEVICE_MAX: 0 = every graph by the SEED kernel's MEG stage, 1 = every graph on the host from the vertex set the
+    kernel hands back (PC_SEED_VERTEX_SET_ONLY), 12 = both in one run.  Same bytes as the reference either way."""
+    env = dict(os.environ, EF_MEG_DEVICE_MAX=limit)
+    for case in ("test-CPB2", "test_gtf7"):
+        d = tmp_path / case
+        d.mkdir()
+        U.check_case(gpu_bin, case, str(d), "--quiet", env=env)
+
+
 @pytest.mark.parametrize("opts", U.OPTION_SETS, ids=lambda o: " ".join(o))
 def test_option_variants_vs_reference_binary(gpu_bin, opts, tmp_path):
     if not os.path.exists(U.REF_BIN):

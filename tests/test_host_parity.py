@@ -216,6 +216,18 @@ def test_streaming_windows_and_back_pressure_keep_the_bytes(cpu_bin, tmp_path):
         U.check_case(cpu_bin, case, str(d), *extra, env=env)
 
 
+@pytest.mark.parametrize("limit", ["0", "1", "12"])
+def test_meg_built_on_either_side_gives_the_same_bytes(cpu_bin, limit, tmp_path):
+    """Vertex sets above EF_MEG_DEVICE_MAX pairings come back from the SEED job as they are and host/meg.c walks the same
+    csrc/meg_core.h over them (include/pintron_cuda.h: PC_SEED_VERTEX_SET_ONLY).  0 = every graph by the SEED job, 1 = every
+    graph on the host, 12 = both in one run; megs.txt / meg-edges.txt / everything downstream must not change."""
+    env = dict(os.environ, EF_MEG_DEVICE_MAX=limit)
+    for case in ("test-CPB2", "test-AMBN"):
+        d = tmp_path / case
+        d.mkdir()
+        U.check_case(cpu_bin, case, str(d), "--quiet", "--threads", "3", env=env)
+
+
 def test_counting_reference_is_the_reference(tmp_path):
     """oracle/_ref/est-fact-cells (the reference sources as a PIC library + the counting interposers of oracle/ref_cells.c)
     writes the reference's bytes and counts cells for every routine bench.py divides GCUPS from."""
