@@ -39,6 +39,7 @@ __attribute__((naked, noinline)) static void ctx_switch(void **save_sp, void *lo
 #include <malloc.h>
 
 #define FIBER_STACK (512u << 10)
+#define EF_MAX_GROUPS 4
 
 double ef_now(void) {
   struct timeval tv;
@@ -216,7 +217,7 @@ typedef struct group {
 typedef struct worker {
   pthread_t th;
   int id, device;
-  group g[2];
+  group g[EF_MAX_GROUPS];     /* g_ngroups of them in use */
   ucontext_t main_ctx;
   void *main_sp;
   const ef_config *cfg;
@@ -232,6 +233,11 @@ static ef_next_fn g_next;            /* where items come from (main.c: the windo
 static void *g_next_user;
 static _Atomic int g_no_more;         /* the source has said -1 */
 static int g_nthreads = 1;
+/* Fiber groups (= engine lanes) per worker thread.  While the requests of one group are with the engine the thread runs the
+ * others; with G groups a batch has the run time of G - 1 groups to come back before the thread would wait for it, at the
+ * same number of suspended ESTs per thread (the cache footprint that decides the cost per EST).  EF_GROUPS=2..4. */
+#define EF_GROUPS_DEFAULT 2
+static int g_ngroups = EF_GROUPS_DEFAULT;
 static __thread fiber *tl_fiber;
 static __thread worker *tl_worker;
 static uint64_t g_batches, g_jobs, g_h2d, g_d2h, g_deferred, g_grows;
@@ -667,24 +673,29 @@ static void *worker_main(void *arg) {
   worker *w = arg;
   tl_worker = w;
   const double tw0 = ef_now();
-  for (int i = 0; i < 2; ++i) { w->g[i].w = w; lane_refresh(&w->g[i]); }
+  const int ng = g_ngroups;
+  for (int i = 0; i < ng; ++i) { w->g[i].w = w; lane_refresh(&w->g[i]); }
   const double tw1 = ef_now();
-  bool alive[2] = {true, true};
-  while (alive[0] || alive[1]) {
-    for (int i = 0; i < 2; ++i)
+  bool alive[EF_MAX_GROUPS];
+  for (int i = 0; i < ng; ++i) alive[i] = true;
+  for (;;) {
+    bool any_alive = false;
+    for (int i = 0; i < ng; ++i) {
       if (alive[i] || w->g[i].pending) alive[i] = run_group(w, &w->g[i]);
-    if (!alive[0] && !alive[1] && !atomic_load(&g_no_more)) {      /* nothing in flight, but the reader may still deliver */
-      struct timespec ts = {0, 100 * 1000};
-      nanosleep(&ts, NULL);
-      alive[0] = true;
+      any_alive |= alive[i];
     }
+    if (any_alive) continue;
+    if (atomic_load(&g_no_more)) break;
+    struct timespec ts = {0, 100 * 1000};                          /* nothing in flight, but the reader may still deliver */
+    nanosleep(&ts, NULL);
+    alive[0] = true;
   }
   const double tw2 = ef_now();
   /* No tear-down: est-fact exits right after the last EST, and freeing pinned / device memory (two dozen streams,
    * each call synchronising the device) only delays the threads that are still working. */
   pthread_mutex_lock(&g_stat_mu);
   g_batches += w->batches; g_jobs += w->jobs; g_gpu_wait += w->gpu_wait; g_h2d += w->h2d; g_d2h += w->d2h;
-  g_deferred += w->g[0].deferred + w->g[1].deferred; g_grows += w->g[0].grows + w->g[1].grows;
+  for (int i = 0; i < ng; ++i) { g_deferred += w->g[i].deferred; g_grows += w->g[i].grows; }
   g_t_fibers += w->t_fibers; g_t_gather += w->t_gather; g_t_submit += w->t_submit;
   g_t_init += tw1 - tw0; g_t_fini += ef_now() - tw2;
   g_t_end_sum += tw2; if (g_t_end_min == 0 || tw2 < g_t_end_min) g_t_end_min = tw2;
@@ -748,7 +759,7 @@ static void *prepare_main(void *arg) {
     int nth = 0;
     for (int i = 0; i < nthreads; ++i) if (i % nuse == d) ++nth;
     if (nth == 0) continue;
-    req.nlanes = 2 * nth;
+    req.nlanes = g_ngroups * nth;
     req.device = d;
     char err[768];
     ef_conn *c = efc_open(cfg->engine, g_prep.use, g_prep.use[0] >= 0 ? nuse : 0, &req, err, sizeof err);
@@ -779,13 +790,14 @@ void sched_prepare(const ef_config *cfg, const ef_seq *gen) {
   const int ncpu = (int)sysconf(_SC_NPROCESSORS_ONLN);
   int nthreads = cfg->threads > 0 ? cfg->threads : ncpu;
   if (nthreads < 1) nthreads = 1;
-  if (nthreads > PCE_MAX_SESSION_LANES / 2) nthreads = PCE_MAX_SESSION_LANES / 2;
+  { const char *e = getenv("EF_GROUPS"); g_ngroups = e && atoi(e) >= 2 && atoi(e) <= EF_MAX_GROUPS ? atoi(e) : EF_GROUPS_DEFAULT; }
+  if (nthreads > PCE_MAX_SESSION_LANES / g_ngroups) nthreads = PCE_MAX_SESSION_LANES / g_ngroups;
   int per_group = cfg->fibers > 0 ? cfg->fibers : 768;       /* measured (C3, 16 and 4 threads): fewer leave the threads waiting for the engine, more outgrow the caches */
   const size_t lim = va_limit();
   if (lim) {
     mallopt(M_ARENA_MAX, 2);
     const size_t budget = lim / 3 / FIBER_STACK * 2 / 3;       /* EST fibers in total (child fibers add half as many again) */
-    if ((size_t)per_group * 2 * (size_t)nthreads > budget) per_group = (int)MAX2((size_t)8, budget / (2 * (size_t)nthreads));
+    if ((size_t)per_group * (size_t)g_ngroups * (size_t)nthreads > budget) per_group = (int)MAX2((size_t)8, budget / ((size_t)g_ngroups * (size_t)nthreads));
   }
   g_prep.nthreads = nthreads; g_prep.per_group = per_group;
   if (pthread_create(&g_prep.th, NULL, prepare_main, NULL)) { perror("pthread_create"); exit(1); }
@@ -808,7 +820,7 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_next_f
     nthreads = n_items ? (int)n_items : 1;
   }
   int per_group = g_prep.per_group;
-  if ((size_t)per_group * 2 * (size_t)nthreads > n_items) per_group = (int)(n_items / (2 * (size_t)nthreads)) + 1;
+  if ((size_t)per_group * (size_t)g_ngroups * (size_t)nthreads > n_items) per_group = (int)(n_items / ((size_t)g_ngroups * (size_t)nthreads)) + 1;
   g_next = next; g_next_user = user;
   atomic_store(&g_no_more, 0);
   g_nthreads = nthreads;
@@ -819,9 +831,9 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_next_f
     worker *w = &ws[i];
     w->id = i; w->device = use[i % nuse];
     w->cfg = cfg; w->gen = gen; w->fn = fn; w->user = user;
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < g_ngroups; ++k) {
       w->g[k].conn = g_prep.conns[i % nuse];
-      w->g[k].lane_k = 2 * (i / nuse) + k;
+      w->g[k].lane_k = g_ngroups * (i / nuse) + k;
       w->g[k].nfibers = per_group;
       w->g[k].nslots = per_group + MAX2(32, per_group / 2);       /* child fibers of dp_parallel_for */
       w->g[k].fibers = calloc((size_t)w->g[k].nslots, sizeof(fiber));
@@ -843,10 +855,10 @@ int sched_run(const ef_config *cfg, const ef_seq *gen, size_t n_items, ef_next_f
     g_prep.conns[d] = NULL;
   }
   if (!cfg->quiet)
-    fprintf(stderr, "* INFO  scheduler: %d thread(s) x 2 x %d fibers on %d GPU(s), engine: %s; engine session(s) open after %.3f s (%.3f s of it still to wait for), workers %.3f s "
+    fprintf(stderr, "* INFO  scheduler: %d thread(s) x %d x %d fibers on %d GPU(s), engine: %s; engine session(s) open after %.3f s (%.3f s of it still to wait for), workers %.3f s "
             "(set-up %.3f s per thread on average), session close %.3f s; "
             "%llu fiber deferrals, %llu lane re-allocations; threads idle at the end %.3f s on average (first done %.3f s before the last)\n",
-            nthreads, per_group, nuse, g_engine_mode, g_prep.secs, ts1 - ts0, ts2 - ts1, g_t_init / nthreads, ef_now() - ts2,
+            nthreads, g_ngroups, per_group, nuse, g_engine_mode, g_prep.secs, ts1 - ts0, ts2 - ts1, g_t_init / nthreads, ef_now() - ts2,
             (unsigned long long)g_deferred, (unsigned long long)g_grows, ts2 - g_t_end_sum / nthreads, ts2 - g_t_end_min);
   return 0;
 }
