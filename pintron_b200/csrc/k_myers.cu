@@ -24,6 +24,7 @@ __device__ __forceinline__ uint32_t my_load4_dev(const uint8_t *p) {
 }
 __shared__ int8_t my_symtab[256];
 #include "myers_core.h"
+#include "align_core.h"
 
 namespace {
 
@@ -90,7 +91,58 @@ void launch_myers(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count
   PC_COUNT_LAUNCH(1);
 }
 
+// ---- compute_alignment, one job per thread (align_core.h) -----------------------------------------------------------
+// The traceback words (two per genome column and 64-row block) go to the stream's scratch pool, interleaved by thread:
+// word r of thread t lives at pool[t + r * T] (T = threads of the grid), so a warp's 32 jobs store 256 contiguous bytes
+// per word.  A job whose columns do not fit its share of the pool, whose EST is longer than 320 nt or that holds a byte
+// outside ACGTacgtNn is listed for the wavefront kernel (op_align, k_dp.cu), like the jobs k_myers cannot answer.
+template <int MAXW>
+__device__ __forceinline__ uint32_t align_dispatch(const uint8_t *pat, int n, const uint8_t *txt, int m, unsigned long long *peq, int stride,
+                                                   unsigned long long *tb, long long tbs, long long cap, uint8_t *ops, int *k) {
+  const int W = (n + 63) >> 6;
+  if (W <= 1) return my_align<1>(pat, n, txt, m, peq, stride, tb, tbs, cap, ops, k);
+  if (W == 2) return my_align<2>(pat, n, txt, m, peq, stride, tb, tbs, cap, ops, k);
+  if (W == 3) return my_align<3>(pat, n, txt, m, peq, stride, tb, tbs, cap, ops, k);
+  if (W == 4) return my_align<4>(pat, n, txt, m, peq, stride, tb, tbs, cap, ops, k);
+  return my_align<MY_MAXW>(pat, n, txt, m, peq, stride, tb, tbs, cap, ops, k);
+}
+
+__global__ void __launch_bounds__(MY_TPB) k_align_bp(PcDevBatch B, uint32_t *slow_list, uint32_t *slow_count) {
+  __shared__ unsigned long long peq[MY_NSYM * MY_MAXW * MY_TPB];
+  for (int c = threadIdx.x; c < 256; c += MY_TPB) my_symtab[c] = (int8_t)my_sym_switch((uint8_t)c);
+  __syncthreads();
+  const long long T = (long long)gridDim.x * MY_TPB;
+  const long long tid = (long long)blockIdx.x * MY_TPB + threadIdx.x;
+  const long long cap = (long long)(B.pool_cap / (16ull * (unsigned long long)T));      // (column, block) entries per thread
+  unsigned long long *tb = (unsigned long long *)B.pool + tid;
+  for (long long w = tid; w < B.n; w += T) {
+    const uint32_t ji = B.idx[w];
+    const pc_job *job = B.jobs + ji;
+    int32_t *res = B.res + (size_t)ji * PC_RES_INTS;
+    const uint8_t *a = B.arena + job->a_off;
+    const uint8_t *b = ((job->flags & PC_B_IN_GENOME) ? B.genome : B.arena) + job->b_off;
+    const int n = (int)job->a_len, m = (int)job->b_len;
+    if ((uint32_t)(n + m) > job->out_cap) { res[0] = PC_E_OUTCAP; continue; }
+    bool slow = n > 64 * MY_MAXW;
+    if (!slow) {
+      int k = 0;
+      const uint32_t d = align_dispatch<MY_MAXW>(a, n, b, m, peq + threadIdx.x, MY_TPB, tb, T, cap, B.var_out + job->out_off, &k);
+      if (d == MY_UNSUPPORTED || d == MY_NOSPACE) slow = true;
+      else { res[0] = PC_OK; res[1] = (int32_t)d; res[2] = k; }
+    }
+    if (slow) slow_list[atomicAdd(slow_count, 1u)] = ji;
+  }
+}
+
 }  // namespace
+
+// compute_alignment jobs of one segment: bit-parallel kernel first, the rest through slow_list to the wavefront kernel
+void pc_launch_align_bp(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count) {
+  const int needed = (B.n + MY_TPB - 1) / MY_TPB;
+  const int grid = needed < 2 * sm_count ? needed : 2 * sm_count;
+  k_align_bp<<<grid < 1 ? 1 : grid, MY_TPB, 0, s>>>(B, slow_list, slow_count);
+  PC_COUNT_LAUNCH(1);
+}
 
 // op = PC_OP_EDIT or PC_OP_KBAND.  cls = length class of the segment (pc_job_class: shorter string <= 64 / 128 / 320
 // letters -> 1 / 2 / 5 words per column).  slow_list (B.n entries) / slow_count (zeroed by the caller) receive the job indices

@@ -18,6 +18,8 @@ static const bool g_prof = getenv("PC_PROFILE") != nullptr;
 static const bool g_prof_host = g_prof || getenv("PC_PROFILE_HOST") != nullptr;      /* only the host-side phase clock: side streams stay on */
 /* how many side streams a small batch forks over (launch_selected): every (op, class) kernel of such a batch is bound by the
  * latency of its longest job, so the batch takes the longest chain on one stream, not the sum.  PC_SIDE_STREAMS=1..8. */
+/* compute_alignment through the bit-parallel kernel (k_myers.cu: k_align_bp); PC_ALIGN_BP=0 keeps every job on the wavefront kernel */
+static const bool g_align_bp = [] { const char *v = getenv("PC_ALIGN_BP"); return !v || atoi(v) != 0; }();
 static const int g_side_streams = [] { const char *v = getenv("PC_SIDE_STREAMS"); const int n = v ? atoi(v) : 0; return n >= 1 && n <= 8 ? n : 8; }();
 #define PC_MULTI_STREAM_MAX ((size_t)1 << 18)        /* batches below this many jobs run their segments on side streams */
 static const bool g_serial = getenv("PC_SERIAL_SEGMENTS") != nullptr;      /* experiments: keep every batch on one stream */
@@ -565,6 +567,13 @@ static int launch_selected(pc_stream *st, pc_ctx *c, const pc_job *h_jobs, const
     } else if (op == PC_OP_BORDERS) {
       // taller than the packed classes: row-chunked packed sweep; what does not fit 16-bit scores goes to the wavefront kernel
       pc_launch_borders_chunked(B, d_slow + i, d_slow_count + sg, ss, c->sm_count);
+      PcDevBatch S = B;
+      S.idx = d_slow + i; S.n_dev = d_slow_count + sg;
+      pc_launch_dp((int)op, S, ss, c->sm_count);
+    } else if (op == PC_OP_ALIGN && g_align_bp) {
+      // one job per thread, bit-parallel with a traceback from stored delta vectors (align_core.h); long ESTs, bytes outside
+      // the alphabet and jobs whose columns do not fit the thread's share of the pool go on to the wavefront kernel
+      pc_launch_align_bp(B, d_slow + i, d_slow_count + sg, ss, c->sm_count);
       PcDevBatch S = B;
       S.idx = d_slow + i; S.n_dev = d_slow_count + sg;
       pc_launch_dp((int)op, S, ss, c->sm_count);

@@ -149,6 +149,7 @@ __device__ __forceinline__ bool pc_is_n(uint8_t c) { return c == 'n' || c == 'N'
 
 void pc_launch_dp(int op, const PcDevBatch &B, cudaStream_t s, int sm_count);
 void pc_launch_myers(int op, int cls, const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count);
+void pc_launch_align_bp(const PcDevBatch &B, uint32_t *slow_list, uint32_t *slow_count, cudaStream_t s, int sm_count);
 void pc_order_jobs(const pc_job *d_jobs, int n, size_t arena_bytes, size_t genome_len, size_t var_bytes, int lcs_tpb, int lcs_max_s2,
                    uint16_t *d_keys, uint32_t *d_work, PcSegStat *d_seg, uint32_t *d_order, cudaStream_t s, int sm_count);
 void pc_collect_status(const int32_t *d_res, int n, int code, uint32_t *d_list, uint32_t *d_count, cudaStream_t s, int sm_count);

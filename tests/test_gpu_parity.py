@@ -190,6 +190,34 @@ def test_long_alignment_band_and_pool_growth(cu, port):
         assert var[j["out_off"]:j["out_off"] + r[2]].tobytes() == ops
 
 
+def test_align_bit_parallel_classes_vs_port(cu, port):
+    """compute_alignment through k_align_bp (one job per thread, traceback from stored delta vectors): EST rows around every
+    block boundary (63..65, 127..129, 319..321 = the hand-over to the wavefront kernel), empty strings, N / n wildcards and
+    lower case on both sides, a byte outside the alphabet (hand-over), a genome piece much longer than the EST (columns
+    beyond the thread's share of the pool: hand-over).  Score, length and every alignment column equal the oracle's."""
+    g = Gen(31337)
+    b, pairs = Batch(), []
+    lens = [0, 1, 2, 7, 19, 40, 63, 64, 65, 100, 127, 128, 129, 191, 192, 193, 255, 256, 257, 319, 320, 321, 400]
+    for it in range(1500):
+        n = lens[it % len(lens)] if it % 3 else g.rnd.randint(0, 90)
+        a = g.rs(n)
+        alpha = ("ACGT", "ACGTN", "ACGTacgtNn")[it % 3]
+        c = g.mutate(a, (0.0, 0.02, 0.08, 0.3)[it % 4], alpha=alpha) if it % 5 else g.rs(g.rnd.randint(0, 120))
+        if it % 11 == 0 and len(a) > 3:
+            a = a[:2] + b"n" + a[3:]
+        if it % 97 == 0 and len(c) > 1:
+            c = c[:1] + b"*" + c[2:]
+        if it % 131 == 0:
+            c = c + g.rs(3000)
+        pairs.append((a, c)); b.add(PC_OP.ALIGN, a, c)
+    res, var = cu.run(b)
+    _, jobs = b.arrays()
+    for (a, c), r, j in zip(pairs, res, jobs):
+        s, ops = port.align(a, c)
+        assert r[0] == 0 and r[1] == s and r[2] == len(ops), (len(a), len(c), r[:3], s, len(ops))
+        assert var[j["out_off"]:j["out_off"] + r[2]].tobytes() == ops, (len(a), len(c))
+
+
 def test_properties_at_scale(cu):
     """Beyond oracle reach (10^4-10^5 nt): score symmetry, ops consistency and identity."""
     g = Gen(5)

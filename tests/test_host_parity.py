@@ -100,6 +100,17 @@ def test_bit_parallel_core_matches_the_port(cpu_bin):
     assert p.stdout.startswith("ok 30000"), p.stdout
 
 
+def test_bit_parallel_alignment_core_matches_the_port(cpu_bin):
+    """pintron_b200/csrc/align_core.h (what every thread of k_align_bp runs: compute_alignment with the N wildcard, traceback
+    from two stored words per column and block) compiled for the host: 40 000 random and mutated pairs, 0 to 5 blocks of EST
+    rows, empty strings, strided storage, unsupported bytes and missing space reported — score and every alignment column
+    against po_align."""
+    exe = os.path.join(os.path.dirname(cpu_bin), "align_fuzz")
+    p = subprocess.run([exe, "40000"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.startswith("ok 40000"), p.stdout
+
+
 def test_back_pressure_and_staging_growth_keep_the_bytes(cpu_bin, tmp_path):
     """The batcher never grows its staging while a batch is being gathered: ESTs whose requests do not fit wait for the next
     batch, and only a single EST larger than an empty batch makes the buffers grow.  With 1 KB of staging both happen
