@@ -2,7 +2,7 @@
  *
  * Replaces the sequential hot loop of the reference (src/main-est-fact.c:249-291): every EST runs the same
  * sequential per-EST code (compute_est_fact, src/compute-est-fact.c:192) on its own fiber; whenever that code needs
- * a DP it queues jobs and yields.  A worker thread owns two groups of fibers and one engine LANE per group
+ * a DP it queues jobs and yields.  A worker thread owns two groups of fibers (EF_GROUPS: up to four) and one engine LANE per group
  * (include/pintron_engine.h): while the jobs of group A are with the engine it runs the fibers of group B, then swaps.
  * The engine — inside this process or in the resident server est-factd — merges the lanes of all threads that are posted
  * at the same moment into one device batch; no worker thread calls CUDA.  ESTs are dealt to threads from a shared
