@@ -31,6 +31,12 @@ def test_single_thread_and_many_fibers_give_the_same_bytes(cpu_bin, tmp_path):
     U.check_case(cpu_bin, "test-AMBN", d2, "--quiet", "--threads", "3", "--fibers", "7")
 
 
+@pytest.mark.parametrize("groups", ["3", "4"])
+def test_more_fiber_groups_per_worker_give_the_same_bytes(cpu_bin, groups, tmp_path):
+    """EF_GROUPS: a worker thread may own up to four fiber groups (= engine lanes) instead of two."""
+    U.check_case(cpu_bin, "test-AMBN", tmp_path, "--quiet", "--threads", "3", "--fibers", "5", env=dict(os.environ, EF_GROUPS=groups))
+
+
 def test_cli_contract(cpu_bin, tmp_path):
     """Option names / defaults of src/options.ggo, config-dump.ini, precedence CLI > config.ini."""
     U.unpack("test-mattia3", str(tmp_path))
