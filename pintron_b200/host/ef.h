@@ -55,7 +55,7 @@ void ar_reset(ef_arena *a);                        /* keeps the first chunk */
 void ar_free_all(ef_arena *a);
 
 /* growable byte buffer (output text) */
-typedef struct ef_buf { char *p; size_t len, cap; } ef_buf;
+typedef struct ef_buf { char *p; size_t len, cap; bool ext; } ef_buf;      /* ext: p is a slice of storage somebody else owns (never realloc / free it) */
 void buf_printf(ef_buf *b, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 void buf_write(ef_buf *b, const void *src, size_t n);
 void buf_ints(ef_buf *b, const char *open, const int *v, int n, char sep, const char *close);

@@ -19,6 +19,7 @@ typedef struct est_item {
   ef_seq fwd, rc;
   bool has_rc;
   ef_buf out[6];                  /* raw, processed-ests, megs, processed-megs, meg-edges, processed-megs-info */
+  char *out_block;                /* the six buffers start as slices of this one allocation (est_task_body) */
   _Atomic uint32_t done;          /* set by the worker when every buffer above is final (futex word) */
   _Atomic uint32_t waited;        /* a writer sleeps on `done` */
   _Atomic int written;            /* writers that are through with this item (the last one frees its strings) */
@@ -168,7 +169,19 @@ static void est_task(ef_task *T, size_t handle, void *user) {
   if (atomic_load(&it->waited)) word_wake(&it->done);
 }
 
+/* One EST's records are 0.6-1.2 KB per file.  Six buffers of their own were six mallocs by the worker and six frees by six
+ * different writer threads (each one into the worker's malloc arena: its lock, its cache lines); now they are slices of ONE
+ * block that the last writer frees, and only a record that outgrows its slice gets storage of its own (buf_reserve). */
+static const uint16_t OUT_SLICE[O_COUNT] = {2048, 1024, 1536, 1536, 1024, 64};
+#define OUT_BLOCK (2048 + 1024 + 1536 + 1536 + 1024 + 64)
+
 static void est_task_body(ef_task *T, run_ctx *R, est_item *it) {
+  it->out_block = malloc(OUT_BLOCK);
+  if (!it->out_block) { fprintf(stderr, "* FATAL est-fact: out of memory\n"); exit(1); }
+  for (size_t k = 0, at = 0; k < O_COUNT; at += OUT_SLICE[k], ++k) {
+    it->out[k].p = it->out_block + at; it->out[k].len = 0; it->out[k].cap = OUT_SLICE[k]; it->out[k].ext = true;
+    it->out[k].p[0] = 0;
+  }
   /* EST preparation (main-est-fact.c:190-213) */
   ef_set_gb(&it->fwd);
   ef_set_strand_and_rc(&it->fwd);
@@ -255,6 +268,7 @@ static void *reader_main(void *arg) {
 
 /* ---- writers: one per output file, each streams the records of its file in INPUT order while the workers run ----- */
 static void item_release(est_item *it) {
+  free(it->out_block);
   free(it->fwd.id); free(it->fwd.gb); free(it->fwd.seq); free(it->fwd.orig);
   if (it->has_rc) { free(it->rc.id); free(it->rc.gb); free(it->rc.seq); free(it->rc.orig); }
 }

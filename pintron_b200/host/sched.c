@@ -121,7 +121,11 @@ static void buf_reserve(ef_buf *b, size_t extra) {
   if (b->len + extra + 1 <= b->cap) return;
   size_t cap = b->cap ? b->cap * 2 : 2048;      /* one EST's records are a few KB per file: start there, not at 256 bytes */
   while (cap < b->len + extra + 1) cap *= 2;
-  b->p = realloc(b->p, cap);
+  if (b->ext) {                                 /* outgrew its slice of the EST's output block: move to storage of its own */
+    char *q = malloc(cap);
+    if (q && b->len) memcpy(q, b->p, b->len + 1);
+    b->p = q; b->ext = false;
+  } else b->p = realloc(b->p, cap);
   if (!b->p) { fprintf(stderr, "* FATAL est-fact: out of memory\n"); exit(1); }
   b->cap = cap;
 }
@@ -165,7 +169,7 @@ void buf_ints(ef_buf *b, const char *open, const int *v, int n, char sep, const 
   b->len = (size_t)(p - b->p);
 }
 
-void buf_free(ef_buf *b) { free(b->p); b->p = NULL; b->len = b->cap = 0; }
+void buf_free(ef_buf *b) { if (!b->ext) free(b->p); b->p = NULL; b->len = b->cap = 0; b->ext = false; }
 
 /* ---- fibers ---------------------------------------------------------------------------------------- */
 enum { F_FREE = 0, F_RUNNABLE, F_WAITING, F_DONE, F_JOINING };      /* JOINING: waits for the child fibers of dp_parallel_for */
