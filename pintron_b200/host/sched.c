@@ -509,6 +509,22 @@ ef_aln aln_from_ops(ef_task *T, const uint8_t *ops, int n, const char *est, cons
 
 /* ---- batching -------------------------------------------------------------------------------------------- */
 #define LANE_MAX_BYTES ((size_t)32 << 20)
+/* The strings of a DP request are mostly 10-100 bytes; two libc memcpy calls per job, 350 per EST, cost their call and size
+ * dispatch more than the copy.  Sizes up to 64 go through overlapping fixed-size moves (never a byte outside [src, src+n)). */
+static inline void copy_small(uint8_t *dst, const char *src, size_t n) {
+  if (n > 64) { memcpy(dst, src, n); return; }
+  if (n >= 16) {
+    typedef struct { uint64_t a, b; } __attribute__((packed, may_alias)) v16;
+    if (n > 32) { *(v16 *)(dst + 16) = *(const v16 *)(src + 16); *(v16 *)(dst + n - 32) = *(const v16 *)(src + n - 32); }
+    *(v16 *)dst = *(const v16 *)src;
+    *(v16 *)(dst + n - 16) = *(const v16 *)(src + n - 16);
+    return;
+  }
+  if (n >= 8) { uint64_t a, b; memcpy(&a, src, 8); memcpy(&b, src + n - 8, 8); memcpy(dst, &a, 8); memcpy(dst + n - 8, &b, 8); return; }
+  if (n >= 4) { uint32_t a, b; memcpy(&a, src, 4); memcpy(&b, src + n - 4, 4); memcpy(dst, &a, 4); memcpy(dst + n - 4, &b, 4); return; }
+  for (size_t i = 0; i < n; ++i) dst[i] = (uint8_t)src[i];
+}
+
 static void gather(group *g) {
   g->arena_len = 0; g->njobs = 0; g->var_len = 0;
   /* Reads with thousands of candidate alignments (mRNAs) fill a lane with a handful of fibers; batches of a handful of
@@ -553,7 +569,7 @@ static void gather(group *g) {
       memset(j, 0, sizeof *j);
       j->op = (uint32_t)r->op;
       j->a_off = (uint32_t)g->arena_len; j->a_len = (uint32_t)r->a.len;
-      if (r->a.len) memcpy(g->arena + g->arena_len, r->a.p, (size_t)r->a.len);
+      if (r->a.len) copy_small(g->arena + g->arena_len, r->a.p, (size_t)r->a.len);
       g->arena_len += (size_t)r->a.len;
       if (r->b.nul_after) j->flags |= PC_B_NUL_AFTER;
       if (r->op == PC_OP_KBAND) j->flags |= PC_KBAND_OK_ONLY;      /* clean_noisy_exons reads the boolean only, like the reference's call sites */
@@ -562,7 +578,7 @@ static void gather(group *g) {
         j->b_off = (uint32_t)g->arena_len; j->b_len = (uint32_t)r->b.len;
         /* BORDERS reads the byte that follows t (refine.c:362-374); callers keep it addressable unless nul_after */
         const size_t nb = (size_t)r->b.len + ((r->op == PC_OP_BORDERS && !r->b.nul_after) ? 1u : 0u);
-        if (nb) memcpy(g->arena + g->arena_len, r->b.p, nb);
+        if (nb) copy_small(g->arena + g->arena_len, r->b.p, nb);
         g->arena_len += nb;
       }
       j->p0 = r->p0; j->p1 = r->p1; j->p2 = r->p2;
